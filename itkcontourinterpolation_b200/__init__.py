@@ -1,0 +1,7 @@
+"""B200-native slice-pair interpolation path of itk::MorphologicalContourInterpolator.
+
+Importing the package does not load the CUDA library; constructing a filter does, and fails loudly
+without a GPU (there is no CPU fallback).
+"""
+from .filter import MorphologicalContourInterpolator, morphological_contour_interpolator  # noqa: F401
+from .nrrd import read_nrrd  # noqa: F401

@@ -1,0 +1,929 @@
+// mci_cabi.cu -- context and phase-level C ABI (layer 1 of include/mci_b200.h).
+// Host code here only marshals descriptors, sizes device arenas and launches kernels; every
+// pixel of the hot path is touched on the device.  There is no CPU fallback.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "mci_launch.h"
+
+using namespace mci;
+
+namespace
+{
+
+struct DBuf
+{
+  void * p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes)
+  {
+    if (bytes <= cap)
+      return cudaSuccess;
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess)
+      cap = want;
+    return e;
+  }
+  void release()
+  {
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct HBuf
+{
+  void * p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes)
+  {
+    if (bytes <= cap)
+      return cudaSuccess;
+    if (p)
+      cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess)
+      cap = want;
+    return e;
+  }
+  void release()
+  {
+    if (p)
+      cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// host blob -> one H2D copy -> typed device pointers
+struct Blob
+{
+  std::vector<uint8_t> bytes;
+  template <typename T>
+  size_t add(const std::vector<T> & v)
+  {
+    size_t off = (bytes.size() + 255) & ~size_t(255);
+    bytes.resize(off + std::max<size_t>(v.size() * sizeof(T), 1));
+    if (!v.empty())
+      std::memcpy(bytes.data() + off, v.data(), v.size() * sizeof(T));
+    return off;
+  }
+  size_t reserve(size_t n)
+  {
+    size_t off = (bytes.size() + 255) & ~size_t(255);
+    bytes.resize(off + std::max<size_t>(n, 1));
+    return off;
+  }
+};
+
+} // namespace
+
+struct mci_ctx
+{
+  int device = 0;
+  Launch L{};
+  std::string err;
+  // volume
+  int ptype = -1;
+  long long dims[3] = { 0, 0, 0 };
+  size_t nvox = 0;
+  void * dIn = nullptr;
+  void * dOut = nullptr;
+  DBuf ownIn, ownOut;
+  // detection
+  DBuf dBBox, dSliceBits, dLabels, dLabeledSlices, dCounters;
+  HBuf hStage;
+  int nLabels = 0, nLabeledSlices = 0;
+  bool detected = false;
+  // slices / components
+  std::vector<mci_slice_desc> slices;
+  std::vector<SliceDev> sliceDev;
+  std::vector<int> ncomp, compBase;
+  int totalComp = 0;
+  bool statsOnHost = false;
+  std::vector<CompStat> hStats;
+  DBuf dSliceBlob, dParent, dRootId, dConn, dRowCount, dNcomp, dCompBase, dTotal, dStats;
+  SliceDev * dSlices = nullptr;
+  int statCap = 0;
+  // pairs
+  DBuf dSegBlob, dPairTable, dPairs;
+  int nPairs = 0, capPairs = 0;
+  // interpolation
+  DBuf dJobBlob, dArena, dScratch, dBigHist, dSlab, dNodes, dLevelCounts, dArenaTop, dTrans;
+  int bigHistGrid = 0;
+  int nJobs = 0;
+  // error flag
+  int * dErr = nullptr;
+};
+
+#define CK(call)                                                                                                               \
+  do                                                                                                                           \
+  {                                                                                                                            \
+    cudaError_t e_ = (call);                                                                                                   \
+    if (e_ != cudaSuccess)                                                                                                     \
+    {                                                                                                                          \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                                           \
+      return MCI_ERR_CUDA;                                                                                                     \
+    }                                                                                                                          \
+  } while (0)
+
+static int
+fail(mci_ctx * ctx, int code, const std::string & msg)
+{
+  ctx->err = msg;
+  return code;
+}
+
+static int
+check_device_error(mci_ctx * ctx)
+{
+  int h = 0;
+  CK(cudaMemcpyAsync(&h, ctx->dErr, sizeof(int), cudaMemcpyDeviceToHost, ctx->L.stream));
+  CK(cudaStreamSynchronize(ctx->L.stream));
+  if (ctx->L.failedKernel)
+  {
+    ctx->err = std::string("launch of ") + ctx->L.failedKernel + " failed: " + cudaGetErrorString(ctx->L.failedCode);
+    ctx->L.failedKernel = nullptr;
+    return MCI_ERR_CUDA;
+  }
+  CK(cudaGetLastError());
+  if (h == ERR_NONE)
+    return MCI_OK;
+  static const char * names[] = { "ok",
+                                  "mask arena overflow",
+                                  "node list overflow",
+                                  "pair table overflow",
+                                  "component table overflow",
+                                  "component count or distance bin does not fit the pixel type",
+                                  "alignment queue overflow",
+                                  "node scratch too small",
+                                  "1-to-N split cannot reach every mask pixel" };
+  int z = 0;
+  cudaMemcpyAsync(ctx->dErr, &z, sizeof(int), cudaMemcpyHostToDevice, ctx->L.stream);
+  cudaStreamSynchronize(ctx->L.stream);
+  ctx->err = std::string("device: ") + (h >= 0 && h <= 8 ? names[h] : "unknown");
+  return h == ERR_PIXELTYPE ? MCI_ERR_PIXELTYPE : MCI_ERR_CAPACITY;
+}
+
+extern "C"
+{
+
+  int mci_create(mci_ctx ** out, int device)
+  {
+    if (!out)
+      return MCI_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n)
+      return MCI_ERR_NO_DEVICE; // no CPU fallback: the path needs a CUDA device
+    mci_ctx * ctx = new mci_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->L.stream, cudaStreamNonBlocking) != cudaSuccess)
+    {
+      delete ctx;
+      return MCI_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    ctx->L.sms = prop.multiProcessorCount;
+    ctx->L.maxSmem = (int)prop.sharedMemPerBlockOptin;
+    ctx->L.count = 0;
+    ctx->L.failedKernel = nullptr;
+    ctx->L.failedCode = cudaSuccess;
+    if (cudaMalloc((void **)&ctx->dErr, sizeof(int)) != cudaSuccess)
+    {
+      delete ctx;
+      return MCI_ERR_CUDA;
+    }
+    cudaMemset(ctx->dErr, 0, sizeof(int));
+    *out = ctx;
+    return MCI_OK;
+  }
+
+  void mci_destroy(mci_ctx * ctx)
+  {
+    if (!ctx)
+      return;
+    mci_filter_forget(ctx);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->L.stream);
+    DBuf * bufs[] = { &ctx->ownIn,     &ctx->ownOut,   &ctx->dBBox,     &ctx->dSliceBits, &ctx->dLabels,  &ctx->dLabeledSlices,
+                      &ctx->dCounters, &ctx->dSliceBlob, &ctx->dParent, &ctx->dRootId,    &ctx->dConn,    &ctx->dRowCount,
+                      &ctx->dNcomp,    &ctx->dCompBase, &ctx->dTotal,   &ctx->dStats,     &ctx->dSegBlob, &ctx->dPairTable,
+                      &ctx->dPairs,    &ctx->dJobBlob,  &ctx->dArena,   &ctx->dScratch,   &ctx->dBigHist, &ctx->dSlab,
+                      &ctx->dNodes,    &ctx->dLevelCounts, &ctx->dArenaTop, &ctx->dTrans };
+    for (DBuf * b : bufs)
+      b->release();
+    ctx->hStage.release();
+    cudaFree(ctx->dErr);
+    cudaStreamDestroy(ctx->L.stream);
+    delete ctx;
+  }
+
+  const char * mci_last_error(const mci_ctx * ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+  void * mci_host_alloc(size_t bytes)
+  {
+    void * p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess)
+      return nullptr;
+    return p;
+  }
+  void mci_host_free(void * p)
+  {
+    if (p)
+      cudaFreeHost(p);
+  }
+  int64_t mci_launch_count(const mci_ctx * ctx) { return ctx ? ctx->L.count : 0; }
+  void * mci_stream(const mci_ctx * ctx) { return ctx ? (void *)ctx->L.stream : nullptr; }
+  int mci_synchronize(mci_ctx * ctx)
+  {
+    if (!ctx)
+      return MCI_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    return check_device_error(ctx);
+  }
+
+  // ---- volume ---------------------------------------------------------------------------------
+  static int set_dims(mci_ctx * ctx, const int64_t dims[3], int ptype)
+  {
+    if (!dims || ptype < MCI_U8 || ptype > MCI_I16)
+      return fail(ctx, MCI_ERR_ARG, "bad dims / pixel type");
+    for (int a = 0; a < 3; ++a)
+      if (dims[a] < 1 || dims[a] > 8192)
+        return fail(ctx, MCI_ERR_ARG, "each volume dimension must be in [1, 8192]");
+    ctx->ptype = ptype;
+    for (int a = 0; a < 3; ++a)
+      ctx->dims[a] = dims[a];
+    ctx->nvox = size_t(dims[0]) * size_t(dims[1]) * size_t(dims[2]);
+    ctx->detected = false;
+    return MCI_OK;
+  }
+
+  int mci_upload_volume(mci_ctx * ctx, const void * host, const int64_t dims[3], int ptype)
+  {
+    if (!ctx || !host)
+      return MCI_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int rc = set_dims(ctx, dims, ptype);
+    if (rc)
+      return rc;
+    size_t bytes = ctx->nvox * (ptype == MCI_U8 ? 1 : 2);
+    CK(ctx->ownIn.ensure(bytes + 16));
+    CK(ctx->ownOut.ensure(bytes + 16));
+    ctx->dIn = ctx->ownIn.p;
+    ctx->dOut = ctx->ownOut.p;
+    CK(cudaMemcpyAsync(ctx->dIn, host, bytes, cudaMemcpyHostToDevice, ctx->L.stream));
+    return MCI_OK;
+  }
+
+  int mci_attach_device_volume(mci_ctx * ctx, const void * dev_in, void * dev_out, const int64_t dims[3], int ptype)
+  {
+    if (!ctx || !dev_in || !dev_out)
+      return MCI_ERR_ARG;
+    if ((reinterpret_cast<size_t>(dev_in) & 15) || (reinterpret_cast<size_t>(dev_out) & 15))
+      return fail(ctx, MCI_ERR_ARG, "device volumes must be 16-byte aligned");
+    int rc = set_dims(ctx, dims, ptype);
+    if (rc)
+      return rc;
+    ctx->dIn = const_cast<void *>(dev_in);
+    ctx->dOut = dev_out;
+    return MCI_OK;
+  }
+
+  int mci_download_volume(mci_ctx * ctx, void * host)
+  {
+    if (!ctx || !host || !ctx->dOut)
+      return MCI_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    size_t bytes = ctx->nvox * (ctx->ptype == MCI_U8 ? 1 : 2);
+    CK(cudaMemcpyAsync(host, ctx->dOut, bytes, cudaMemcpyDeviceToHost, ctx->L.stream));
+    return check_device_error(ctx);
+  }
+
+  void * mci_device_output(mci_ctx * ctx) { return ctx ? ctx->dOut : nullptr; }
+
+  int mci_volume_dims(const mci_ctx * ctx, int64_t dims[3], int * pixel_type)
+  {
+    if (!ctx || !dims || ctx->ptype < 0)
+      return MCI_ERR_STATE;
+    for (int a = 0; a < 3; ++a)
+      dims[a] = ctx->dims[a];
+    if (pixel_type)
+      *pixel_type = ctx->ptype;
+    return MCI_OK;
+  }
+
+  // ---- slice detection ------------------------------------------------------------------------
+  int mci_detect_slices(mci_ctx * ctx, int axis, int32_t * n_labels, int32_t * n_labeled_slices)
+  {
+    if (!ctx || !ctx->dIn || axis < -1 || axis > 2)
+      return MCI_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const int nl = ctx->ptype == MCI_U8 ? 256 : 65536;
+    int wpa[3];
+    for (int a = 0; a < 3; ++a)
+      wpa[a] = (int)((ctx->dims[a] + 31) / 32);
+    const int wo1 = wpa[0], wo2 = wpa[0] + wpa[1], wpl = wpa[0] + wpa[1] + wpa[2];
+    const int capSlices = 1 << 20;
+    CK(ctx->dBBox.ensure(size_t(6) * nl * sizeof(int)));
+    CK(ctx->dSliceBits.ensure(size_t(nl) * wpl * sizeof(uint32_t)));
+    CK(ctx->dLabels.ensure(size_t(nl) * sizeof(mci_label_info)));
+    CK(ctx->dLabeledSlices.ensure(size_t(capSlices) * sizeof(mci_labeled_slice)));
+    CK(ctx->dCounters.ensure(2 * sizeof(int)));
+    cudaStream_t s = ctx->L.stream;
+    CK(cudaMemsetAsync(ctx->dBBox.p, 0x7F, size_t(3) * nl * sizeof(int), s));
+    CK(cudaMemsetAsync((int *)ctx->dBBox.p + size_t(3) * nl, 0xFF, size_t(3) * nl * sizeof(int), s));
+    CK(cudaMemsetAsync(ctx->dSliceBits.p, 0, size_t(nl) * wpl * sizeof(uint32_t), s));
+    CK(cudaMemsetAsync(ctx->dCounters.p, 0, 2 * sizeof(int), s));
+    launch_detect(ctx->L, ctx->ptype, ctx->dIn, ctx->dOut, ctx->dims, axis, (int *)ctx->dBBox.p, nl, (uint32_t *)ctx->dSliceBits.p,
+                  wpl, wo1, wo2);
+    launch_compact_labels(ctx->L, (int *)ctx->dBBox.p, nl, (uint32_t *)ctx->dSliceBits.p, wpl, wo1, wo2, ctx->ptype == MCI_I16,
+                          (mci_label_info *)ctx->dLabels.p, (mci_labeled_slice *)ctx->dLabeledSlices.p, capSlices,
+                          (int *)ctx->dCounters.p);
+    int h[2] = { 0, 0 };
+    CK(cudaMemcpyAsync(h, ctx->dCounters.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    if (h[1] > capSlices)
+      return fail(ctx, MCI_ERR_CAPACITY, "too many labelled slices");
+    ctx->nLabels = h[0];
+    ctx->nLabeledSlices = h[1];
+    ctx->detected = true;
+    if (n_labels)
+      *n_labels = h[0];
+    if (n_labeled_slices)
+      *n_labeled_slices = h[1];
+    return MCI_OK;
+  }
+
+  int mci_get_detection(mci_ctx * ctx, mci_label_info * labels, mci_labeled_slice * slices)
+  {
+    if (!ctx || !ctx->detected)
+      return MCI_ERR_STATE;
+    CK(cudaSetDevice(ctx->device));
+    if (labels && ctx->nLabels)
+      CK(cudaMemcpyAsync(labels, ctx->dLabels.p, size_t(ctx->nLabels) * sizeof(mci_label_info), cudaMemcpyDeviceToHost,
+                         ctx->L.stream));
+    if (slices && ctx->nLabeledSlices)
+      CK(cudaMemcpyAsync(slices, ctx->dLabeledSlices.p, size_t(ctx->nLabeledSlices) * sizeof(mci_labeled_slice),
+                         cudaMemcpyDeviceToHost, ctx->L.stream));
+    CK(cudaStreamSynchronize(ctx->L.stream));
+    return MCI_OK;
+  }
+
+  // ---- connected components ---------------------------------------------------------------------
+  static void make_tiles(const std::vector<int> & widths, const std::vector<int> & heights, std::vector<RowTile> & tiles)
+  {
+    tiles.clear();
+    for (size_t k = 0; k < widths.size(); ++k)
+    {
+      int rows = std::max(1, 8192 / std::max(1, widths[k]));
+      for (int r0 = 0; r0 < heights[k]; r0 += rows)
+      {
+        RowTile t;
+        t.item = (int)k;
+        t.row0 = r0;
+        t.nrows = std::min(rows, heights[k] - r0);
+        tiles.push_back(t);
+      }
+    }
+  }
+
+  int mci_label_slices(mci_ctx * ctx, int32_t n, const mci_slice_desc * descs, int fully, int32_t * n_components)
+  {
+    if (!ctx || !ctx->dIn || n < 0 || (n > 0 && !descs))
+      return MCI_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    ctx->slices.assign(descs, descs + n);
+    ctx->sliceDev.resize(n);
+    ctx->ncomp.assign(n, 0);
+    ctx->compBase.assign(n, 0);
+    ctx->totalComp = 0;
+    ctx->statsOnHost = false;
+    ctx->hStats.clear();
+    if (n == 0)
+      return MCI_OK;
+    const long long X = ctx->dims[0], Y = ctx->dims[1];
+    u64 pix = 0;
+    long long rows = 0;
+    std::vector<int> ws(n), hs(n);
+    u64 compBound = 0;
+    for (int k = 0; k < n; ++k)
+    {
+      const mci_slice_desc & d = descs[k];
+      if (d.axis < 0 || d.axis > 2 || d.w < 1 || d.h < 1 || d.u0 < 0 || d.v0 < 0 || d.slice < 0 || d.slice >= ctx->dims[d.axis])
+        return fail(ctx, MCI_ERR_ARG, "bad slice descriptor");
+      const int d0 = d.axis == 0 ? 1 : 0, d1 = d.axis == 2 ? 1 : 2;
+      if (d.u0 + d.w > ctx->dims[d0] || d.v0 + d.h > ctx->dims[d1])
+        return fail(ctx, MCI_ERR_ARG, "slice region outside the volume");
+      if ((u64)d.w * (u64)d.h >= 0xFFFFFFFFull)
+        return fail(ctx, MCI_ERR_ARG, "slice region too large");
+      SliceDev & S = ctx->sliceDev[k];
+      S.axis = d.axis;
+      S.slice = d.slice;
+      S.label = (int)d.label;
+      S.u0 = d.u0;
+      S.v0 = d.v0;
+      S.w = d.w;
+      S.h = d.h;
+      S.rowOff = (int)rows;
+      S.pixOff = pix;
+      if (d.axis == 2)
+      {
+        S.su = 1;
+        S.sv = X;
+        S.base = (u64)d.slice * X * Y + (u64)d.v0 * X + d.u0;
+      }
+      else if (d.axis == 1)
+      {
+        S.su = 1;
+        S.sv = X * Y;
+        S.base = (u64)d.slice * X + (u64)d.v0 * X * Y + d.u0;
+      }
+      else
+      {
+        S.su = X;
+        S.sv = X * Y;
+        S.base = (u64)d.slice + (u64)d.u0 * X + (u64)d.v0 * X * Y;
+      }
+      pix += (u64)d.w * d.h;
+      rows += d.h;
+      ws[k] = d.w;
+      hs[k] = d.h;
+      compBound += ((u64)d.w * d.h + 1) / 2;
+    }
+    std::vector<RowTile> tiles;
+    make_tiles(ws, hs, tiles);
+    Blob blob;
+    size_t oS = blob.add(ctx->sliceDev), oT = blob.add(tiles);
+    CK(ctx->dSliceBlob.ensure(blob.bytes.size()));
+    CK(ctx->hStage.ensure(blob.bytes.size()));
+    std::memcpy(ctx->hStage.p, blob.bytes.data(), blob.bytes.size());
+    cudaStream_t s = ctx->L.stream;
+    CK(cudaMemcpyAsync(ctx->dSliceBlob.p, ctx->hStage.p, blob.bytes.size(), cudaMemcpyHostToDevice, s));
+    ctx->dSlices = (SliceDev *)((uint8_t *)ctx->dSliceBlob.p + oS);
+    RowTile * dTiles = (RowTile *)((uint8_t *)ctx->dSliceBlob.p + oT);
+    ctx->statCap = (int)std::min<u64>(compBound, 2u << 20);
+    CK(ctx->dParent.ensure(pix * 4));
+    CK(ctx->dRootId.ensure(pix * 4));
+    CK(ctx->dConn.ensure(pix * 2));
+    CK(ctx->dRowCount.ensure(size_t(rows) * 4));
+    CK(ctx->dNcomp.ensure(size_t(n) * 4));
+    CK(ctx->dCompBase.ensure(size_t(n) * 4));
+    CK(ctx->dTotal.ensure(4));
+    CK(ctx->dStats.ensure(size_t(ctx->statCap) * sizeof(CompStat)));
+    CK(cudaMemsetAsync(ctx->dRowCount.p, 0, size_t(rows) * 4, s));
+    launch_cc(ctx->L, ctx->ptype, ctx->dIn, ctx->dSlices, n, dTiles, (int)tiles.size(), (uint32_t *)ctx->dParent.p,
+              (uint32_t *)ctx->dRootId.p, (uint16_t *)ctx->dConn.p, (int *)ctx->dRowCount.p, (int *)ctx->dNcomp.p,
+              (int *)ctx->dCompBase.p, (int *)ctx->dTotal.p, (CompStat *)ctx->dStats.p, ctx->statCap, fully, ctx->dErr);
+    CK(cudaMemcpyAsync(ctx->ncomp.data(), ctx->dNcomp.p, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
+    int rc = check_device_error(ctx);
+    if (rc)
+      return rc;
+    int acc = 0;
+    for (int k = 0; k < n; ++k)
+    {
+      ctx->compBase[k] = acc;
+      acc += ctx->ncomp[k];
+    }
+    ctx->totalComp = acc;
+    if (n_components)
+      std::memcpy(n_components, ctx->ncomp.data(), size_t(n) * 4);
+    return MCI_OK;
+  }
+
+  static int fetch_stats(mci_ctx * ctx)
+  {
+    if (ctx->statsOnHost)
+      return MCI_OK;
+    ctx->hStats.resize(ctx->totalComp);
+    if (ctx->totalComp)
+    {
+      CK(cudaMemcpyAsync(ctx->hStats.data(), ctx->dStats.p, size_t(ctx->totalComp) * sizeof(CompStat), cudaMemcpyDeviceToHost,
+                         ctx->L.stream));
+      CK(cudaStreamSynchronize(ctx->L.stream));
+    }
+    ctx->statsOnHost = true;
+    return MCI_OK;
+  }
+
+  int mci_get_components(mci_ctx * ctx, mci_component_info * out)
+  {
+    if (!ctx || !out)
+      return MCI_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int rc = fetch_stats(ctx);
+    if (rc)
+      return rc;
+    for (int k = 0; k < ctx->totalComp; ++k)
+    {
+      const CompStat & s = ctx->hStats[k];
+      out[k].count = s.count;
+      out[k].sum_u = s.sumU;
+      out[k].sum_v = s.sumV;
+      out[k].min_u = s.minU;
+      out[k].min_v = s.minV;
+      out[k].max_u = s.maxU;
+      out[k].max_v = s.maxV;
+    }
+    return MCI_OK;
+  }
+
+  int mci_get_component_image(mci_ctx * ctx, int32_t k, uint16_t * ids)
+  {
+    if (!ctx || !ids || k < 0 || k >= (int)ctx->slices.size())
+      return MCI_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const SliceDev & S = ctx->sliceDev[k];
+    CK(cudaMemcpyAsync(ids, (uint16_t *)ctx->dConn.p + S.pixOff, size_t(S.w) * S.h * 2, cudaMemcpyDeviceToHost, ctx->L.stream));
+    CK(cudaStreamSynchronize(ctx->L.stream));
+    return MCI_OK;
+  }
+
+  // ---- component matching ---------------------------------------------------------------------
+  int mci_match_pairs(mci_ctx * ctx, int32_t nseg, const mci_segment_desc * segs, int32_t * n_pairs)
+  {
+    if (!ctx || nseg < 0 || (nseg > 0 && !segs))
+      return MCI_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    ctx->nPairs = 0;
+    if (n_pairs)
+      *n_pairs = 0;
+    if (nseg == 0)
+      return MCI_OK;
+    std::vector<SegDev> sd(nseg);
+    std::vector<int> ws(nseg), hs(nseg);
+    u64 bound = 0;
+    for (int k = 0; k < nseg; ++k)
+    {
+      int a = segs[k].slice_i, b = segs[k].slice_j;
+      if (a < 0 || b < 0 || a >= (int)ctx->slices.size() || b >= (int)ctx->slices.size())
+        return fail(ctx, MCI_ERR_ARG, "segment refers to an unknown slice");
+      const SliceDev &A = ctx->sliceDev[a], &B = ctx->sliceDev[b];
+      if (A.w != B.w || A.h != B.h || A.u0 != B.u0 || A.v0 != B.v0)
+        return fail(ctx, MCI_ERR_ARG, "the two slices of a segment must share one region");
+      sd[k].si = a;
+      sd[k].sj = b;
+      ws[k] = A.w;
+      hs[k] = A.h;
+      bound += std::min<u64>((u64)(ctx->ncomp[a] + 1) * (u64)(ctx->ncomp[b] + 1), (u64)A.w * A.h);
+    }
+    std::vector<RowTile> tiles;
+    make_tiles(ws, hs, tiles);
+    Blob blob;
+    size_t oS = blob.add(sd), oT = blob.add(tiles);
+    CK(ctx->dSegBlob.ensure(blob.bytes.size()));
+    CK(ctx->hStage.ensure(blob.bytes.size()));
+    std::memcpy(ctx->hStage.p, blob.bytes.data(), blob.bytes.size());
+    cudaStream_t s = ctx->L.stream;
+    CK(cudaMemcpyAsync(ctx->dSegBlob.p, ctx->hStage.p, blob.bytes.size(), cudaMemcpyHostToDevice, s));
+    u64 tsize = 1 << 14;
+    while (tsize < 4 * bound && tsize < (1ull << 27))
+      tsize <<= 1;
+    ctx->capPairs = (int)std::min<u64>(bound + 16, tsize / 2);
+    CK(ctx->dPairTable.ensure(tsize * 8));
+    CK(ctx->dPairs.ensure(size_t(ctx->capPairs) * sizeof(mci_pair)));
+    CK(ctx->dCounters.ensure(2 * sizeof(int)));
+    CK(cudaMemsetAsync(ctx->dPairTable.p, 0xFF, tsize * 8, s));
+    CK(cudaMemsetAsync(ctx->dCounters.p, 0, sizeof(int), s));
+    launch_pairs(ctx->L, ctx->dSlices, (SegDev *)((uint8_t *)ctx->dSegBlob.p + oS), (RowTile *)((uint8_t *)ctx->dSegBlob.p + oT),
+                 (int)tiles.size(), (uint16_t *)ctx->dConn.p, (u64 *)ctx->dPairTable.p, (uint32_t)(tsize - 1),
+                 (mci_pair *)ctx->dPairs.p, ctx->capPairs, (int *)ctx->dCounters.p, ctx->dErr);
+    int h = 0;
+    CK(cudaMemcpyAsync(&h, ctx->dCounters.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    int rc = check_device_error(ctx);
+    if (rc)
+      return rc;
+    ctx->nPairs = h;
+    if (n_pairs)
+      *n_pairs = h;
+    return MCI_OK;
+  }
+
+  int mci_get_pairs(mci_ctx * ctx, mci_pair * pairs)
+  {
+    if (!ctx || (!pairs && ctx->nPairs))
+      return MCI_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->nPairs)
+    {
+      CK(cudaMemcpyAsync(pairs, ctx->dPairs.p, size_t(ctx->nPairs) * sizeof(mci_pair), cudaMemcpyDeviceToHost, ctx->L.stream));
+      CK(cudaStreamSynchronize(ctx->L.stream));
+    }
+    return MCI_OK;
+  }
+
+  // ---- interpolation --------------------------------------------------------------------------
+  static int depth_of_gap(int g)
+  {
+    int d = 1;
+    while (g > 2)
+    {
+      g = (g + 1) / 2;
+      if (g <= 1)
+        break;
+      ++d;
+    }
+    return d;
+  }
+
+  int mci_interpolate(mci_ctx * ctx, int32_t njobs, const mci_job * jobs, const int32_t * b_ids, int32_t n_b_ids,
+                      const mci_params * prm)
+  {
+    if (!ctx || !prm || njobs < 0 || (njobs > 0 && !jobs))
+      return MCI_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    ctx->nJobs = njobs;
+    if (njobs == 0)
+      return MCI_OK;
+    int rc = fetch_stats(ctx);
+    if (rc)
+      return rc;
+    const int nsl = (int)ctx->slices.size();
+    cudaStream_t s = ctx->L.stream;
+
+    std::vector<MaskRef> refs;
+    std::vector<ExtractJob> extracts;
+    std::vector<AlignJob> aligns(njobs);
+    std::vector<SplitJob> splits;
+    std::vector<RootJob> roots(njobs);
+    std::map<std::pair<int, int>, MaskRef> compMasks;
+    u64 arenaWords = 0, scratchWords = 0;
+    const int alignSmemCap = 160 * 1024;
+    int alignSmem = 0;
+    int nRootNodes = 0;
+    int maxDepth = 0;
+    std::vector<long long> levelCap;
+    u64 midWords = 0, maxNodeWords = 0;
+
+    auto statOf = [&](int slice, int id) -> const CompStat & { return ctx->hStats[ctx->compBase[slice] + id - 1]; };
+    auto compMask = [&](int slice, int id) -> MaskRef {
+      auto key = std::make_pair(slice, id);
+      auto it = compMasks.find(key);
+      if (it != compMasks.end())
+        return it->second;
+      const CompStat & c = statOf(slice, id);
+      MaskRef m;
+      m.x0 = c.minU;
+      m.y0 = c.minV;
+      m.w = c.maxU - c.minU + 1;
+      m.h = c.maxV - c.minV + 1;
+      m.pitch = (m.w + 31) >> 5;
+      m.pad = 0;
+      m.off = arenaWords;
+      arenaWords += (u64)m.h * m.pitch;
+      ExtractJob e;
+      e.slice = slice;
+      e.id = id;
+      e.m = m;
+      extracts.push_back(e);
+      compMasks[key] = m;
+      return m;
+    };
+
+    for (int k = 0; k < njobs; ++k)
+    {
+      const mci_job & jb = jobs[k];
+      if (jb.kind < 0 || jb.kind > 2 || jb.slice_a < 0 || jb.slice_a >= nsl || jb.a_id < 1 || jb.a_id > ctx->ncomp[jb.slice_a])
+        return fail(ctx, MCI_ERR_ARG, "bad job (a side)");
+      const SliceDev & SA = ctx->sliceDev[jb.slice_a];
+      const int gap = std::abs(jb.pos_a - jb.pos_b);
+      if (gap < 2)
+        return fail(ctx, MCI_ERR_ARG, "job between adjacent slices");
+      AlignJob & A = aligns[k];
+      RootJob & R = roots[k];
+      std::memset(&A, 0, sizeof(A));
+      std::memset(&R, 0, sizeof(R));
+      A.kind = R.kind = jb.kind;
+      R.job = k;
+      R.posA = jb.pos_a;
+      R.posB = jb.pos_b;
+      R.axis = SA.axis;
+      R.label = SA.label;
+      R.rootOff = nRootNodes;
+      const CompStat & ca = statOf(jb.slice_a, jb.a_id);
+      const long long acu = (long long)((unsigned long long)ca.sumU / (unsigned long long)ca.count);
+      const long long acv = (long long)((unsigned long long)ca.sumV / (unsigned long long)ca.count);
+      MaskRef ma = compMask(jb.slice_a, jb.a_id);
+      A.aRef = R.aRef = (int)refs.size();
+      refs.push_back(ma);
+      int rbU0, rbV0, rbW, rbH; // region of the "j" image handed to Align
+      long long wbSum = 0, hbMax = 0;
+      int nRootsHere = 1;
+      if (jb.kind == JOB_EXTRAPOLATE)
+      {
+        A.nB = 0;
+        A.indx = A.indy = 0; // both centroids coincide (X:216,240)
+        A.phx = R.phx = (int)acu;
+        A.phy = R.phy = (int)acv;
+        rbU0 = (int)acu - 1;
+        rbV0 = (int)acv - 1;
+        rbW = rbH = 3;
+        MaskRef ph;
+        ph.x0 = ph.y0 = 0;
+        ph.w = ph.h = 1;
+        ph.pitch = 1;
+        ph.pad = 0;
+        ph.off = arenaWords;
+        arenaWords += 1;
+        R.phRef = (int)refs.size();
+        refs.push_back(ph);
+        wbSum = 1;
+        hbMax = 1;
+      }
+      else
+      {
+        if (jb.slice_b < 0 || jb.slice_b >= nsl || jb.n_b < 1 || jb.b_ids_offset < 0 || jb.b_ids_offset + jb.n_b > n_b_ids ||
+            (jb.kind == JOB_ONE_TO_ONE && jb.n_b != 1))
+          return fail(ctx, MCI_ERR_ARG, "bad job (b side)");
+        const SliceDev & SB = ctx->sliceDev[jb.slice_b];
+        rbU0 = SB.u0;
+        rbV0 = SB.v0;
+        rbW = SB.w;
+        rbH = SB.h;
+        A.nB = R.nB = jb.n_b;
+        A.bRef = R.bRef = (int)refs.size();
+        unsigned long long su = 0, sv = 0, cnt = 0;
+        for (int q = 0; q < jb.n_b; ++q)
+        {
+          int id = b_ids[jb.b_ids_offset + q];
+          if (id < 1 || id > ctx->ncomp[jb.slice_b])
+            return fail(ctx, MCI_ERR_ARG, "bad job (b id)");
+          const CompStat & cb = statOf(jb.slice_b, id);
+          su += (unsigned long long)cb.sumU;
+          sv += (unsigned long long)cb.sumV;
+          cnt += (unsigned long long)cb.count;
+          MaskRef mb = compMask(jb.slice_b, id);
+          refs.push_back(mb);
+          wbSum = std::max<long long>(wbSum, mb.w);
+          hbMax = std::max<long long>(hbMax, mb.h);
+        }
+        A.indx = (int)((long long)(su / cnt) - acu); // X:1147-1154
+        A.indy = (int)((long long)(sv / cnt) - acv);
+        if (jb.kind == JOB_ONE_TO_N)
+        {
+          SplitJob sp;
+          sp.job = k;
+          sp.aRef = A.aRef;
+          sp.nB = jb.n_b;
+          sp.bRef = A.bRef;
+          sp.outRef = (int)refs.size();
+          sp.pad = 0;
+          sp.scratchOff = scratchWords;
+          scratchWords += (u64)jb.n_b * ma.h * ma.pitch;
+          R.splitRef = sp.outRef;
+          for (int q = 0; q < jb.n_b; ++q)
+          {
+            MaskRef mo = ma;
+            mo.off = arenaWords;
+            arenaWords += (u64)ma.h * ma.pitch;
+            refs.push_back(mo);
+          }
+          splits.push_back(sp);
+          nRootsHere = jb.n_b;
+        }
+      }
+      // search region of translations (X:1156-1164)
+      A.sx0 = rbU0 - SA.u0 - SA.w + 1;
+      A.sy0 = rbV0 - SA.v0 - SA.h + 1;
+      A.sw = SA.w + rbW - 1;
+      A.sh = SA.h + rbH - 1;
+      const unsigned long long nS = (unsigned long long)A.sw * (unsigned long long)A.sh;
+      A.minIter = (long long)std::min<unsigned long long>((unsigned long long)prm->min_align_iters, nS);
+      A.maxIter = (long long)std::max<unsigned long long>((unsigned long long)prm->max_align_iters,
+                                                        (unsigned long long)std::sqrt((double)nS));
+      long long need = std::max<long long>(A.maxIter + 16, 8ll * (A.sw + A.sh)) + 64;
+      int qcap = 64;
+      while (qcap < need)
+        qcap <<= 1;
+      A.qcap = qcap;
+      const u64 bwords = (u64)((A.sw + 31) >> 5) * (u64)A.sh;
+      const u64 smemNeed = (bwords + 3ull * qcap) * 4;
+      if (smemNeed <= (u64)alignSmemCap)
+      {
+        A.useSmem = 1;
+        alignSmem = std::max(alignSmem, (int)smemNeed);
+      }
+      else
+      {
+        A.useSmem = 0;
+        A.bitmapOff = scratchWords;
+        scratchWords += bwords;
+        A.queueOff = scratchWords;
+        scratchWords += 3ull * qcap;
+      }
+      // node bookkeeping
+      nRootNodes += nRootsHere;
+      int depth = depth_of_gap(gap);
+      maxDepth = std::max(maxDepth, depth);
+      if ((int)levelCap.size() < depth)
+        levelCap.resize(depth, 0);
+      for (int d = 0; d < depth; ++d)
+        levelCap[d] += (long long)nRootsHere * std::min<long long>(1ll << std::min(d, 30), gap - 1);
+      const int d0 = SA.axis == 0 ? 1 : 0, d1 = SA.axis == 2 ? 1 : 2;
+      long long bw = std::min<long long>(ctx->dims[d0], 2 * (ma.w + wbSum));
+      long long bh = std::min<long long>(ctx->dims[d1], 2 * (ma.h + hbMax));
+      u64 nodeWords = (u64)((bw + 31) / 32 + 1) * (u64)bh;
+      maxNodeWords = std::max(maxNodeWords, nodeWords);
+      midWords += (u64)nRootsHere * (u64)(gap - 1) * nodeWords;
+    }
+
+    // ---- device memory
+    const u64 arenaCap = arenaWords + midWords + 64;
+    Blob blob;
+    const size_t oRefs = blob.add(refs), oExtract = blob.add(extracts), oAlign = blob.add(aligns), oSplit = blob.add(splits),
+                 oRoots = blob.add(roots);
+    CK(ctx->dJobBlob.ensure(blob.bytes.size()));
+    CK(ctx->hStage.ensure(blob.bytes.size()));
+    std::memcpy(ctx->hStage.p, blob.bytes.data(), blob.bytes.size());
+    CK(cudaMemcpyAsync(ctx->dJobBlob.p, ctx->hStage.p, blob.bytes.size(), cudaMemcpyHostToDevice, s));
+    uint8_t * jb = (uint8_t *)ctx->dJobBlob.p;
+    MaskRef * dRefs = (MaskRef *)(jb + oRefs);
+    CK(ctx->dArena.ensure(arenaCap * 4));
+    CK(ctx->dScratch.ensure((scratchWords + 64) * 4));
+    CK(ctx->dTrans.ensure(size_t(njobs) * sizeof(int2)));
+    long long nodeTotal = 0;
+    for (long long c : levelCap)
+      nodeTotal += c;
+    CK(ctx->dNodes.ensure(size_t(nodeTotal + 1) * sizeof(Node)));
+    CK(ctx->dLevelCounts.ensure(size_t(maxDepth + 2) * sizeof(int)));
+    CK(ctx->dArenaTop.ensure(8));
+    const int nodeSmem = 100 * 1024;
+    const int nodeGrid = ctx->L.sms * 2;
+    if (ctx->bigHistGrid < nodeGrid)
+    {
+      CK(ctx->dBigHist.ensure(size_t(nodeGrid) * 2 * 65536 * 4));
+      CK(cudaMemsetAsync(ctx->dBigHist.p, 0, size_t(nodeGrid) * 2 * 65536 * 4, s));
+      ctx->bigHistGrid = nodeGrid;
+    }
+    const int nArr = prm->use_distance_transform ? 3 : 6;
+    const u64 smemWords = (u64)nodeSmem / 4 - 2 * 2048;
+    u64 slabWords = 0;
+    if (maxNodeWords * nArr > smemWords)
+    {
+      slabWords = maxNodeWords * nArr;
+      CK(ctx->dSlab.ensure(size_t(nodeGrid) * slabWords * 4));
+    }
+    // bitmaps of the global-scratch Align jobs must start cleared (the kernel clears them itself as well)
+    std::vector<int> lc(maxDepth + 2, 0);
+    lc[0] = nRootNodes;
+    CK(cudaMemcpyAsync(ctx->dLevelCounts.p, lc.data(), lc.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    unsigned long long top = arenaWords;
+    CK(cudaMemcpyAsync(ctx->dArenaTop.p, &top, 8, cudaMemcpyHostToDevice, s));
+
+    // ---- launches
+    launch_extract(ctx->L, ctx->dSlices, (ExtractJob *)(jb + oExtract), (int)extracts.size(), (uint16_t *)ctx->dConn.p,
+                   (uint32_t *)ctx->dArena.p);
+    launch_align(ctx->L, (AlignJob *)(jb + oAlign), njobs, dRefs, (uint32_t *)ctx->dArena.p, (uint32_t *)ctx->dScratch.p,
+                 prm->heuristic_alignment, (int2 *)ctx->dTrans.p, alignSmem, ctx->dErr);
+    launch_split(ctx->L, (SplitJob *)(jb + oSplit), (int)splits.size(), dRefs, (uint32_t *)ctx->dArena.p,
+                 (uint32_t *)ctx->dScratch.p, (int2 *)ctx->dTrans.p, prm->use_ball, ctx->dErr);
+    Node * dNodes = (Node *)ctx->dNodes.p;
+    launch_make_roots(ctx->L, (RootJob *)(jb + oRoots), njobs, dRefs, (uint32_t *)ctx->dArena.p, (int2 *)ctx->dTrans.p, dNodes);
+    long long off = 0;
+    int * dCounts = (int *)ctx->dLevelCounts.p;
+    for (int d = 0; d < maxDepth; ++d)
+    {
+      Node * cur = dNodes + off;
+      Node * nxt = dNodes + off + levelCap[d];
+      int nextCap = d + 1 < maxDepth ? (int)levelCap[d + 1] : 0;
+      launch_nodes(ctx->L, ctx->ptype, cur, dCounts + d, (int)levelCap[d], nxt, dCounts + d + 1, nextCap,
+                   (uint32_t *)ctx->dArena.p, (unsigned long long *)ctx->dArenaTop.p, arenaCap, ctx->dIn, ctx->dOut, ctx->dims,
+                   prm->use_distance_transform, prm->use_ball, (unsigned *)ctx->dBigHist.p, (uint32_t *)ctx->dSlab.p, slabWords,
+                   nodeGrid, nodeSmem, ctx->dErr);
+      off += levelCap[d];
+    }
+    CK(cudaGetLastError());
+    return MCI_OK;
+  }
+
+  int mci_get_translations(mci_ctx * ctx, int32_t * t)
+  {
+    if (!ctx || !t)
+      return MCI_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->nJobs)
+    {
+      CK(cudaMemcpyAsync(t, ctx->dTrans.p, size_t(ctx->nJobs) * 8, cudaMemcpyDeviceToHost, ctx->L.stream));
+      CK(cudaStreamSynchronize(ctx->L.stream));
+    }
+    return MCI_OK;
+  }
+
+} // extern "C"

@@ -1,0 +1,1788 @@
+// mci_kernels.cu -- kernels + launch wrappers (see mci_kernels.cuh for helpers).
+#include <algorithm>
+#include <type_traits>
+#include "mci_kernels.cuh"
+#include "mci_launch.h"
+#include "../../include/mci_b200.h"
+
+namespace mci
+{
+
+// ================================================================================================
+// K12  slice detection + output initialisation      (DetermineSliceOrientations, X:128-201;
+//      AllocateOutputs X:1541-1557 and the final overwrite X:1623-1636 folded into one pass)
+// ================================================================================================
+template <typename T>
+__device__ __forceinline__ void
+detect_voxel(const T * __restrict__ in, long long i, long long x, long long y, long long z, long long X, long long Y,
+             long long Z, T val, int axisSel, int * bbox, int nl, uint32_t * sliceBits, int wordsPerLabel, int wo1, int wo2)
+{
+  const long long XY = X * Y;
+  T nb[6];
+  nb[0] = x > 0 ? in[i - 1] : T(0);
+  nb[1] = x + 1 < X ? in[i + 1] : T(0);
+  nb[2] = y > 0 ? in[i - X] : T(0);
+  nb[3] = y + 1 < Y ? in[i + X] : T(0);
+  nb[4] = z > 0 ? in[i - XY] : T(0);
+  nb[5] = z + 1 < Z ? in[i + XY] : T(0);
+  int cTrue = 0, cAdj = 0, axis = 0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+  {
+    T p = nb[2 * a], n = nb[2 * a + 1];
+    if (p == 0 && n == 0)
+    {
+      axis = a;
+      ++cTrue;
+    }
+    else if (p == val && n == val)
+      ++cAdj;
+  }
+  const unsigned li = (unsigned)(typename std::make_unsigned<T>::type)val;
+  // per-label bounding box (X:148-159): test first, the table lives in L2 and rarely changes
+  int c[3] = { (int)x, (int)y, (int)z };
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+  {
+    int * mn = bbox + (size_t)a * nl + li;
+    int * mx = bbox + (size_t)(3 + a) * nl + li;
+    if (c[a] < __ldcg(mn))
+      atomicMin(mn, c[a]);
+    if (c[a] > __ldcg(mx))
+      atomicMax(mx, c[a]);
+  }
+  if (cTrue == 1 && cAdj == 2 && (axisSel == -1 || axisSel == axis))
+  {
+    int wo = axis == 0 ? 0 : (axis == 1 ? wo1 : wo2);
+    uint32_t * w = sliceBits + (size_t)li * wordsPerLabel + wo + (c[axis] >> 5);
+    uint32_t bit = 1u << (c[axis] & 31);
+    if (!(__ldcg(w) & bit))
+      atomicOr(w, bit);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_detect_copy(const T * __restrict__ in, T * __restrict__ out, long long X, long long Y,
+                                                     long long Z, int axisSel, int * bbox, int nl, uint32_t * sliceBits,
+                                                     int wordsPerLabel, int wo1, int wo2)
+{
+  constexpr int VEC = 16 / sizeof(T);
+  const long long n = X * Y * Z;
+  const long long nchunks = (n + VEC - 1) / VEC;
+  const long long XY = X * Y;
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < nchunks; c += (long long)gridDim.x * blockDim.x)
+  {
+    const long long i0 = c * VEC;
+    T v[VEC];
+    bool any = false;
+    if (i0 + VEC <= n)
+    {
+      uint4 q = __ldg(reinterpret_cast<const uint4 *>(in + i0));
+      if (out)
+        *reinterpret_cast<uint4 *>(out + i0) = q;
+      any = (q.x | q.y | q.z | q.w) != 0u;
+      *reinterpret_cast<uint4 *>(v) = q;
+    }
+    else
+    {
+      for (int e = 0; e < VEC; ++e)
+      {
+        v[e] = (i0 + e < n) ? in[i0 + e] : T(0);
+        if (out && i0 + e < n)
+          out[i0 + e] = v[e];
+        any |= v[e] != 0;
+      }
+    }
+    if (!any)
+      continue;
+    long long z = i0 / XY;
+    long long rem = i0 - z * XY;
+    long long y = rem / X;
+    long long x = rem - y * X;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e)
+    {
+      if (v[e] != 0)
+        detect_voxel<T>(in, i0 + e, x, y, z, X, Y, Z, v[e], axisSel, bbox, nl, sliceBits, wordsPerLabel, wo1, wo2);
+      if (++x == X)
+      {
+        x = 0;
+        if (++y == Y)
+        {
+          y = 0;
+          ++z;
+        }
+      }
+    }
+  }
+}
+
+// Compacts the per-label tables into lists the host scheduler reads back.
+__global__ void
+k_compact_labels(const int * __restrict__ bbox, int nl, const uint32_t * __restrict__ sliceBits, int wordsPerLabel, int wo1,
+                 int wo2, int signedLabels, mci_label_info * labels, mci_labeled_slice * slices, int capSlices, int * counters)
+{
+  int li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= nl)
+    return;
+  int mnx = bbox[li], mxx = bbox[(size_t)3 * nl + li];
+  if (mnx > mxx)
+    return;
+  long long label = signedLabels ? (long long)(short)li : (long long)li;
+  int slot = atomicAdd(&counters[0], 1);
+  mci_label_info L;
+  L.label = label;
+  for (int a = 0; a < 3; ++a)
+  {
+    int mn = bbox[(size_t)a * nl + li], mx = bbox[(size_t)(3 + a) * nl + li];
+    L.bbox_index[a] = mn;
+    L.bbox_size[a] = mx - mn + 1;
+  }
+  labels[slot] = L;
+  const uint32_t * w = sliceBits + (size_t)li * wordsPerLabel;
+  for (int k = 0; k < wordsPerLabel; ++k)
+  {
+    uint32_t bits = w[k];
+    if (!bits)
+      continue;
+    int axis = k >= wo2 ? 2 : (k >= wo1 ? 1 : 0);
+    int base = (k - (axis == 0 ? 0 : (axis == 1 ? wo1 : wo2))) * 32;
+    int pos = atomicAdd(&counters[1], __popc(bits));
+    while (bits)
+    {
+      int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      if (pos < capSlices)
+      {
+        mci_labeled_slice s;
+        s.axis = axis;
+        s.slice = base + b;
+        s.label = label;
+        slices[pos] = s;
+      }
+      ++pos;
+    }
+  }
+}
+
+void
+launch_detect(Launch & L, int ptype, const void * in, void * out, const long long dims[3], int axisSel, int * bbox, int nl,
+              uint32_t * sliceBits, int wordsPerLabel, int wo1, int wo2)
+{
+  const int elt = ptype == MCI_U8 ? 1 : 2;
+  long long n = dims[0] * dims[1] * dims[2];
+  long long nchunks = (n + (16 / elt) - 1) / (16 / elt);
+  long long want = (nchunks + 255) / 256;
+  int grid = (int)std::min<long long>(want, (long long)L.sms * 16);
+  if (grid < 1)
+    grid = 1;
+  switch (ptype)
+  {
+    case MCI_U8:
+      k_detect_copy<uint8_t><<<grid, 256, 0, L.stream>>>((const uint8_t *)in, (uint8_t *)out, dims[0], dims[1], dims[2], axisSel,
+                                                         bbox, nl, sliceBits, wordsPerLabel, wo1, wo2);
+      break;
+    case MCI_U16:
+      k_detect_copy<uint16_t><<<grid, 256, 0, L.stream>>>((const uint16_t *)in, (uint16_t *)out, dims[0], dims[1], dims[2],
+                                                          axisSel, bbox, nl, sliceBits, wordsPerLabel, wo1, wo2);
+      break;
+    default:
+      k_detect_copy<int16_t><<<grid, 256, 0, L.stream>>>((const int16_t *)in, (int16_t *)out, dims[0], dims[1], dims[2], axisSel,
+                                                         bbox, nl, sliceBits, wordsPerLabel, wo1, wo2);
+  }
+  L.post("k_detect_copy");
+}
+
+void
+launch_compact_labels(Launch & L, const int * bbox, int nl, const uint32_t * sliceBits, int wordsPerLabel, int wo1, int wo2,
+                      int signedLabels, mci_label_info * labels, mci_labeled_slice * slices, int capSlices, int * counters)
+{
+  k_compact_labels<<<(nl + 255) / 256, 256, 0, L.stream>>>(bbox, nl, sliceBits, wordsPerLabel, wo1, wo2, signedLabels, labels,
+                                                          slices, capSlices, counters);
+  L.post("k_compact_labels");
+}
+
+// ================================================================================================
+// K1/K2/K4  batched 2-D connected components on the annotated slices
+//           (RegionedConnectedComponents, X:1224-1238; numbering of ITK ConnectedComponentImageFilter:
+//            ids 1..n by raster position of each component's first pixel; Centroid sums X:1101-1134)
+// Union-find on pixels with the smaller index as parent, so every root is its component's
+// raster-first pixel; consecutive ids = rank of the root in raster order.
+// ================================================================================================
+__device__ __forceinline__ uint32_t
+uf_find(volatile uint32_t * parent, uint32_t p)
+{
+  uint32_t q;
+  while ((q = parent[p]) != p)
+    p = q;
+  return p;
+}
+__device__ __forceinline__ void
+uf_union(uint32_t * parent, uint32_t a, uint32_t b)
+{
+  for (;;)
+  {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b)
+      return;
+    if (a < b)
+    {
+      uint32_t t = a;
+      a = b;
+      b = t;
+    }
+    uint32_t old = atomicMin(&parent[a], b);
+    if (old == a)
+      return;
+    a = old;
+  }
+}
+
+// Warps walk (row, 32-pixel chunk) cells of a tile.
+#define MCI_TILE_LOOP(tile, S, cw)                                                                                            \
+  const RowTile tile = tiles[blockIdx.x];                                                                                     \
+  const SliceDev S = slices[tile.item];                                                                                       \
+  const int cw = (S.w + 31) >> 5;                                                                                             \
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;                                       \
+  for (int cell = warp; cell < tile.nrows * cw; cell += nwarps)
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_cc_init(const T * __restrict__ in, const SliceDev * __restrict__ slices, const RowTile * __restrict__ tiles, uint32_t * parentAll)
+{
+  MCI_TILE_LOOP(tile, S, cw)
+  {
+    const int y = tile.row0 + cell / cw;
+    const int x = (cell % cw) * 32 + lane;
+    bool fg = false;
+    if (x < S.w)
+      fg = in[S.base + (u64)((long long)x * S.su + (long long)y * S.sv)] == (T)S.label;
+    uint32_t bits = __ballot_sync(0xFFFFFFFFu, fg);
+    if (x < S.w)
+    {
+      uint32_t p = (uint32_t)y * (uint32_t)S.w + (uint32_t)x;
+      uint32_t v = MCI_NOLABEL;
+      if (fg)
+      {
+        uint32_t zeros = ~bits & ((1u << lane) - 1u);
+        int start = zeros ? 32 - __clz(zeros) : 0; // first pixel of this pixel's run inside the chunk
+        v = p - (uint32_t)(lane - start);
+      }
+      parentAll[S.pixOff + p] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_cc_merge(const SliceDev * __restrict__ slices, const RowTile * __restrict__ tiles, uint32_t * parentAll, int fully)
+{
+  MCI_TILE_LOOP(tile, S, cw)
+  {
+    const int y = tile.row0 + cell / cw;
+    const int x = (cell % cw) * 32 + lane;
+    if (x >= S.w)
+      continue;
+    uint32_t * parent = parentAll + S.pixOff;
+    const uint32_t p = (uint32_t)y * (uint32_t)S.w + (uint32_t)x;
+    if (parent[p] == MCI_NOLABEL)
+      continue;
+    const bool left = x > 0 && parent[p - 1] != MCI_NOLABEL;
+    if (left && lane == 0)
+      uf_union(parent, p, p - 1);
+    if (y > 0)
+    {
+      const uint32_t u = p - (uint32_t)S.w;
+      const bool up = parent[u] != MCI_NOLABEL;
+      const bool upleft = x > 0 && parent[u - 1] != MCI_NOLABEL;
+      if (up)
+      {
+        if (!(left && upleft)) // otherwise the left neighbour already links the two rows
+          uf_union(parent, p, u);
+      }
+      else if (fully)
+      {
+        if (upleft)
+          uf_union(parent, p, u - 1);
+        if (x + 1 < S.w && parent[u + 1] != MCI_NOLABEL)
+          uf_union(parent, p, u + 1);
+      }
+    }
+  }
+}
+
+// path compression + number of roots per row
+__global__ void __launch_bounds__(256)
+k_cc_flatten(const SliceDev * __restrict__ slices, const RowTile * __restrict__ tiles, uint32_t * parentAll, int * rowCount)
+{
+  MCI_TILE_LOOP(tile, S, cw)
+  {
+    const int y = tile.row0 + cell / cw;
+    const int x = (cell % cw) * 32 + lane;
+    bool root = false;
+    if (x < S.w)
+    {
+      uint32_t * parent = parentAll + S.pixOff;
+      const uint32_t p = (uint32_t)y * (uint32_t)S.w + (uint32_t)x;
+      if (parent[p] != MCI_NOLABEL)
+      {
+        uint32_t r = uf_find(parent, p);
+        root = r == p;
+        if (!root)
+          parent[p] = r;
+      }
+    }
+    uint32_t bits = __ballot_sync(0xFFFFFFFFu, root);
+    if (lane == 0 && bits)
+      atomicAdd(&rowCount[S.rowOff + y], __popc(bits));
+  }
+}
+
+// one CTA per slice: exclusive scan of the per-row root counts; total = component count
+__global__ void __launch_bounds__(256) k_cc_rowscan(const SliceDev * __restrict__ slices, int * rowCount, int * ncomp)
+{
+  const SliceDev S = slices[blockIdx.x];
+  __shared__ int wsum[8];
+  __shared__ int carry;
+  if (threadIdx.x == 0)
+    carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < S.h; base += 256)
+  {
+    int y = base + threadIdx.x;
+    int v = y < S.h ? rowCount[S.rowOff + y] : 0;
+    int s = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      int t = __shfl_up_sync(0xFFFFFFFFu, s, o);
+      if (lane >= o)
+        s += t;
+    }
+    if (lane == 31)
+      wsum[warp] = s;
+    __syncthreads();
+    int off = carry;
+    for (int k = 0; k < warp; ++k)
+      off += wsum[k];
+    if (y < S.h)
+      rowCount[S.rowOff + y] = off + s - v;
+    __syncthreads();
+    if (threadIdx.x == 255)
+      carry = off + s;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    ncomp[blockIdx.x] = carry;
+}
+
+// single CTA: exclusive scan over slices -> first CompStat slot of each slice; checks capacities
+__global__ void __launch_bounds__(256)
+k_cc_base(const int * __restrict__ ncomp, int nslices, int * compBase, int * total, int cap, int maxPerSlice, int * err)
+{
+  __shared__ int wsum[8];
+  __shared__ int carry;
+  if (threadIdx.x == 0)
+    carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < nslices; base += 256)
+  {
+    int k = base + threadIdx.x;
+    int v = k < nslices ? ncomp[k] : 0;
+    if (v > maxPerSlice)
+      atomicMax(err, ERR_PIXELTYPE);
+    int s = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      int t = __shfl_up_sync(0xFFFFFFFFu, s, o);
+      if (lane >= o)
+        s += t;
+    }
+    if (lane == 31)
+      wsum[warp] = s;
+    __syncthreads();
+    int off = carry;
+    for (int q = 0; q < warp; ++q)
+      off += wsum[q];
+    if (k < nslices)
+      compBase[k] = off + s - v;
+    __syncthreads();
+    if (threadIdx.x == 255)
+      carry = off + s;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+  {
+    *total = carry;
+    if (carry > cap)
+      atomicMax(err, ERR_COMPONENTS);
+  }
+}
+
+__global__ void
+k_stats_init(CompStat * stats, const int * total, int cap)
+{
+  int n = min(*total, cap);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+  {
+    CompStat s;
+    s.count = 0;
+    s.sumU = 0;
+    s.sumV = 0;
+    s.minU = 0x7FFFFFFF;
+    s.minV = 0x7FFFFFFF;
+    s.maxU = -0x7FFFFFFF;
+    s.maxV = -0x7FFFFFFF;
+    stats[k] = s;
+  }
+}
+
+// warp per row: roots receive consecutive ids in raster order
+__global__ void __launch_bounds__(256)
+k_cc_assign(const SliceDev * __restrict__ slices, const RowTile * __restrict__ tiles, const uint32_t * __restrict__ parentAll,
+            const int * __restrict__ rowCount, uint32_t * rootIdAll)
+{
+  const RowTile tile = tiles[blockIdx.x];
+  const SliceDev S = slices[tile.item];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const uint32_t * parent = parentAll + S.pixOff;
+  uint32_t * rootId = rootIdAll + S.pixOff;
+  for (int r = warp; r < tile.nrows; r += nwarps)
+  {
+    const int y = tile.row0 + r;
+    int cnt = rowCount[S.rowOff + y]; // exclusive prefix = roots before this row
+    for (int x0 = 0; x0 < S.w; x0 += 32)
+    {
+      const int x = x0 + lane;
+      bool root = false;
+      uint32_t p = (uint32_t)y * (uint32_t)S.w + (uint32_t)x;
+      if (x < S.w)
+        root = parent[p] == p;
+      uint32_t bits = __ballot_sync(0xFFFFFFFFu, root);
+      if (root)
+        rootId[p] = (uint32_t)(cnt + __popc(bits & ((1u << lane) - 1u)) + 1);
+      cnt += __popc(bits);
+    }
+  }
+}
+
+// component image + per-component statistics (one set of atomics per horizontal run chunk)
+__global__ void __launch_bounds__(256)
+k_cc_write(const SliceDev * __restrict__ slices, const RowTile * __restrict__ tiles, const uint32_t * __restrict__ parentAll,
+           const uint32_t * __restrict__ rootIdAll, const int * __restrict__ compBase, int statCap, uint16_t * connAll,
+           CompStat * stats)
+{
+  MCI_TILE_LOOP(tile, S, cw)
+  {
+    const int y = tile.row0 + cell / cw;
+    const int x = (cell % cw) * 32 + lane;
+    uint32_t id = 0;
+    if (x < S.w)
+    {
+      const uint32_t p = (uint32_t)y * (uint32_t)S.w + (uint32_t)x;
+      uint32_t r = parentAll[S.pixOff + p];
+      if (r != MCI_NOLABEL)
+        id = rootIdAll[S.pixOff + r];
+      connAll[S.pixOff + p] = (uint16_t)id;
+    }
+    uint32_t bits = __ballot_sync(0xFFFFFFFFu, id != 0);
+    if (id != 0 && !(lane > 0 && ((bits >> (lane - 1)) & 1u)))
+    {
+      uint32_t rest = ~(bits >> lane);
+      int len = rest ? __ffs(rest) - 1 : 32 - lane;
+      int slot = compBase[tile.item] + (int)id - 1;
+      if (slot < statCap)
+      {
+        CompStat * st = stats + slot;
+        long long u = S.u0 + x, v = S.v0 + y;
+        atomicAdd((unsigned long long *)&st->count, (unsigned long long)len);
+        atomicAdd((unsigned long long *)&st->sumU, (unsigned long long)(u * len + (long long)len * (len - 1) / 2));
+        atomicAdd((unsigned long long *)&st->sumV, (unsigned long long)(v * len));
+        atomicMin(&st->minU, (int)u);
+        atomicMax(&st->maxU, (int)u + len - 1);
+        atomicMin(&st->minV, (int)v);
+        atomicMax(&st->maxV, (int)v);
+      }
+    }
+  }
+}
+
+void
+launch_cc(Launch & L, int ptype, const void * in, const SliceDev * slices, int nslices, const RowTile * tiles, int ntiles,
+          uint32_t * parent, uint32_t * rootId, uint16_t * conn, int * rowCount, int * ncomp, int * compBase, int * total,
+          CompStat * stats, int statCap, int fully, int * err)
+{
+  if (nslices == 0 || ntiles == 0)
+    return;
+  switch (ptype)
+  {
+    case MCI_U8:
+      k_cc_init<uint8_t><<<ntiles, 256, 0, L.stream>>>((const uint8_t *)in, slices, tiles, parent);
+      break;
+    case MCI_U16:
+      k_cc_init<uint16_t><<<ntiles, 256, 0, L.stream>>>((const uint16_t *)in, slices, tiles, parent);
+      break;
+    default:
+      k_cc_init<int16_t><<<ntiles, 256, 0, L.stream>>>((const int16_t *)in, slices, tiles, parent);
+  }
+  k_cc_merge<<<ntiles, 256, 0, L.stream>>>(slices, tiles, parent, fully);
+  k_cc_flatten<<<ntiles, 256, 0, L.stream>>>(slices, tiles, parent, rowCount);
+  k_cc_rowscan<<<nslices, 256, 0, L.stream>>>(slices, rowCount, ncomp);
+  int maxPer = ptype == MCI_U8 ? 255 : (ptype == MCI_U16 ? 65535 : 32767);
+  k_cc_base<<<1, 256, 0, L.stream>>>(ncomp, nslices, compBase, total, statCap, maxPer, err);
+  k_stats_init<<<std::max(1, std::min(L.sms * 4, (statCap + 255) / 256)), 256, 0, L.stream>>>(stats, total, statCap);
+  k_cc_assign<<<ntiles, 256, 0, L.stream>>>(slices, tiles, parent, rowCount, rootId);
+  k_cc_write<<<ntiles, 256, 0, L.stream>>>(slices, tiles, parent, rootId, compBase, statCap, conn, stats);
+  L.post("k_cc_*", 8);
+}
+
+// ================================================================================================
+// K3  component matching: distinct (iId, jId) pairs of every segment  (X:1250-1272)
+// ================================================================================================
+__global__ void __launch_bounds__(256)
+k_pairs(const SliceDev * __restrict__ slices, const SegDev * __restrict__ segs, const RowTile * __restrict__ tiles,
+        const uint16_t * __restrict__ connAll, u64 * table, uint32_t tableMask, mci_pair * pairs, int capPairs, int * nPairs,
+        int * err)
+{
+  const RowTile tile = tiles[blockIdx.x];
+  const SegDev G = segs[tile.item];
+  const SliceDev A = slices[G.si], B = slices[G.sj];
+  const int cw = (A.w + 31) >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int cell = warp; cell < tile.nrows * cw; cell += nwarps)
+  {
+    const int y = tile.row0 + cell / cw;
+    const int x = (cell % cw) * 32 + lane;
+    uint32_t key = 0;
+    if (x < A.w)
+    {
+      const u64 p = (u64)y * (u64)A.w + (u64)x;
+      key = ((uint32_t)connAll[A.pixOff + p] << 16) | (uint32_t)connAll[B.pixOff + p];
+    }
+    uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, key, 1);
+    if (key != 0 && (lane == 0 || key != prev))
+    {
+      u64 full = ((u64)(uint32_t)tile.item << 32) | key;
+      uint32_t h = (uint32_t)((full * 0x9E3779B97F4A7C15ull) >> 40) & tableMask;
+      for (uint32_t probe = 0; probe <= tableMask; ++probe)
+      {
+        u64 cur = table[h];
+        if (cur == full)
+          break;
+        if (cur == ~0ull)
+        {
+          u64 old = atomicCAS(&table[h], ~0ull, full);
+          if (old == ~0ull)
+          {
+            int pos = atomicAdd(nPairs, 1);
+            if (pos < capPairs)
+            {
+              mci_pair q;
+              q.segment = tile.item;
+              q.i_id = (uint16_t)(key >> 16);
+              q.j_id = (uint16_t)(key & 0xFFFFu);
+              pairs[pos] = q;
+            }
+            else
+              atomicMax(err, ERR_PAIR_TABLE);
+            break;
+          }
+          if (old == full)
+            break;
+        }
+        h = (h + 1) & tableMask;
+        if (probe == tableMask)
+          atomicMax(err, ERR_PAIR_TABLE);
+      }
+    }
+  }
+}
+
+void
+launch_pairs(Launch & L, const SliceDev * slices, const SegDev * segs, const RowTile * tiles, int ntiles, const uint16_t * conn,
+             u64 * table, uint32_t tableMask, mci_pair * pairs, int capPairs, int * nPairs, int * err)
+{
+  if (ntiles == 0)
+    return;
+  k_pairs<<<ntiles, 256, 0, L.stream>>>(slices, segs, tiles, conn, table, tableMask, pairs, capPairs, nPairs, err);
+  L.post("k_pairs");
+}
+
+// ================================================================================================
+// K6 (part)  bit-packed mask of one component over its bounding box
+// ================================================================================================
+__global__ void __launch_bounds__(256)
+k_extract(const SliceDev * __restrict__ slices, const ExtractJob * __restrict__ jobs, const uint16_t * __restrict__ connAll,
+          uint32_t * arena)
+{
+  const ExtractJob J = jobs[blockIdx.x];
+  const SliceDev S = slices[J.slice];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int cells = J.m.h * J.m.pitch;
+  for (int cell = warp; cell < cells; cell += nwarps)
+  {
+    const int r = cell / J.m.pitch, wi = cell % J.m.pitch;
+    const int x = wi * 32 + lane;
+    bool on = false;
+    if (x < J.m.w)
+    {
+      const int u = J.m.x0 + x - S.u0, v = J.m.y0 + r - S.v0;
+      on = connAll[S.pixOff + (u64)v * (u64)S.w + (u64)u] == (uint16_t)J.id;
+    }
+    uint32_t bits = __ballot_sync(0xFFFFFFFFu, on);
+    if (lane == 0)
+      arena[J.m.off + (u64)cell] = bits;
+  }
+}
+
+void
+launch_extract(Launch & L, const SliceDev * slices, const ExtractJob * jobs, int njobs, const uint16_t * conn, uint32_t * arena)
+{
+  if (njobs == 0)
+    return;
+  k_extract<<<njobs, 256, 0, L.stream>>>(slices, jobs, conn, arena);
+  L.post("k_extract");
+}
+
+// ================================================================================================
+// K5  Align: breadth-first translation search maximising the overlap  (X:1136-1222, Intersection X:1032-1077)
+// One CTA per job.  Every translation that enters the queue is evaluated sooner or later, so all
+// queued-but-unscored entries are scored in parallel (one warp each); one thread then replays the
+// reference's sequential pop / compare / expand logic over those scores, which pushes the next wave.
+// ================================================================================================
+__device__ __forceinline__ unsigned
+align_score(const AlignJob & J, const MaskRef * __restrict__ refs, const uint32_t * __restrict__ arena, int tx, int ty, int lane)
+{
+  const MaskRef A = refs[J.aRef];
+  if (J.kind == JOB_EXTRAPOLATE)
+    return mask_bit(arena, A, J.phx - tx, J.phy - ty) ? 1u : 0u;
+  unsigned total = 0;
+  for (int k = 0; k < J.nB; ++k)
+  {
+    const MaskRef B = refs[J.bRef + k];
+    int ylo = max(A.y0, B.y0 - ty), yhi = min(A.y0 + A.h, B.y0 + B.h - ty);
+    unsigned c = 0;
+    if (yhi > ylo)
+    {
+      // columns of A that can meet B
+      int wlo = max(0, (B.x0 - tx - A.x0) >> 5), whi = min(A.pitch, ((B.x0 + B.w - tx - A.x0 + 31) >> 5));
+      int nw = whi - wlo;
+      if (nw > 0)
+      {
+        int cells = (yhi - ylo) * nw;
+        for (int cell = lane; cell < cells; cell += 32)
+        {
+          int r = cell / nw, wi = wlo + cell % nw;
+          int y = ylo + r;
+          uint32_t a = arena[A.off + (u64)(y - A.y0) * (u64)A.pitch + wi];
+          if (a)
+            c += __popc(a & mask_word(arena, B, y + ty, A.x0 + 32 * wi + tx));
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    if (c == 0)
+      return 0u; // iConn must intersect every listed component of jConn (X:1068-1075)
+    total += c;
+  }
+  return total;
+}
+
+__global__ void __launch_bounds__(256)
+k_align(const AlignJob * __restrict__ jobs, int njobs, const MaskRef * __restrict__ refs, const uint32_t * __restrict__ arena,
+        uint32_t * gscratch, int heuristic, int2 * result, int * err)
+{
+  extern __shared__ uint32_t smem[];
+  __shared__ int s_head, s_tail, s_scored, s_done;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int jb = blockIdx.x; jb < njobs; jb += gridDim.x)
+  {
+    const AlignJob J = jobs[jb];
+    const int bpitch = (J.sw + 31) >> 5;
+    const int bwords = bpitch * J.sh;
+    uint32_t * bitmap = J.useSmem ? smem : gscratch + J.bitmapOff;
+    uint32_t * qbuf = J.useSmem ? smem + bwords : gscratch + J.queueOff;
+    int * qx = (int *)qbuf;
+    int * qy = qx + J.qcap;
+    unsigned * qs = (unsigned *)(qy + J.qcap);
+    const int qmask = J.qcap - 1;
+    __syncthreads();
+    for (int k = threadIdx.x; k < bwords; k += blockDim.x)
+      bitmap[k] = 0u;
+    __syncthreads();
+    // replay state lives in registers of thread 0
+    unsigned maxScore = 0;
+    long long iter = 0;
+    int bestx = 0, besty = 0;
+    if (threadIdx.x == 0)
+    {
+      qx[0] = 0;
+      qy[0] = 0;
+      qx[1] = J.indx;
+      qy[1] = J.indy;
+      bitmap[(0 - J.sy0) * bpitch + ((0 - J.sx0) >> 5)] |= 1u << ((0 - J.sx0) & 31);
+      if ((unsigned)(J.indx - J.sx0) < (unsigned)J.sw && (unsigned)(J.indy - J.sy0) < (unsigned)J.sh)
+        bitmap[(J.indy - J.sy0) * bpitch + ((J.indx - J.sx0) >> 5)] |= 1u << ((J.indx - J.sx0) & 31);
+      s_head = 0;
+      s_tail = 2;
+      s_scored = 0;
+      s_done = 0;
+    }
+    __syncthreads();
+    for (;;)
+    {
+      const int from = s_scored, to = s_tail;
+      for (int e = from + warp; e < to; e += nwarps)
+      {
+        unsigned sc = align_score(J, refs, arena, qx[e & qmask], qy[e & qmask], lane);
+        if (lane == 0)
+          qs[e & qmask] = sc;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0)
+      {
+        int head = s_head, tail = to;
+        while (head < to)
+        {
+          int tx = qx[head & qmask], ty = qy[head & qmask];
+          unsigned sc = qs[head & qmask];
+          ++head;
+          if (sc > maxScore)
+          {
+            maxScore = sc;
+            bestx = tx;
+            besty = ty;
+          }
+          if (!heuristic || maxScore == 0 || iter <= J.minIter || ((double)sc > (double)maxScore * 0.9 && iter <= J.maxIter))
+          {
+#pragma unroll
+            for (int d = 0; d < 4; ++d)
+            {
+              int nx = tx + (d == 0 ? -1 : (d == 1 ? 1 : 0));
+              int ny = ty + (d == 2 ? -1 : (d == 3 ? 1 : 0));
+              int rx = nx - J.sx0, ry = ny - J.sy0;
+              if ((unsigned)rx < (unsigned)J.sw && (unsigned)ry < (unsigned)J.sh)
+              {
+                uint32_t * w = &bitmap[ry * bpitch + (rx >> 5)];
+                uint32_t bit = 1u << (rx & 31);
+                if (!(*w & bit))
+                {
+                  *w |= bit;
+                  if (tail - head >= J.qcap)
+                  {
+                    atomicMax(err, ERR_QUEUE);
+                  }
+                  else
+                  {
+                    qx[tail & qmask] = nx;
+                    qy[tail & qmask] = ny;
+                    ++tail;
+                  }
+                  ++iter;
+                }
+              }
+            }
+          }
+        }
+        s_head = head;
+        s_scored = to;
+        s_tail = tail;
+        s_done = (head == tail);
+      }
+      __syncthreads();
+      if (s_done)
+        break;
+    }
+    if (threadIdx.x == 0)
+      result[jb] = make_int2(bestx, besty);
+  }
+}
+
+void
+launch_align(Launch & L, const AlignJob * jobs, int njobs, const MaskRef * refs, const uint32_t * arena, uint32_t * gscratch,
+             int heuristic, int2 * result, int smemBytes, int * err)
+{
+  if (njobs == 0)
+    return;
+  static bool attr = false;
+  if (!attr)
+  {
+    cudaFuncSetAttribute(k_align, cudaFuncAttributeMaxDynamicSharedMemorySize, L.maxSmem - 1024);
+    attr = true;
+  }
+  int grid = std::min(njobs, L.sms * 8);
+  k_align<<<grid, 256, smemBytes, L.stream>>>(jobs, njobs, refs, arena, gscratch, heuristic, result, err);
+  L.post("k_align");
+}
+
+// ================================================================================================
+// K9  1-to-N split: synchronous multi-source geodesic growth inside the mask, ties to the
+//     lowest index (Interpolate1toN, X:824-986)
+// ================================================================================================
+__global__ void __launch_bounds__(256)
+k_split(const SplitJob * __restrict__ jobs, const MaskRef * __restrict__ refs, uint32_t * arena, uint32_t * gscratch,
+        const int2 * __restrict__ trans, int ball, int * err)
+{
+  const SplitJob J = jobs[blockIdx.x];
+  const MaskRef A = refs[J.aRef];
+  const int2 t = trans[J.job];
+  const int words = A.h * A.pitch;
+  const uint32_t * mask = arena + A.off;
+  // seeds: pixels of the mask whose translate lies in component k of the other slice (X:871-892)
+  for (int idx = threadIdx.x; idx < words; idx += blockDim.x)
+  {
+    int r = idx / A.pitch, wi = idx % A.pitch;
+    uint32_t m = mask[idx];
+    for (int k = 0; k < J.nB; ++k)
+    {
+      const MaskRef B = refs[J.bRef + k];
+      arena[refs[J.outRef + k].off + idx] = m ? (m & mask_word(arena, B, A.y0 + r + t.y, A.x0 + 32 * wi + t.x)) : 0u;
+    }
+  }
+  __syncthreads();
+  // growth (X:905-963).  cur = planes in the arena (final home), nxt = scratch; swapped every step.
+  bool curIsArena = true;
+  for (int step = 0;; ++step)
+  {
+    int pending = 0, grew = 0;
+    for (int idx = threadIdx.x; idx < words; idx += blockDim.x)
+    {
+      int r = idx / A.pitch, wi = idx % A.pitch;
+      uint32_t m = mask[idx];
+      uint32_t owned = 0;
+      for (int k = 0; k < J.nB; ++k)
+      {
+        const uint32_t * cur = curIsArena ? arena + refs[J.outRef + k].off : gscratch + J.scratchOff + (u64)k * words;
+        owned |= cur[idx];
+      }
+      uint32_t freeBits = m & ~owned;
+      uint32_t taken = 0;
+      for (int k = 0; k < J.nB; ++k)
+      {
+        const uint32_t * cur = curIsArena ? arena + refs[J.outRef + k].off : gscratch + J.scratchOff + (u64)k * words;
+        uint32_t * nxt = curIsArena ? gscratch + J.scratchOff + (u64)k * words : arena + refs[J.outRef + k].off;
+        uint32_t c = freeBits ? (dilate_word(cur, A.h, A.pitch, r, wi, ball != 0) & freeBits & ~taken) : 0u;
+        nxt[idx] = cur[idx] | c;
+        taken |= c;
+      }
+      if (freeBits & ~taken)
+        pending = 1;
+      if (taken)
+        grew = 1;
+    }
+    pending = __syncthreads_or(pending);
+    grew = __syncthreads_or(grew);
+    curIsArena = !curIsArena;
+    if (!pending)
+      break;
+    if (!grew)
+    {
+      if (threadIdx.x == 0)
+        atomicMax(err, ERR_SPLIT_STUCK); // reference would loop forever: a mask pixel no seed can reach
+      break;
+    }
+  }
+  if (!curIsArena)
+  {
+    for (int idx = threadIdx.x; idx < words; idx += blockDim.x)
+      for (int k = 0; k < J.nB; ++k)
+        arena[refs[J.outRef + k].off + idx] = gscratch[J.scratchOff + (u64)k * words + idx];
+  }
+}
+
+void
+launch_split(Launch & L, const SplitJob * jobs, int njobs, const MaskRef * refs, uint32_t * arena, uint32_t * gscratch,
+             const int2 * trans, int ball, int * err)
+{
+  if (njobs == 0)
+    return;
+  k_split<<<njobs, 256, 0, L.stream>>>(jobs, refs, arena, gscratch, trans, ball, err);
+  L.post("k_split");
+}
+
+// ================================================================================================
+// root nodes of the Interpolate1to1 trees
+// ================================================================================================
+__global__ void
+k_make_roots(const RootJob * __restrict__ roots, int nroots, MaskRef * refs, uint32_t * arena, const int2 * __restrict__ trans,
+             Node * nodes)
+{
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nroots)
+    return;
+  const RootJob R = roots[k];
+  const int2 t = trans[R.job];
+  if (R.kind == JOB_EXTRAPOLATE)
+  {
+    // phantom point, moved against the alignment so that it lands inside the shape (X:218-250)
+    MaskRef ph = refs[R.phRef];
+    ph.x0 = R.phx - t.x;
+    ph.y0 = R.phy - t.y;
+    ph.w = ph.h = 1;
+    ph.pitch = 1;
+    arena[ph.off] = 1u;
+    refs[R.phRef] = ph;
+    Node n;
+    n.A = refs[R.aRef];
+    n.B = ph;
+    n.tx = 0;
+    n.ty = 0;
+    n.i = R.posA;
+    n.j = R.posB;
+    n.axis = R.axis;
+    n.label = R.label;
+    nodes[R.rootOff] = n;
+  }
+  else if (R.kind == JOB_ONE_TO_ONE)
+  {
+    Node n;
+    n.A = refs[R.aRef];
+    n.B = refs[R.bRef];
+    n.tx = t.x;
+    n.ty = t.y;
+    n.i = R.posA;
+    n.j = R.posB;
+    n.axis = R.axis;
+    n.label = R.label;
+    nodes[R.rootOff] = n;
+  }
+  else
+  {
+    for (int q = 0; q < R.nB; ++q)
+    {
+      Node n;
+      n.A = refs[R.splitRef + q];
+      n.B = refs[R.bRef + q];
+      n.tx = t.x;
+      n.ty = t.y;
+      n.i = R.posA;
+      n.j = R.posB;
+      n.axis = R.axis;
+      n.label = R.label;
+      nodes[R.rootOff + q] = n;
+    }
+  }
+}
+
+void
+launch_make_roots(Launch & L, const RootJob * roots, int nroots, MaskRef * refs, uint32_t * arena, const int2 * trans, Node * nodes)
+{
+  if (nroots == 0)
+    return;
+  k_make_roots<<<(nroots + 127) / 128, 128, 0, L.stream>>>(roots, nroots, refs, arena, trans, nodes);
+  L.post("k_make_roots");
+}
+
+// ================================================================================================
+// K6/K7/K8/K10  one Interpolate1to1 call per CTA  (X:556-793)
+//   translate + binarise + AND (X:570-666), median by exact squared distances (FindMedianImageDistances,
+//   X:405-516) or by constrained dilations (FindMedianImageDilations, X:340-388), clip + write with the
+//   max rule (X:679-764), spawn the two children (X:766-792).
+// ================================================================================================
+
+// nearest set bit of a bit row to column x, as squared distance, searching only while it can beat lim
+__device__ __forceinline__ int
+row_nearest_sq(const uint32_t * row, int pitch, int x, int lim)
+{
+  const int w0 = x >> 5, b = x & 31;
+  int best = lim;
+  {
+    uint32_t m = row[w0] & (0xFFFFFFFFu >> (31 - b));
+    int wl = w0;
+    for (;;)
+    {
+      if (m)
+      {
+        int dx = x - (wl * 32 + 31 - __clz(m));
+        best = min(best, dx * dx);
+        break;
+      }
+      if (--wl < 0)
+        break;
+      int dmin = x - (wl * 32 + 31);
+      if (dmin * dmin >= best)
+        break;
+      m = row[wl];
+    }
+  }
+  {
+    uint32_t m = row[w0] & (0xFFFFFFFEu << b);
+    int wr = w0;
+    for (;;)
+    {
+      if (m)
+      {
+        int dx = (wr * 32 + __ffs(m) - 1) - x;
+        best = min(best, dx * dx);
+        break;
+      }
+      if (++wr >= pitch)
+        break;
+      int dmin = wr * 32 - x;
+      if (dmin * dmin >= best)
+        break;
+      m = row[wr];
+    }
+  }
+  return best;
+}
+
+// exact squared Euclidean distance from pixel (x, r) to the nearest set bit of Xb, or `cap` if not below cap
+__device__ __forceinline__ int
+edt_sq(const uint32_t * Xb, int pitch, int xr0, int xr1, int x, int r, int cap)
+{
+  int best = cap;
+  int k = max(0, max(xr0 - r, r - xr1));
+  for (;; ++k)
+  {
+    int kk = k * k;
+    if (kk >= best)
+      break;
+    int r1 = r - k, r2 = r + k;
+    if (r1 < xr0 && r2 > xr1)
+      break;
+    if (r1 >= xr0 && r1 <= xr1)
+      best = min(best, kk + row_nearest_sq(Xb + (size_t)r1 * pitch, pitch, x, best - kk));
+    if (k > 0 && r2 <= xr1 && r2 >= xr0)
+      best = min(best, kk + row_nearest_sq(Xb + (size_t)r2 * pitch, pitch, x, best - kk));
+  }
+  return best;
+}
+
+#define MCI_NODE_THREADS 256
+#define MCI_SMALL_HIST 2048
+
+struct NodeShared
+{
+  int xr0, xr1;           // first / last row holding intersection pixels
+  int anyXor;
+  int bigUsed;            // a distance beyond the small histogram was met
+  int maxIdx;             // largest histogram index used (small: d2; big: bin)
+  int bx0, by0, bx1, by1; // bounding box of the median
+  unsigned long long midOff;
+  long long redA[MCI_NODE_THREADS / 32], redB[MCI_NODE_THREADS / 32];
+  long long bestDiff[MCI_NODE_THREADS / 32];
+  int bestIdx[MCI_NODE_THREADS / 32];
+  int result;
+  int cnt, chg;
+  int K[2];
+};
+
+// block-wide exclusive scan of two per-thread values (returns exclusive prefixes, totals via tot*)
+__device__ __forceinline__ void
+block_scan2(NodeShared & sh, long long a, long long b, long long & pa, long long & pb, long long & totA, long long & totB)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long sa = a, sb = b;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+  {
+    long long ta = __shfl_up_sync(0xFFFFFFFFu, sa, o), tb = __shfl_up_sync(0xFFFFFFFFu, sb, o);
+    if (lane >= o)
+    {
+      sa += ta;
+      sb += tb;
+    }
+  }
+  __syncthreads();
+  if (lane == 31)
+  {
+    sh.redA[warp] = sa;
+    sh.redB[warp] = sb;
+  }
+  __syncthreads();
+  long long oa = 0, ob = 0;
+  totA = 0;
+  totB = 0;
+  for (int k = 0; k < MCI_NODE_THREADS / 32; ++k)
+  {
+    if (k < warp)
+    {
+      oa += sh.redA[k];
+      ob += sh.redB[k];
+    }
+    totA += sh.redA[k];
+    totB += sh.redB[k];
+  }
+  pa = oa + sa - a;
+  pb = ob + sb - b;
+}
+
+// block-wide arg-min with ties to the lowest index
+__device__ __forceinline__ int
+block_argmin(NodeShared & sh, long long diff, int idx)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    long long od = __shfl_xor_sync(0xFFFFFFFFu, diff, o);
+    int oi = __shfl_xor_sync(0xFFFFFFFFu, idx, o);
+    if (od < diff || (od == diff && oi < idx))
+    {
+      diff = od;
+      idx = oi;
+    }
+  }
+  __syncthreads();
+  if (lane == 0)
+  {
+    sh.bestDiff[warp] = diff;
+    sh.bestIdx[warp] = idx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    long long d = sh.bestDiff[0];
+    int i = sh.bestIdx[0];
+    for (int k = 1; k < MCI_NODE_THREADS / 32; ++k)
+      if (sh.bestDiff[k] < d || (sh.bestDiff[k] == d && sh.bestIdx[k] < i))
+      {
+        d = sh.bestDiff[k];
+        i = sh.bestIdx[k];
+      }
+    sh.result = i;
+  }
+  __syncthreads();
+  return sh.result;
+}
+
+// FindMedianImageDistances (X:405-516).  Xb = intersection, Ib = i-shape, Sb = i xor j on entry; on exit
+// Sb holds the median.  Histograms are indexed by d2 while 10*d2 fits the pixel type without wrapping
+// (bins are then 10*d2, so scanning d2 ascending visits exactly the bins where the score can change);
+// otherwise by the wrapped bin `PixelType(10 * d2)` of X:431 in the per-CTA global table.
+template <typename T>
+__device__ void
+median_distances(NodeShared & sh, uint32_t * Xb, const uint32_t * Ib, uint32_t * Sb, int h, int pitch, unsigned * smallHist,
+                 unsigned * bigHist, int * err)
+{
+  const int words = h * pitch;
+  const int tid = threadIdx.x;
+  for (int k = tid; k < 2 * MCI_SMALL_HIST; k += MCI_NODE_THREADS)
+    smallHist[k] = 0u;
+  if (tid == 0)
+  {
+    sh.bigUsed = 0;
+    sh.maxIdx = -1;
+  }
+  __syncthreads();
+  const int xr0 = sh.xr0, xr1 = sh.xr1;
+  constexpr int kSmall = PixTraits<T>::kNoWrapD2 < MCI_SMALL_HIST - 1 ? PixTraits<T>::kNoWrapD2 : MCI_SMALL_HIST - 1;
+  int localMaxSmall = -1, localMaxBig = -1;
+  for (int idx = tid; idx < words; idx += MCI_NODE_THREADS)
+  {
+    uint32_t s = Sb[idx];
+    if (!s)
+      continue;
+    const int r = idx / pitch, wi = idx % pitch;
+    const uint32_t iw = Ib[idx];
+    while (s)
+    {
+      int b = __ffs(s) - 1;
+      s &= s - 1;
+      int d2 = edt_sq(Xb, pitch, xr0, xr1, wi * 32 + b, r, 0x7FFFFFFF);
+      int side = (iw >> b) & 1u ? 0 : 1;
+      if (d2 <= kSmall)
+      {
+        atomicAdd(&smallHist[side * MCI_SMALL_HIST + d2], 1u);
+        localMaxSmall = max(localMaxSmall, d2);
+      }
+      else
+      {
+        int q = __float2int_rz(__fmul_rn(10.0f, (float)d2));
+        int bin;
+        if (sizeof(T) == 1)
+          bin = q & 0xFF;
+        else if (std::is_signed<T>::value)
+        {
+          short v = (short)q;
+          if (v < 0)
+          {
+            atomicMax(err, ERR_PIXELTYPE); // reference: negative index into the histogram (X:431-437)
+            v = 0;
+          }
+          bin = v;
+        }
+        else
+          bin = q & 0xFFFF;
+        atomicAdd(&bigHist[side * 65536 + bin], 1u);
+        localMaxBig = max(localMaxBig, bin);
+      }
+    }
+  }
+  if (localMaxBig >= 0)
+  {
+    sh.bigUsed = 1;
+    atomicMax(&sh.maxIdx, localMaxBig);
+  }
+  __syncthreads();
+  const int big = sh.bigUsed;
+  __syncthreads();
+  if (!big && localMaxSmall >= 0)
+    atomicMax(&sh.maxIdx, localMaxSmall);
+  if (big)
+  {
+    // fold the small histogram into the bin table (bin = 10*d2 below the wrap)
+    for (int k = tid; k < 2 * MCI_SMALL_HIST; k += MCI_NODE_THREADS)
+    {
+      unsigned c = smallHist[k];
+      if (c)
+      {
+        int side = k / MCI_SMALL_HIST, d2 = k % MCI_SMALL_HIST;
+        int bin = (sizeof(T) == 1) ? ((10 * d2) & 0xFF) : 10 * d2;
+        atomicAdd(&bigHist[side * 65536 + bin], c);
+        atomicMax(&sh.maxIdx, bin);
+      }
+    }
+  }
+  __syncthreads();
+  const int n = sh.maxIdx + 1; // histogram length (maxSize, X:462)
+  if (n <= 0)
+  {
+    // no pixel outside the intersection: the median is the intersection (X:463-466)
+    for (int idx = tid; idx < words; idx += MCI_NODE_THREADS)
+      Sb[idx] = Xb[idx];
+    __syncthreads();
+    return;
+  }
+  const unsigned * hi = big ? bigHist : smallHist;
+  const unsigned * hj = big ? bigHist + 65536 : smallHist + MCI_SMALL_HIST;
+  const int chunk = (n + MCI_NODE_THREADS - 1) / MCI_NODE_THREADS;
+  const int lo = min(n, tid * chunk), hiEnd = min(n, lo + chunk);
+  long long ci = 0, cj = 0;
+  for (int k = lo; k < hiEnd; ++k)
+  {
+    ci += hi[k];
+    cj += hj[k];
+  }
+  long long pi, pj, iTot, jTot;
+  block_scan2(sh, ci, cj, pi, pj, iTot, jTot);
+  long long bestDiff = 0x7FFFFFFFFFFFFFFFll;
+  int bestIdx = 0x7FFFFFFF;
+  long long si = pi, sj = pj;
+  for (int k = lo; k < hiEnd; ++k)
+  {
+    si += hi[k];
+    sj += hj[k];
+    long long a = llabs(iTot - si + sj), b = llabs(jTot - sj + si);
+    long long d = llabs(a - b);
+    if (d < bestDiff)
+    {
+      bestDiff = d;
+      bestIdx = k;
+    }
+  }
+  int best = block_argmin(sh, bestDiff, bestIdx);
+  // threshold sdf <= float(bestBin)/10 on integer d2 (X:497-508)
+  int thr;
+  if (big)
+    thr = (int)floorf(__fdiv_rn((float)best, 10.0f));
+  else
+    thr = best;
+  if (big)
+  {
+    for (int k = tid; k < n; k += MCI_NODE_THREADS)
+    {
+      bigHist[k] = 0u;
+      bigHist[65536 + k] = 0u;
+    }
+  }
+  for (int idx = tid; idx < words; idx += MCI_NODE_THREADS)
+  {
+    uint32_t s = Sb[idx];
+    uint32_t m = Xb[idx];
+    if (s)
+    {
+      const int r = idx / pitch, wi = idx % pitch;
+      while (s)
+      {
+        int b = __ffs(s) - 1;
+        s &= s - 1;
+        if (edt_sq(Xb, pitch, xr0, xr1, wi * 32 + b, r, thr + 1) <= thr)
+          m |= 1u << b;
+      }
+    }
+    Sb[idx] = m;
+  }
+  __syncthreads();
+}
+
+// Constrained dilation sequence from Xb inside maskb (GenerateDilationSequence X:322-338, Dilate1 X:253-320).
+// Runs until the set stops growing or `stopAt` images have been produced (stopAt < 0: run to the end and
+// record in hist[s] how many pixels outside `otherb` joined at step s).  Returns the sequence length K.
+// D / Dn are ping-pong buffers; on return *cur points at the last image.
+__device__ int
+dilation_sequence(NodeShared & sh, const uint32_t * Xb, const uint32_t * maskb, const uint32_t * otherb, uint32_t * D,
+                  uint32_t * Dn, int h, int pitch, bool ball, int stopAt, unsigned * hist, uint32_t ** cur)
+{
+  const int words = h * pitch;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < words; idx += MCI_NODE_THREADS)
+    D[idx] = Xb[idx];
+  __syncthreads();
+  int steps = 0; // number of growth steps so far
+  uint32_t * a = D;
+  uint32_t * b = Dn;
+  while (stopAt < 0 || steps < stopAt)
+  {
+    if (tid == 0)
+      sh.cnt = 0;
+    __syncthreads();
+    int changed = 0, cnt = 0;
+    for (int idx = tid; idx < words; idx += MCI_NODE_THREADS)
+    {
+      const int r = idx / pitch, wi = idx % pitch;
+      uint32_t old = a[idx];
+      uint32_t m = maskb[idx];
+      uint32_t v = old;
+      if (m & ~old)
+        v = old | (dilate_word(a, h, pitch, r, wi, ball) & m);
+      b[idx] = v;
+      uint32_t diff = v & ~old;
+      if (diff)
+      {
+        changed = 1;
+        cnt += __popc(diff & ~otherb[idx]);
+      }
+    }
+    if (cnt)
+      atomicAdd(&sh.cnt, cnt);
+    changed = __syncthreads_or(changed);
+    if (!changed)
+      break;
+    ++steps;
+    if (stopAt < 0 && tid == 0 && steps < 65536)
+      hist[steps] = (unsigned)sh.cnt;
+    uint32_t * t = a;
+    a = b;
+    b = t;
+    __syncthreads();
+  }
+  *cur = a;
+  return steps > 0 ? steps : 1; // [D1] alone when nothing grows (X:328-336)
+}
+
+// FindMedianImageDilations (X:340-388) without storing the sequences: only how many pixels of i\j (j\i)
+// join at each step matters for the scores, because intersection pixels are in every image.
+__device__ void
+median_dilations(NodeShared & sh, const uint32_t * Xb, const uint32_t * Ib, const uint32_t * Jb, uint32_t * Sb, uint32_t * D,
+                 uint32_t * Dn, int h, int pitch, bool ball, unsigned * bigHist, int * err)
+{
+  const int words = h * pitch;
+  const int tid = threadIdx.x;
+  unsigned * hI = bigHist;         // hI[s], s = 1..Ki : pixels of i\j joining at step s
+  unsigned * hJ = bigHist + 65536; // same for j\i
+  uint32_t * cur;
+  int Ki = dilation_sequence(sh, Xb, Ib, Jb, D, Dn, h, pitch, ball, -1, hI, &cur);
+  __syncthreads();
+  int Kj = dilation_sequence(sh, Xb, Jb, Ib, D, Dn, h, pitch, ball, -1, hJ, &cur);
+  __syncthreads();
+  if (Ki > 65535 || Kj > 65535)
+  {
+    if (tid == 0)
+      atomicMax(err, ERR_SCRATCH);
+    Ki = min(Ki, 65535);
+    Kj = min(Kj, 65535);
+  }
+  // totals of i\j and j\i (pixels a sequence never reaches still count in the symmetric differences)
+  long long ni = 0, nj = 0;
+  for (int idx = tid; idx < words; idx += MCI_NODE_THREADS)
+  {
+    ni += __popc(Ib[idx] & ~Jb[idx]);
+    nj += __popc(Jb[idx] & ~Ib[idx]);
+  }
+  long long d0, d1, Ni, Nj;
+  block_scan2(sh, ni, nj, d0, d1, Ni, Nj);
+  // inclusive prefix sums of the step histograms, in place (thread-chunked)
+  const int n = max(Ki, Kj) + 1;
+  {
+    const int chunk = (n + MCI_NODE_THREADS - 1) / MCI_NODE_THREADS;
+    const int lo = min(n, tid * chunk), hiEnd = min(n, lo + chunk);
+    long long ci = 0, cj = 0;
+    for (int k = lo; k < hiEnd; ++k)
+    {
+      ci += (k >= 1 && k <= Ki) ? hI[k] : 0u;
+      cj += (k >= 1 && k <= Kj) ? hJ[k] : 0u;
+    }
+    long long pi, pj, ti, tj;
+    block_scan2(sh, ci, cj, pi, pj, ti, tj);
+    long long si = pi, sj = pj;
+    for (int k = lo; k < hiEnd; ++k)
+    {
+      si += (k >= 1 && k <= Ki) ? hI[k] : 0u;
+      sj += (k >= 1 && k <= Kj) ? hJ[k] : 0u;
+      hI[k] = (unsigned)si;
+      hJ[k] = (unsigned)sj;
+    }
+  }
+  __syncthreads();
+  // seq[x] (X:349-371): the i-sequence is reversed BEFORE the swap that makes iSeq the longer one
+  const bool swapped = Ki < Kj;
+  const int L = swapped ? Kj : Ki;
+  const float ratio = __fdiv_rn((float)(swapped ? Ki : Kj), (float)L);
+  long long bestDiff = 0x7FFFFFFFFFFFFFFFll;
+  int bestIdx = 0x7FFFFFFF;
+  for (int x = tid; x < L; x += MCI_NODE_THREADS)
+  {
+    unsigned xj = __float2uint_rz(__fmul_rn(ratio, (float)x));
+    int si, sj; // sequence images D^i_si and D^j_sj forming seq[x]
+    if (!swapped)
+    {
+      si = Ki - x;
+      sj = (int)xj + 1;
+    }
+    else
+    {
+      sj = x + 1;
+      si = Ki - (int)xj;
+    }
+    long long ci = hI[min(si, Ki)], cj = hJ[min(sj, Kj)];
+    long long iS = cj + (Ni - ci);
+    long long jS = ci + (Nj - cj);
+    long long d = llabs(iS - jS);
+    if (d < bestDiff)
+    {
+      bestDiff = d;
+      bestIdx = x;
+    }
+  }
+  int bx = block_argmin(sh, bestDiff, bestIdx);
+  // (the reference starts from min = number of region pixels with a strict "<": any x beats it)
+  int si, sj;
+  {
+    unsigned xj = __float2uint_rz(__fmul_rn(ratio, (float)bx));
+    if (!swapped)
+    {
+      si = Ki - bx;
+      sj = (int)xj + 1;
+    }
+    else
+    {
+      sj = bx + 1;
+      si = Ki - (int)xj;
+    }
+  }
+  for (int k = tid; k < n; k += MCI_NODE_THREADS)
+  {
+    hI[k] = 0u;
+    hJ[k] = 0u;
+  }
+  __syncthreads();
+  // rebuild the chosen image: D^i_si | D^j_sj
+  dilation_sequence(sh, Xb, Ib, Jb, D, Dn, h, pitch, ball, si, nullptr, &cur);
+  __syncthreads();
+  for (int idx = tid; idx < words; idx += MCI_NODE_THREADS)
+    Sb[idx] = cur[idx];
+  __syncthreads();
+  dilation_sequence(sh, Xb, Jb, Ib, D, Dn, h, pitch, ball, sj, nullptr, &cur);
+  __syncthreads();
+  for (int idx = tid; idx < words; idx += MCI_NODE_THREADS)
+    Sb[idx] |= cur[idx];
+  __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(MCI_NODE_THREADS)
+k_nodes(const Node * __restrict__ nodes, const int * __restrict__ count, Node * next, int * nextCount, int nextCap,
+        uint32_t * arena, unsigned long long * arenaTop, unsigned long long arenaCap, const T * __restrict__ in, T * out,
+        long long VX, long long VY, long long VZ, int useDT, int ball, unsigned * bigHistAll, uint32_t * slabAll,
+        unsigned long long slabWords, int smemWords, int * err)
+{
+  extern __shared__ uint32_t smem[];
+  __shared__ NodeShared sh;
+  unsigned * smallHist = smem;
+  uint32_t * smemArr = smem + 2 * MCI_SMALL_HIST;
+  unsigned * bigHist = bigHistAll + (size_t)blockIdx.x * 2 * 65536;
+  const int tid = threadIdx.x;
+  const int nNodes = *count;
+  for (int nidx = blockIdx.x; nidx < nNodes; nidx += gridDim.x)
+  {
+    const Node nd = nodes[nidx];
+    // ---- translation halving with carry (X:570-608)
+    int t[2] = { nd.tx, nd.ty }, iT[2], jT[2];
+    bool carry = false;
+#pragma unroll
+    for (int d = 0; d < 2; ++d)
+    {
+      if (!carry)
+      {
+        iT[d] = t[d] / 2;
+        carry = (t[d] % 2) != 0;
+      }
+      else if (t[d] % 2 == 0)
+        iT[d] = t[d] / 2;
+      else
+      {
+        iT[d] = t[d] > 0 ? t[d] / 2 + 1 : t[d] / 2 - 1;
+        carry = false;
+      }
+      jT[d] = iT[d] - t[d];
+    }
+    const int mid = (nd.i + nd.j + (carry ? 1 : 0)) / 2;
+    // ---- working region: union of the two translated shapes' regions
+    const int ux0 = min(nd.A.x0 + iT[0], nd.B.x0 + jT[0]), uy0 = min(nd.A.y0 + iT[1], nd.B.y0 + jT[1]);
+    const int ux1 = max(nd.A.x0 + nd.A.w + iT[0], nd.B.x0 + nd.B.w + jT[0]);
+    const int uy1 = max(nd.A.y0 + nd.A.h + iT[1], nd.B.y0 + nd.B.h + jT[1]);
+    const int w = ux1 - ux0, h = uy1 - uy0;
+    const int pitch = (w + 31) >> 5;
+    const int words = h * pitch;
+    const int nArr = useDT ? 3 : 6;
+    uint32_t * base;
+    if ((long long)words * nArr <= smemWords)
+      base = smemArr;
+    else if ((unsigned long long)words * nArr <= slabWords)
+      base = slabAll + (size_t)blockIdx.x * slabWords;
+    else
+    {
+      if (tid == 0)
+        atomicMax(err, ERR_SCRATCH);
+      continue;
+    }
+    uint32_t * Xb = base;
+    uint32_t * Ib = base + words;
+    uint32_t * Sb = base + 2 * (size_t)words;
+    uint32_t * Jb = useDT ? nullptr : base + 3 * (size_t)words;
+    uint32_t * D = useDT ? nullptr : base + 4 * (size_t)words;
+    uint32_t * Dn = useDT ? nullptr : base + 5 * (size_t)words;
+    __syncthreads(); // previous node done with shared state
+    if (tid == 0)
+    {
+      sh.xr0 = 0x7FFFFFFF;
+      sh.xr1 = -1;
+      sh.anyXor = 0;
+      sh.bx0 = sh.by0 = 0x7FFFFFFF;
+      sh.bx1 = sh.by1 = -0x7FFFFFFF;
+    }
+    __syncthreads();
+    // ---- translate, binarise, intersect (X:610-666)
+    {
+      int r0 = 0x7FFFFFFF, r1 = -1;
+      for (int idx = tid; idx < words; idx += MCI_NODE_THREADS)
+      {
+        const int r = idx / pitch, wi = idx % pitch;
+        const int y = uy0 + r, x = ux0 + 32 * wi;
+        uint32_t a = mask_word(arena, nd.A, y - iT[1], x - iT[0]);
+        uint32_t b = mask_word(arena, nd.B, y - jT[1], x - jT[0]);
+        Xb[idx] = a & b;
+        Ib[idx] = a;
+        Sb[idx] = a ^ b;
+        if (Jb)
+          Jb[idx] = b;
+        if (a & b)
+        {
+          r0 = min(r0, r);
+          r1 = max(r1, r);
+        }
+      }
+      if (r1 >= 0)
+      {
+        atomicMin(&sh.xr0, r0);
+        atomicMax(&sh.xr1, r1);
+      }
+    }
+    __syncthreads();
+    if (sh.xr1 < 0)
+      continue; // empty intersection: both median finders return an empty image, nothing below can be written
+    // ---- median (X:668-676)
+    if (useDT)
+      median_distances<T>(sh, Xb, Ib, Sb, h, pitch, smallHist, bigHist, err);
+    else
+      median_dilations(sh, Xb, Ib, Jb, Sb, D, Dn, h, pitch, ball != 0, bigHist, err);
+    // ---- clip to the slice (X:679-712) and crop to the median's bounding box
+    const int d0 = nd.axis == 0 ? 1 : 0, d1 = nd.axis == 2 ? 1 : 2;
+    const long long dimsV[3] = { VX, VY, VZ };
+    const int SU = (int)dimsV[d0], SV = (int)dimsV[d1];
+    {
+      int bx0 = 0x7FFFFFFF, bx1 = -0x7FFFFFFF, by0 = 0x7FFFFFFF, by1 = -0x7FFFFFFF;
+      for (int idx = tid; idx < words; idx += MCI_NODE_THREADS)
+      {
+        const int r = idx / pitch, wi = idx % pitch;
+        const int y = uy0 + r;
+        uint32_t m = Sb[idx];
+        if (!m || y < 0 || y >= SV)
+          continue;
+        // clip columns
+        int xa = ux0 + 32 * wi;
+        if (xa < 0)
+          m = (xa <= -32) ? 0u : (m & (0xFFFFFFFFu << (-xa)));
+        if (xa + 32 > SU)
+          m = (xa >= SU) ? 0u : (m & (0xFFFFFFFFu >> (xa + 32 - SU)));
+        if (!m)
+          continue;
+        bx0 = min(bx0, xa + __ffs(m) - 1);
+        bx1 = max(bx1, xa + 31 - __clz(m));
+        by0 = min(by0, y);
+        by1 = max(by1, y);
+      }
+      if (by1 >= by0)
+      {
+        atomicMin(&sh.bx0, bx0);
+        atomicMax(&sh.bx1, bx1);
+        atomicMin(&sh.by0, by0);
+        atomicMax(&sh.by1, by1);
+      }
+    }
+    __syncthreads();
+    if (sh.by1 < sh.by0)
+      continue; // nothing inside the image
+    MaskRef M;
+    M.x0 = sh.bx0;
+    M.y0 = sh.by0;
+    M.w = sh.bx1 - sh.bx0 + 1;
+    M.h = sh.by1 - sh.by0 + 1;
+    M.pitch = (M.w + 31) >> 5;
+    M.pad = 0;
+    const int mwords = M.h * M.pitch;
+    if (tid == 0)
+      sh.midOff = atomicAdd(arenaTop, (unsigned long long)mwords);
+    __syncthreads();
+    M.off = sh.midOff;
+    if (M.off + (unsigned long long)mwords > arenaCap)
+    {
+      if (tid == 0)
+        atomicMax(err, ERR_ARENA);
+      continue;
+    }
+    // ---- store the mid shape and write it into the volume with the max rule (X:714-764)
+    {
+      const int lane = tid & 31, warp = tid >> 5;
+      const T label = (T)nd.label;
+      long long su, sv;
+      unsigned long long vbase;
+      if (nd.axis == 2)
+      {
+        su = 1;
+        sv = VX;
+        vbase = (unsigned long long)mid * VX * VY;
+      }
+      else if (nd.axis == 1)
+      {
+        su = 1;
+        sv = VX * VY;
+        vbase = (unsigned long long)mid * VX;
+      }
+      else
+      {
+        su = VX;
+        sv = VX * VY;
+        vbase = (unsigned long long)mid;
+      }
+      for (int cell = warp; cell < mwords; cell += MCI_NODE_THREADS / 32)
+      {
+        const int r = cell / M.pitch, wi = cell % M.pitch;
+        const int y = M.y0 + r, x = M.x0 + 32 * wi;
+        // 32 bits of the median starting at slice column x
+        const uint32_t * row = Sb + (size_t)(y - uy0) * pitch;
+        int rx = x - ux0; // >= 0
+        int sw = rx >> 5, shf = rx & 31;
+        uint32_t lo = row[sw];
+        uint32_t hi = sw + 1 < pitch ? row[sw + 1] : 0u;
+        uint32_t m = __funnelshift_r(lo, hi, shf);
+        int valid = M.w - 32 * wi;
+        if (valid < 32)
+          m &= (1u << valid) - 1u;
+        if (lane == 0)
+          arena[M.off + cell] = m;
+        if ((m >> lane) & 1u)
+        {
+          unsigned long long a = vbase + (unsigned long long)((long long)(x + lane) * su + (long long)y * sv);
+          if (in[a] == 0)
+            atomic_max_pixel(out + a, label);
+        }
+      }
+    }
+    // ---- children (X:766-792)
+    if (tid == 0 && abs(nd.i - nd.j) > 2)
+    {
+      const bool first = abs(nd.i - mid) > 1, second = abs(nd.j - mid) > 1;
+      int nnew = (first ? 1 : 0) + (second ? 1 : 0);
+      if (nnew)
+      {
+        int pos = atomicAdd(nextCount, nnew);
+        if (pos + nnew > nextCap)
+          atomicMax(err, ERR_NODE_LIST);
+        else
+        {
+          if (first)
+          {
+            Node c;
+            c.A = nd.A;
+            c.B = M;
+            c.tx = iT[0];
+            c.ty = iT[1];
+            c.i = nd.i;
+            c.j = mid;
+            c.axis = nd.axis;
+            c.label = nd.label;
+            next[pos++] = c;
+          }
+          if (second)
+          {
+            Node c;
+            c.A = nd.B;
+            c.B = M;
+            c.tx = jT[0];
+            c.ty = jT[1];
+            c.i = nd.j;
+            c.j = mid;
+            c.axis = nd.axis;
+            c.label = nd.label;
+            next[pos++] = c;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <typename T>
+static void
+launch_nodes_t(Launch & L, const Node * nodes, const int * count, int maxNodes, Node * next, int * nextCount, int nextCap,
+               uint32_t * arena, unsigned long long * arenaTop, unsigned long long arenaCap, const void * in, void * out,
+               const long long dims[3], int useDT, int ball, unsigned * bigHist, uint32_t * slab, unsigned long long slabWords,
+               int grid, int smemBytes, int * err)
+{
+  static bool attr = false;
+  if (!attr)
+  {
+    cudaFuncSetAttribute(k_nodes<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.maxSmem - 1024);
+    attr = true;
+  }
+  int g = std::max(1, std::min(grid, maxNodes));
+  int smemWords = smemBytes / 4 - 2 * MCI_SMALL_HIST;
+  k_nodes<T><<<g, MCI_NODE_THREADS, smemBytes, L.stream>>>(nodes, count, next, nextCount, nextCap, arena, arenaTop, arenaCap,
+                                                          (const T *)in, (T *)out, dims[0], dims[1], dims[2], useDT, ball,
+                                                          bigHist, slab, slabWords, smemWords, err);
+  L.post("k_nodes");
+}
+
+void
+launch_nodes(Launch & L, int ptype, const Node * nodes, const int * count, int maxNodes, Node * next, int * nextCount,
+             int nextCap, uint32_t * arena, unsigned long long * arenaTop, unsigned long long arenaCap, const void * in,
+             void * out, const long long dims[3], int useDT, int ball, unsigned * bigHist, uint32_t * slab,
+             unsigned long long slabWords, int grid, int smemBytes, int * err)
+{
+  if (maxNodes <= 0)
+    return;
+  switch (ptype)
+  {
+    case MCI_U8:
+      launch_nodes_t<uint8_t>(L, nodes, count, maxNodes, next, nextCount, nextCap, arena, arenaTop, arenaCap, in, out, dims,
+                              useDT, ball, bigHist, slab, slabWords, grid, smemBytes, err);
+      break;
+    case MCI_U16:
+      launch_nodes_t<uint16_t>(L, nodes, count, maxNodes, next, nextCount, nextCap, arena, arenaTop, arenaCap, in, out, dims,
+                               useDT, ball, bigHist, slab, slabWords, grid, smemBytes, err);
+      break;
+    default:
+      launch_nodes_t<int16_t>(L, nodes, count, maxNodes, next, nextCount, nextCap, arena, arenaTop, arenaCap, in, out, dims,
+                              useDT, ball, bigHist, slab, slabWords, grid, smemBytes, err);
+  }
+}
+
+} // namespace mci

@@ -1,0 +1,52 @@
+// mci_launch.h -- host-callable launch wrappers of the kernels in mci_kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "mci_types.h"
+#include "../../include/mci_b200.h"
+
+namespace mci
+{
+
+struct Launch
+{
+  cudaStream_t stream;
+  int sms;      // SM count of the device (148 on B200)
+  int maxSmem;  // opt-in dynamic shared memory per CTA
+  int64_t count; // kernels launched so far
+  const char * failedKernel; // first launch that returned an error, if any
+  cudaError_t failedCode;
+  void post(const char * name, int n = 1)
+  {
+    count += n;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess && !failedKernel)
+    {
+      failedKernel = name;
+      failedCode = e;
+    }
+  }
+};
+
+void launch_detect(Launch & L, int ptype, const void * in, void * out, const long long dims[3], int axisSel, int * bbox, int nl,
+                   uint32_t * sliceBits, int wordsPerLabel, int wo1, int wo2);
+void launch_compact_labels(Launch & L, const int * bbox, int nl, const uint32_t * sliceBits, int wordsPerLabel, int wo1, int wo2,
+                           int signedLabels, mci_label_info * labels, mci_labeled_slice * slices, int capSlices, int * counters);
+void launch_cc(Launch & L, int ptype, const void * in, const SliceDev * slices, int nslices, const RowTile * tiles, int ntiles,
+               uint32_t * parent, uint32_t * rootId, uint16_t * conn, int * rowCount, int * ncomp, int * compBase, int * total,
+               CompStat * stats, int statCap, int fully, int * err);
+void launch_pairs(Launch & L, const SliceDev * slices, const SegDev * segs, const RowTile * tiles, int ntiles, const uint16_t * conn,
+                  u64 * table, uint32_t tableMask, mci_pair * pairs, int capPairs, int * nPairs, int * err);
+void launch_extract(Launch & L, const SliceDev * slices, const ExtractJob * jobs, int njobs, const uint16_t * conn, uint32_t * arena);
+void launch_align(Launch & L, const AlignJob * jobs, int njobs, const MaskRef * refs, const uint32_t * arena, uint32_t * gscratch,
+                  int heuristic, int2 * result, int smemBytes, int * err);
+void launch_split(Launch & L, const SplitJob * jobs, int njobs, const MaskRef * refs, uint32_t * arena, uint32_t * gscratch,
+                  const int2 * trans, int ball, int * err);
+void launch_make_roots(Launch & L, const RootJob * roots, int nroots, MaskRef * refs, uint32_t * arena, const int2 * trans,
+                       Node * nodes);
+void launch_nodes(Launch & L, int ptype, const Node * nodes, const int * count, int maxNodes, Node * next, int * nextCount,
+                  int nextCap, uint32_t * arena, unsigned long long * arenaTop, unsigned long long arenaCap, const void * in,
+                  void * out, const long long dims[3], int useDT, int ball, unsigned * bigHist, uint32_t * slab,
+                  unsigned long long slabWords, int grid, int smemBytes, int * err);
+
+} // namespace mci

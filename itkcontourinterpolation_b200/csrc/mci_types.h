@@ -1,0 +1,139 @@
+// mci_types.h -- POD records shared by the host side of the library and its kernels.
+// Vocabulary follows the reference: slice = 2-D cross-section perpendicular to an
+// axis; segment = (axis, label, slice i, slice j); job = one Align + interpolation tree;
+// node = one Interpolate1to1 call (reference X:556-793).
+#pragma once
+#include <stdint.h>
+
+namespace mci
+{
+
+typedef unsigned long long u64;
+
+// A bit-packed 2-D mask living in the mask arena.  Pixel (x, y) of the slice, with
+// x0 <= x < x0+w and y0 <= y < y0+h, is bit ((x-x0)&31) of word off + (y-y0)*pitch + ((x-x0)>>5).
+// Bits at or beyond w in the last word of a row are always 0.
+struct MaskRef
+{
+  int x0, y0, w, h;
+  int pitch; // 32-bit words per row
+  int pad;
+  u64 off; // word offset in the arena
+};
+
+// One annotated slice of the batch handed to mci_label_slices.
+struct SliceDev
+{
+  int axis, slice, label;
+  int u0, v0, w, h;
+  int rowOff;    // offset into per-row arrays
+  u64 pixOff;    // offset into per-pixel arrays (parent, root id, component image)
+  u64 base;      // voxel index of slice pixel (u0, v0)
+  long long su, sv; // voxel strides of u and v
+};
+
+// A tile of rows of one slice (CC kernels) or one segment (pair kernel).
+struct RowTile
+{
+  int item; // slice index or segment index
+  int row0, nrows;
+};
+
+struct SegDev
+{
+  int si, sj; // slice indices
+};
+
+struct CompStat
+{
+  long long count;
+  long long sumU, sumV;
+  int minU, minV, maxU, maxV;
+};
+
+struct ExtractJob
+{
+  int slice, id;
+  MaskRef m;
+};
+
+enum
+{
+  JOB_ONE_TO_ONE = 0,
+  JOB_ONE_TO_N = 1,
+  JOB_EXTRAPOLATE = 2
+};
+
+struct AlignJob
+{
+  int kind;
+  int nB;
+  int aRef; // index into the MaskRef table
+  int bRef; // first of nB consecutive MaskRefs
+  int indx, indy; // centroid offset (second BFS seed)
+  int sx0, sy0, sw, sh; // search region of translations
+  int phx, phy; // phantom pixel (EXTRAPOLATE)
+  int qcap; // ring capacity (power of two)
+  int useSmem;
+  long long minIter, maxIter;
+  u64 bitmapOff; // global scratch (words) when !useSmem
+  u64 queueOff;  // global scratch (words) when !useSmem: qcap*3 words
+};
+
+struct SplitJob
+{
+  int job;     // index of the AlignJob whose translation is used
+  int aRef;    // mask being split
+  int nB, bRef;
+  int outRef;  // first of nB output MaskRefs (geometry of A)
+  int pad;
+  u64 scratchOff; // nB planes of A.h*A.pitch words (ping-pong buffer)
+};
+
+// One Interpolate1to1 call: shapes A (slice position i) and B (slice position j), with
+// translation t such that pixel p of A corresponds to pixel p+t of B (reference X:556-568).
+struct Node
+{
+  MaskRef A, B;
+  int tx, ty;
+  int i, j;
+  int axis, label;
+};
+
+struct RootJob
+{
+  int kind;
+  int job;     // AlignJob index
+  int aRef, bRef, nB;
+  int splitRef; // ONE_TO_N: first of nB split masks
+  int posA, posB;
+  int axis, label;
+  int rootOff; // index of the first root node written
+  int phRef;   // EXTRAPOLATE: MaskRef slot (1 word) for the phantom
+  int phx, phy;
+};
+
+struct VolDev
+{
+  long long X, Y, Z;
+};
+
+struct DevParams
+{
+  int heuristic, useDT, useBall;
+};
+
+enum
+{
+  ERR_NONE = 0,
+  ERR_ARENA = 1,
+  ERR_NODE_LIST = 2,
+  ERR_PAIR_TABLE = 3,
+  ERR_COMPONENTS = 4,
+  ERR_PIXELTYPE = 5,
+  ERR_QUEUE = 6,
+  ERR_SCRATCH = 7,
+  ERR_SPLIT_STUCK = 8
+};
+
+} // namespace mci

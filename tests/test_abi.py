@@ -1,0 +1,70 @@
+"""The C-ABI shared library: builds, loads, exports every symbol include/mci_b200.h declares, and
+refuses to run without a GPU (no CPU fallback).  No compute calls here.  CPU only."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from itkcontourinterpolation_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "mci_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mci_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    lib = L.lib()
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), "libmci_b200.so does not export " + n
+    bound = sorted(s[0] for s in L.SYMBOLS)
+    assert bound == names, "ctypes binding and header disagree"
+
+
+def test_struct_layouts_match_header_sizes():
+    assert ctypes.sizeof(L.LabelInfo) == 32
+    assert ctypes.sizeof(L.LabeledSlice) == 16
+    assert ctypes.sizeof(L.SliceDesc) == 32
+    assert ctypes.sizeof(L.ComponentInfo) == 40
+    assert ctypes.sizeof(L.Pair) == 8
+    assert ctypes.sizeof(L.Job) == 32
+    assert ctypes.sizeof(L.Params) == 20
+    assert ctypes.sizeof(L.FilterOptions) == 32
+    assert ctypes.sizeof(L.FilterStats) == 14 * 8
+
+
+def test_default_options_mirror_reference_defaults():
+    # H:229-235: label 0, axis -1, heuristic on, distance transform on, cross SE, auto slices, extrapolation on
+    o = L.FilterOptions()
+    L.lib().mci_filter_default_options(ctypes.byref(o))
+    assert (o.label, o.axis, o.heuristic_alignment, o.use_distance_transform, o.use_ball_structuring_element,
+            o.use_custom_slice_positions, o.use_extrapolation) == (0, -1, 1, 1, 0, 0, 1)
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    ctx = ctypes.c_void_p()
+    rc = L.lib().mci_create(ctypes.byref(ctx), 0)
+    assert rc != 0 and not ctx
+    from itkcontourinterpolation_b200 import MorphologicalContourInterpolator
+    with pytest.raises(L.MciError):
+        MorphologicalContourInterpolator()
+
+
+def test_product_does_not_reference_the_oracle():
+    pkg = os.path.join(ROOT, "itkcontourinterpolation_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "_build" in dirpath or "__pycache__" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower() or f == "synthetic.py", f

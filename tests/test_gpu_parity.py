@@ -1,0 +1,197 @@
+"""Parity of the CUDA path against the oracle, through the C ABI (ctypes -> libmci_b200.so).
+Bit-exact: integer / label work, no tolerance.  Needs a B200: pytest -m gpu."""
+import ctypes
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from itkcontourinterpolation_b200 import MorphologicalContourInterpolator, _lib as L
+from itkcontourinterpolation_b200.synthetic import make_config
+from oracle import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+GOLD = json.load(open(os.path.join(cases.GOLDEN, "golden.json")))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def flt():
+    f = MorphologicalContourInterpolator(0)
+    yield f
+    f.close()
+
+
+def run_gpu(f, vol, label=0, axis=-1, use_distance_transform=True, use_ball=False, heuristic=True, extrapolation=True):
+    f.SetLabel(label)
+    f.SetAxis(axis)
+    f.SetUseDistanceTransform(use_distance_transform)
+    f.SetUseBallStructuringElement(use_ball)
+    f.SetHeuristicAlignment(heuristic)
+    f.SetUseExtrapolation(extrapolation)
+    f.SetUseCustomSlicePositions(False)
+    f.SetInput(vol)
+    return f.Update()
+
+
+def assert_same(gpu, ref, what):
+    if not np.array_equal(gpu, ref):
+        bad = np.argwhere(gpu != ref)
+        z, y, x = bad[0]
+        raise AssertionError("%s: %d voxels differ, first at (x=%d,y=%d,z=%d): gpu=%d oracle=%d" %
+                             (what, len(bad), x, y, z, gpu[z, y, x], ref[z, y, x]))
+
+
+def test_loaded_native_library_is_the_in_tree_one(flt):
+    assert os.path.abspath(L.library_path()).startswith(os.path.dirname(os.path.abspath(L.__file__)))
+    maps = open("/proc/self/maps").read()
+    assert "libmci_b200.so" in maps
+
+
+@pytest.mark.parametrize("algo", sorted(cases.ALGOS))
+def test_fixtures_and_handcrafted_all_algorithms(flt, seven_labels, many_to_many, algo):
+    kw = cases.ALGOS[algo]
+    inputs = {"SevenLabels": seven_labels, "ManyToMany": many_to_many, "SevenLabels_u8": seven_labels.astype(np.uint8)}
+    inputs.update(cases.handcrafted())
+    for name, vol in inputs.items():
+        out = run_gpu(flt, vol, **kw)
+        assert sha(out) == GOLD["%s_%s" % (name, algo)]["output"], (name, algo)
+        assert_same(out, O.interpolate(vol, **kw), "%s_%s" % (name, algo))
+
+
+def test_synthetic_small_configs(flt):
+    for name, (vol, cfg) in cases.synthetic_small().items():
+        out = run_gpu(flt, vol, axis=cfg.get("axis", -1), use_distance_transform=cfg["use_dt"], use_ball=cfg["ball"])
+        assert sha(out) == GOLD["synthetic_%s" % name]["output"], name
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_axis_restriction(flt, axis):
+    vol = cases.handcrafted()["ThreeAxis"]
+    assert_same(run_gpu(flt, vol, axis=axis), O.interpolate(vol, axis=axis), "ThreeAxis axis %d" % axis)
+    vol, _ = cases.synthetic_small()["C4"]
+    assert_same(run_gpu(flt, vol, axis=axis, use_distance_transform=False, use_ball=True),
+                O.interpolate(vol, axis=axis, use_distance_transform=False, use_ball=True), "C4 axis %d" % axis)
+
+
+def test_label_restriction(flt, seven_labels):
+    for label in (3, 5, 200):
+        assert_same(run_gpu(flt, seven_labels, label=label), O.interpolate(seven_labels, label=label), "label %d" % label)
+
+
+def test_no_extrapolation_and_exhaustive_alignment(flt):
+    h = cases.handcrafted()
+    for name in ("ExtrapolationAppearing", "RingExtrapolate", "OneToThree", "DriftOddGaps"):
+        v = h[name]
+        assert_same(run_gpu(flt, v, extrapolation=False), O.interpolate(v, use_extrapolation=False), name + " noextrap")
+        assert_same(run_gpu(flt, v, heuristic=False), O.interpolate(v, heuristic_alignment=False), name + " exhaustive")
+
+
+def test_int16_and_uint8_pixel_types(flt):
+    h = cases.handcrafted()
+    for name in ("SimplestOneToOne", "OneToThree", "TwoAxisTwoLabel"):
+        for dt in (np.int16, np.uint8):
+            v = h[name].astype(dt)
+            for kw in cases.ALGOS.values():
+                assert_same(run_gpu(flt, v, **kw), O.interpolate(v, **kw), "%s %s" % (name, dt.__name__))
+
+
+def test_int16_distance_bin_overflow_fails_cleanly(flt):
+    # d2 >= 3277 makes `short dist = 10 * sdf` negative: the reference indexes out of bounds (X:431-437);
+    # both the oracle and the CUDA path report an error instead
+    v = np.zeros((9, 60, 230), np.int16)
+    v[0, 2:58, 2:228] = 1
+    v[8, 28:32, 110:116] = 1
+    with pytest.raises(O.OracleError):
+        O.interpolate(v)
+    with pytest.raises(L.MciError):
+        run_gpu(flt, v)
+    # the context stays usable
+    w = cases.handcrafted()["SimplestOneToOne"]
+    assert_same(run_gpu(flt, w), O.interpolate(w), "after error")
+
+
+def test_empty_and_no_slices_identity(flt):
+    h = cases.handcrafted()
+    for name in ("Empty", "NoSlices"):
+        assert np.array_equal(run_gpu(flt, h[name]), h[name])
+    one = np.zeros((1, 1, 1), np.uint16)
+    assert np.array_equal(run_gpu(flt, one), one)
+    odd = np.zeros((3, 5, 7), np.uint16)
+    odd[:, 2, 3] = 4
+    assert_same(run_gpu(flt, odd), O.interpolate(odd), "odd sizes")
+
+
+def test_custom_slice_positions(flt, many_to_many):
+    flt.SetLabel(0); flt.SetAxis(-1); flt.SetUseDistanceTransform(True); flt.SetUseBallStructuringElement(False)
+    flt.SetHeuristicAlignment(True); flt.SetUseExtrapolation(True)
+    flt.ClearLabeledSliceIndices()
+    flt.SetLabeledSliceIndices(2, 1, [0, 7])
+    flt.SetUseCustomSlicePositions(True)
+    flt.SetInput(many_to_many)
+    out = flt.Update()
+    flt.SetUseCustomSlicePositions(False)
+    assert_same(out, O.interpolate(many_to_many, custom_slices=[(2, 1, 0), (2, 1, 7)]), "custom positions")
+
+
+def test_slice_detection_phase(flt):
+    vol, _ = cases.synthetic_small()["C4"]
+    flt.SetAxis(-1); flt.SetLabel(0); flt.SetUseCustomSlicePositions(False)
+    flt.SetInput(vol)
+    table = flt.DetermineSliceOrientations()
+    got = set((a, l, s) for a, d in table.items() for l, ss in d.items() for s in ss)
+    trip, _ = O.detect(vol)
+    assert got == set(map(tuple, trip.tolist()))
+
+
+def test_connected_components_phase_raster_numbering(flt):
+    # phase-level ABI: component images must equal the oracle's (ITK numbering), 4- and 8-connected
+    rng = np.random.default_rng(5)
+    vol = np.zeros((3, 70, 90), np.uint16)
+    vol[1] = (rng.random((70, 90)) < 0.55) * 7
+    lib = L.lib()
+    dims = (ctypes.c_int64 * 3)(90, 70, 3)
+    ctx = flt._ctx
+    assert lib.mci_upload_volume(ctx, vol.ctypes.data, dims, L.U16) == 0
+    for fully in (0, 1):
+        desc = (L.SliceDesc * 1)(L.SliceDesc(2, 1, 7, 0, 0, 90, 70))
+        n = (ctypes.c_int32 * 1)()
+        assert lib.mci_label_slices(ctx, 1, desc, fully, n) == 0
+        ids = np.zeros((70, 90), np.uint16)
+        assert lib.mci_get_component_image(ctx, 0, ids.ctypes.data) == 0
+        ref, nref = O.cc2d(vol[1] == 7, bool(fully))
+        assert n[0] == nref
+        assert np.array_equal(ids, ref)
+        info = (L.ComponentInfo * n[0])()
+        assert lib.mci_get_components(ctx, info) == 0
+        for k in range(n[0]):
+            yy, xx = np.nonzero(ref == k + 1)
+            assert (info[k].count, info[k].sum_u, info[k].sum_v) == (len(xx), xx.sum(), yy.sum())
+            assert (info[k].min_u, info[k].max_u, info[k].min_v, info[k].max_v) == (xx.min(), xx.max(), yy.min(), yy.max())
+
+
+def test_full_size_c3_against_oracle_and_invariants(flt):
+    # BASELINE.json configs[2]: 512x512x256 uint16, 20 labels, every 8th z-slice, DT, axis 2
+    vol, dense, cfg = make_config("C3")
+    out = run_gpu(flt, vol, axis=2)
+    assert np.array_equal(out[vol != 0], vol[vol != 0])          # output contains input (X:1623-1636)
+    assert set(np.unique(out)) <= set(np.unique(vol))            # no new labels
+    ann = np.arange(0, vol.shape[0], 8)
+    assert np.array_equal(out[ann], vol[ann])                    # annotated slices untouched
+    assert (out != 0).sum() > 4 * (vol != 0).sum()               # the gaps were filled
+    assert_same(out, O.interpolate(vol, axis=2, threads=os.cpu_count() or 1), "C3 full size")
+    again = run_gpu(flt, out, axis=2)                            # a dense input: few or no isolated slices left
+    assert_same(again, O.interpolate(out, axis=2, threads=os.cpu_count() or 1), "C3 second pass")
+
+
+def test_ball_dilation_medium(flt):
+    vol, _, cfg = make_config("C4", 0.25)
+    out = run_gpu(flt, vol, use_distance_transform=False, use_ball=True)
+    assert_same(out, O.interpolate(vol, use_distance_transform=False, use_ball=True, threads=os.cpu_count() or 1), "C4/4 ball")

@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the slice-pair interpolation path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload C3|C4|C5] [--scale S]
+
+One "step" = one GenerateData-equivalent (slice detection, connected components, component matching,
+Align, 1-to-N splits, every level of the Interpolate1to1 recursion, output composition) on one synthetic
+sparse-annotated label volume.  Metric: interpolated Mvoxel/s per label-volume = X*Y*Z / time.
+
+  value : volume already resident in HBM, result left in HBM (mci_filter_run_resident)
+  e2e   : through the reference-facing call with HOST buffers (mci_filter_run: pinned host in -> pinned host out),
+          H2D and D2H copies inside the timed region
+
+N > 1 (torchrun, one rank per GPU): the path partitions into independent label volumes, one per GPU, no
+data-path collective; value = voxels all ranks processed / max-over-ranks time; scaling "weak".
+--impl reference times the CPU restatement of the reference (oracle/, all host threads) on rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from itkcontourinterpolation_b200.synthetic import make_config  # noqa: E402
+
+WORKLOAD_DESC = {
+    "C3": "synthetic 512x512x256 uint16, 20 labels annotated every 8th z-slice, UseDistanceTransform=on, axis 2",
+    "C4": "synthetic 1024x1024x512 uint16, 20 labels annotated sparsely along 3 axes, ball dilations",
+    "C5": "synthetic 2048x2048x1024 uint16, 200 labels annotated every 8th z-slice, UseDistanceTransform=on, axis 2",
+}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_time(vol, cfg, threads, runs):
+    from oracle import oracle_lib as O
+    times, out = [], None
+    for _ in range(runs + 1):  # first run = warm-up
+        t0 = time.perf_counter()
+        out = O.interpolate(vol, axis=cfg["axis"], use_distance_transform=cfg["use_dt"], use_ball=cfg["ball"], threads=threads)
+        times.append(time.perf_counter() - t0)
+    return statistics.median(times[1:]), out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C3", choices=["C3", "C4", "C5"])
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--no-check", action="store_true", help="skip the bit-exact check against the oracle before timing")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_gpus = max(args.gpus, world)
+
+    vol, _, cfg = make_config(args.workload, args.scale)
+    if rank > 0:  # every rank owns a different label volume of the same shape
+        from itkcontourinterpolation_b200.synthetic import ellipsoid_volume, sparsify
+        vol = sparsify(ellipsoid_volume(cfg["dims"], cfg["n_labels"], cfg["seed"] + 1000 * rank, cfg["semi_axes"]), cfg["nth"])
+    nvox = int(vol.size)
+    cores = os.cpu_count() or 1
+    config = {"workload": "%s: %s" % (args.workload, WORKLOAD_DESC[args.workload]), "dims": list(cfg["dims"]),
+              "labels": cfg["n_labels"], "annotated_every": list(cfg["nth"]), "axis": cfg["axis"],
+              "use_distance_transform": bool(cfg["use_dt"]), "ball": bool(cfg["ball"]), "seed": cfg["seed"],
+              "l2_policy": "inputs larger than L2 (volume in+out = %d MB per step)" % (2 * vol.nbytes // 2 ** 20)}
+
+    if args.impl == "reference":
+        # the reference's own CPU implementation cannot be built here (needs ITK 5.4); its restatement (oracle/)
+        # runs on all host cores, rank 0 only
+        if rank != 0:
+            return 0
+        from oracle import oracle_lib as O
+        kw = dict(axis=cfg["axis"], use_distance_transform=cfg["use_dt"], use_ball=cfg["ball"], threads=cores)
+        for _ in range(args.warmup):
+            O.interpolate(vol, **kw)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.interpolate(vol, **kw)
+        dt = (time.perf_counter() - t0) / args.steps
+        v = nvox / dt / 1e6
+        line = {"impl": "reference", "metric": "interpolated Mvoxel/s per label-volume", "value": v, "unit": "Mvoxel/s",
+                "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": "Mvoxel/s", "cores": cores, "kind": "port",
+                                 "sample": "full %s volume per step, %d steps" % (args.workload, args.steps)},
+                "e2e": {"value": v, "unit": "Mvoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from itkcontourinterpolation_b200 import _lib as L
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    lib = L.lib()
+    ctx = ctypes.c_void_p()
+    rc = lib.mci_create(ctypes.byref(ctx), local_rank)
+    if rc:
+        raise SystemExit("mci_create failed: %d" % rc)
+
+    def check(rc):
+        if rc:
+            raise SystemExit("mci error %d: %s" % (rc, lib.mci_last_error(ctx).decode()))
+
+    opt = L.FilterOptions()
+    lib.mci_filter_default_options(ctypes.byref(opt))
+    opt.axis = cfg["axis"]
+    opt.use_distance_transform = int(cfg["use_dt"])
+    opt.use_ball_structuring_element = int(cfg["ball"])
+    dims = (ctypes.c_int64 * 3)(*cfg["dims"])
+    nbytes = vol.nbytes
+    h_in = lib.mci_host_alloc(nbytes)
+    h_out = lib.mci_host_alloc(nbytes)
+    ctypes.memmove(h_in, vol.ctypes.data, nbytes)
+    stats = L.FilterStats()
+
+    # ---- correctness first: bit-exact against the oracle (rank 0 also times the oracle = cpu_baseline)
+    check(lib.mci_filter_run(ctx, ctypes.byref(opt), h_in, h_out, dims, L.U16, None, 0, ctypes.byref(stats)))
+    gpu_out = np.ctypeslib.as_array(ctypes.cast(h_out, ctypes.POINTER(ctypes.c_uint16)), shape=vol.shape).copy()
+    cpu_baseline = None
+    if rank == 0:
+        runs = 3 if args.workload == "C3" and args.scale <= 1.0 else 1
+        t_cpu, ref = oracle_time(vol, cfg, cores, runs)
+        if not args.no_check and not np.array_equal(ref, gpu_out):
+            raise SystemExit("GPU output differs from the oracle in %d voxels -- no number reported" % int((ref != gpu_out).sum()))
+        cpu_baseline = {"value": nvox / t_cpu / 1e6, "unit": "Mvoxel/s", "cores": cores, "kind": "port",
+                        "sample": "full %s volume, 1 warm-up + %d timed runs (median), restated reference, baseline only"
+                                  % (args.workload, runs)}
+    job_stats = stats.as_dict()
+
+    stream = torch.cuda.ExternalStream(lib.mci_stream(ctx), device=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        for _ in range(args.warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as cs:
+            e0.record(stream)
+            for _ in range(args.steps):
+                fn()
+            e1.record(stream)
+            e1.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / args.steps, cs.summary()
+
+    # ---- value: volume resident in HBM
+    check(lib.mci_upload_volume(ctx, h_in, dims, L.U16))
+    check(lib.mci_synchronize(ctx))
+
+    def step_resident():
+        check(lib.mci_filter_run_resident(ctx, ctypes.byref(opt), None, 0, ctypes.byref(stats)))
+
+    check(lib.mci_profile_enable(ctx, 1))
+    l0 = lib.mci_launch_count(ctx)
+    ms_res, clocks = timed(step_resident)
+    launches = (lib.mci_launch_count(ctx) - l0) // (args.steps + args.warmup)
+    kt = (L.KernelTime * 64)()
+    nk = ctypes.c_int32(0)
+    check(lib.mci_profile_read(ctx, kt, 64, ctypes.byref(nk)))
+    check(lib.mci_profile_enable(ctx, 0))
+    kernels = {kt[k].name.decode(): (int(kt[k].launches), float(kt[k].total_ms)) for k in range(min(nk.value, 64))}
+    total_kernel_ms = sum(v[1] for v in kernels.values()) or 1.0
+
+    # ---- e2e: host buffers through the reference-facing call
+    def step_e2e():
+        check(lib.mci_filter_run(ctx, ctypes.byref(opt), h_in, h_out, dims, L.U16, None, 0, ctypes.byref(stats)))
+
+    ms_e2e, clocks_e2e = timed(step_e2e)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        # dominant kernel = largest share of device time; the HBM-streaming kernel of this path is k_detect_copy
+        # (reads every input voxel once, writes every output voxel once: 2*s*N algorithmic bytes per launch)
+        dom = max(kernels.items(), key=lambda kv: kv[1][1])[0] if kernels else None
+        table = {k: {"launches_per_step": v[0] / float(args.steps + args.warmup), "ms_per_step": v[1] / (args.steps + args.warmup),
+                     "share": v[1] / total_kernel_ms} for k, v in sorted(kernels.items(), key=lambda kv: -kv[1][1])}
+        roof = None
+        if "k_detect_copy" in kernels:
+            n_l, t_ms = kernels["k_detect_copy"]
+            avg_ms = t_ms / n_l
+            alg = 2.0 * vol.itemsize * nvox
+            achieved = alg / (avg_ms * 1e-3) / 1e9
+            traffic = None
+            prof = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(prof):
+                try:
+                    traffic = json.load(open(prof)).get("k_detect_copy", {}).get("dram_bytes_per_launch")
+                except Exception:
+                    traffic = None
+            roof = {"bound": "hbm", "kernel": "k_detect_copy", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                    "avg_launch_ms": avg_ms, "dominant_kernel_by_time": dom,
+                    "whole_step_frac": alg / (ms_res * 1e-3) / 1e9 / peak}
+        line = {"metric": "interpolated Mvoxel/s per label-volume", "value": world * nvox / (ms_res * 1e-3) / 1e6, "unit": "Mvoxel/s", "n_gpus": n_gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u16", "data": "synthetic", "config": config, "clocks": clocks,
+                "e2e": {"value": world * nvox / (ms_e2e * 1e-3) / 1e6, "unit": "Mvoxel/s", "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "clocks": clocks_e2e},
+                "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches), "roofline": roof,
+                "cpu_baseline": cpu_baseline, "kernels": table,
+                "job": {k: job_stats[k] for k in ("n_labels", "n_annotated_slices", "n_segments", "n_pairs", "n_jobs", "n_components")},
+                "bit_exact_vs_oracle": (not args.no_check)}
+        print(json.dumps(line))
+    lib.mci_host_free(h_in)
+    lib.mci_host_free(h_out)
+    lib.mci_destroy(ctx)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -53,6 +53,15 @@ int64_t mci_launch_count(const mci_ctx * ctx);
 /* CUDA stream the context launches on (cudaStream_t as void*), for callers that time with events */
 void * mci_stream(const mci_ctx * ctx);
 int mci_synchronize(mci_ctx * ctx);
+/* per-kernel device times, CUDA events recorded on the launching stream around every launch while enabled */
+typedef struct
+{
+  char name[32];
+  int64_t launches;
+  double total_ms;
+} mci_kernel_time;
+int mci_profile_enable(mci_ctx * ctx, int on);
+int mci_profile_read(mci_ctx * ctx, mci_kernel_time * out, int32_t cap, int32_t * n);
 
 /* ---- volume ------------------------------------------------------------------------------- */
 /* Replaces GetInput()/AllocateOutputs() (X:1541-1565).  dims = {X, Y, Z}, X fastest.

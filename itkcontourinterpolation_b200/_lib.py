@@ -60,6 +60,10 @@ class FilterOptions(ctypes.Structure):
                 ("use_custom_slice_positions", ctypes.c_int32), ("use_extrapolation", ctypes.c_int32)]
 
 
+class KernelTime(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 32), ("launches", ctypes.c_int64), ("total_ms", ctypes.c_double)]
+
+
 class FilterStats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int64) for n in ("n_labels", "n_annotated_slices", "n_segments", "n_pairs", "n_jobs",
                                                "n_components", "n_launches")] + \
@@ -82,6 +86,8 @@ SYMBOLS = [
     ("mci_launch_count", ctypes.c_int64, [_P]),
     ("mci_stream", _P, [_P]),
     ("mci_synchronize", _I, [_P]),
+    ("mci_profile_enable", _I, [_P, _I]),
+    ("mci_profile_read", _I, [_P, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
     ("mci_upload_volume", _I, [_P, _P, ctypes.POINTER(ctypes.c_int64), _I]),
     ("mci_attach_device_volume", _I, [_P, _P, _P, ctypes.POINTER(ctypes.c_int64), _I]),
     ("mci_download_volume", _I, [_P, _P]),

@@ -180,6 +180,8 @@ check_device_error(mci_ctx * ctx)
   return h == ERR_PIXELTYPE ? MCI_ERR_PIXELTYPE : MCI_ERR_CAPACITY;
 }
 
+static void recycle_events(mci_ctx * ctx);
+
 extern "C"
 {
 
@@ -205,6 +207,7 @@ extern "C"
     ctx->L.count = 0;
     ctx->L.failedKernel = nullptr;
     ctx->L.failedCode = cudaSuccess;
+    ctx->L.profile = false;
     if (cudaMalloc((void **)&ctx->dErr, sizeof(int)) != cudaSuccess)
     {
       delete ctx;
@@ -229,6 +232,9 @@ extern "C"
                       &ctx->dNodes,    &ctx->dLevelCounts, &ctx->dArenaTop, &ctx->dTrans };
     for (DBuf * b : bufs)
       b->release();
+    recycle_events(ctx);
+    for (cudaEvent_t e : ctx->L.pool)
+      cudaEventDestroy(e);
     ctx->hStage.release();
     cudaFree(ctx->dErr);
     cudaStreamDestroy(ctx->L.stream);
@@ -257,6 +263,64 @@ extern "C"
       return MCI_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     return check_device_error(ctx);
+  }
+
+} // extern C (helper below has C++ linkage)
+static void recycle_events(mci_ctx * ctx)
+  {
+    for (auto & r : ctx->L.recs)
+    {
+      ctx->L.pool.push_back(r.a);
+      ctx->L.pool.push_back(r.b);
+    }
+    ctx->L.recs.clear();
+  }
+extern "C"
+{
+
+  int mci_profile_enable(mci_ctx * ctx, int on)
+  {
+    if (!ctx)
+      return MCI_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->L.stream));
+    recycle_events(ctx);
+    ctx->L.profile = on != 0;
+    return MCI_OK;
+  }
+
+  int mci_profile_read(mci_ctx * ctx, mci_kernel_time * out, int32_t cap, int32_t * n)
+  {
+    if (!ctx || !n || (cap > 0 && !out))
+      return MCI_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->L.stream));
+    std::map<std::string, std::pair<int64_t, double>> agg;
+    for (auto & r : ctx->L.recs)
+    {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess)
+      {
+        auto & e = agg[r.name];
+        e.first += 1;
+        e.second += ms;
+      }
+    }
+    recycle_events(ctx);
+    int k = 0;
+    for (auto & kv : agg)
+    {
+      if (k < cap)
+      {
+        std::memset(out[k].name, 0, sizeof(out[k].name));
+        std::strncpy(out[k].name, kv.first.c_str(), sizeof(out[k].name) - 1);
+        out[k].launches = kv.second.first;
+        out[k].total_ms = kv.second.second;
+      }
+      ++k;
+    }
+    *n = k;
+    return MCI_OK;
   }
 
   // ---- volume ---------------------------------------------------------------------------------

@@ -179,14 +179,17 @@ launch_detect(Launch & L, int ptype, const void * in, void * out, const long lon
   switch (ptype)
   {
     case MCI_U8:
+      L.pre();
       k_detect_copy<uint8_t><<<grid, 256, 0, L.stream>>>((const uint8_t *)in, (uint8_t *)out, dims[0], dims[1], dims[2], axisSel,
                                                          bbox, nl, sliceBits, wordsPerLabel, wo1, wo2);
       break;
     case MCI_U16:
+      L.pre();
       k_detect_copy<uint16_t><<<grid, 256, 0, L.stream>>>((const uint16_t *)in, (uint16_t *)out, dims[0], dims[1], dims[2],
                                                           axisSel, bbox, nl, sliceBits, wordsPerLabel, wo1, wo2);
       break;
     default:
+      L.pre();
       k_detect_copy<int16_t><<<grid, 256, 0, L.stream>>>((const int16_t *)in, (int16_t *)out, dims[0], dims[1], dims[2], axisSel,
                                                          bbox, nl, sliceBits, wordsPerLabel, wo1, wo2);
   }
@@ -197,6 +200,7 @@ void
 launch_compact_labels(Launch & L, const int * bbox, int nl, const uint32_t * sliceBits, int wordsPerLabel, int wo1, int wo2,
                       int signedLabels, mci_label_info * labels, mci_labeled_slice * slices, int capSlices, int * counters)
 {
+  L.pre();
   k_compact_labels<<<(nl + 255) / 256, 256, 0, L.stream>>>(bbox, nl, sliceBits, wordsPerLabel, wo1, wo2, signedLabels, labels,
                                                           slices, capSlices, counters);
   L.post("k_compact_labels");
@@ -520,23 +524,41 @@ launch_cc(Launch & L, int ptype, const void * in, const SliceDev * slices, int n
   switch (ptype)
   {
     case MCI_U8:
+      L.pre();
       k_cc_init<uint8_t><<<ntiles, 256, 0, L.stream>>>((const uint8_t *)in, slices, tiles, parent);
       break;
     case MCI_U16:
+      L.pre();
       k_cc_init<uint16_t><<<ntiles, 256, 0, L.stream>>>((const uint16_t *)in, slices, tiles, parent);
       break;
     default:
+      L.pre();
       k_cc_init<int16_t><<<ntiles, 256, 0, L.stream>>>((const int16_t *)in, slices, tiles, parent);
   }
+  L.post("k_cc_init");
+  L.pre();
   k_cc_merge<<<ntiles, 256, 0, L.stream>>>(slices, tiles, parent, fully);
+  L.post("k_cc_merge");
+  L.pre();
   k_cc_flatten<<<ntiles, 256, 0, L.stream>>>(slices, tiles, parent, rowCount);
+  L.post("k_cc_flatten");
+  L.pre();
   k_cc_rowscan<<<nslices, 256, 0, L.stream>>>(slices, rowCount, ncomp);
+  L.post("k_cc_rowscan");
   int maxPer = ptype == MCI_U8 ? 255 : (ptype == MCI_U16 ? 65535 : 32767);
+  L.pre();
   k_cc_base<<<1, 256, 0, L.stream>>>(ncomp, nslices, compBase, total, statCap, maxPer, err);
+  L.post("k_cc_base");
+  L.pre();
   k_stats_init<<<std::max(1, std::min(L.sms * 4, (statCap + 255) / 256)), 256, 0, L.stream>>>(stats, total, statCap);
+  L.post("k_stats_init");
+  L.pre();
   k_cc_assign<<<ntiles, 256, 0, L.stream>>>(slices, tiles, parent, rowCount, rootId);
+  L.post("k_cc_assign");
+  L.pre();
   k_cc_write<<<ntiles, 256, 0, L.stream>>>(slices, tiles, parent, rootId, compBase, statCap, conn, stats);
-  L.post("k_cc_*", 8);
+  L.post("k_cc_write");
+
 }
 
 // ================================================================================================
@@ -607,6 +629,7 @@ launch_pairs(Launch & L, const SliceDev * slices, const SegDev * segs, const Row
 {
   if (ntiles == 0)
     return;
+  L.pre();
   k_pairs<<<ntiles, 256, 0, L.stream>>>(slices, segs, tiles, conn, table, tableMask, pairs, capPairs, nPairs, err);
   L.post("k_pairs");
 }
@@ -643,6 +666,7 @@ launch_extract(Launch & L, const SliceDev * slices, const ExtractJob * jobs, int
 {
   if (njobs == 0)
     return;
+  L.pre();
   k_extract<<<njobs, 256, 0, L.stream>>>(slices, jobs, conn, arena);
   L.post("k_extract");
 }
@@ -816,6 +840,7 @@ launch_align(Launch & L, const AlignJob * jobs, int njobs, const MaskRef * refs,
     attr = true;
   }
   int grid = std::min(njobs, L.sms * 8);
+  L.pre();
   k_align<<<grid, 256, smemBytes, L.stream>>>(jobs, njobs, refs, arena, gscratch, heuristic, result, err);
   L.post("k_align");
 }
@@ -901,6 +926,7 @@ launch_split(Launch & L, const SplitJob * jobs, int njobs, const MaskRef * refs,
 {
   if (njobs == 0)
     return;
+  L.pre();
   k_split<<<njobs, 256, 0, L.stream>>>(jobs, refs, arena, gscratch, trans, ball, err);
   L.post("k_split");
 }
@@ -974,6 +1000,7 @@ launch_make_roots(Launch & L, const RootJob * roots, int nroots, MaskRef * refs,
 {
   if (nroots == 0)
     return;
+  L.pre();
   k_make_roots<<<(nroots + 127) / 128, 128, 0, L.stream>>>(roots, nroots, refs, arena, trans, nodes);
   L.post("k_make_roots");
 }
@@ -1755,6 +1782,7 @@ launch_nodes_t(Launch & L, const Node * nodes, const int * count, int maxNodes, 
   }
   int g = std::max(1, std::min(grid, maxNodes));
   int smemWords = smemBytes / 4 - 2 * MCI_SMALL_HIST;
+  L.pre();
   k_nodes<T><<<g, MCI_NODE_THREADS, smemBytes, L.stream>>>(nodes, count, next, nextCount, nextCap, arena, arenaTop, arenaCap,
                                                           (const T *)in, (T *)out, dims[0], dims[1], dims[2], useDT, ball,
                                                           bigHist, slab, slabWords, smemWords, err);

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <vector>
 #include "mci_types.h"
 #include "../../include/mci_b200.h"
 
@@ -16,9 +17,48 @@ struct Launch
   int64_t count; // kernels launched so far
   const char * failedKernel; // first launch that returned an error, if any
   cudaError_t failedCode;
-  void post(const char * name, int n = 1)
+  // optional per-launch timing with CUDA events on the launching stream (bench.py roofline)
+  bool profile;
+  struct Rec
   {
-    count += n;
+    const char * name;
+    cudaEvent_t a, b;
+  };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t pendingStart;
+  cudaEvent_t take()
+  {
+    cudaEvent_t e;
+    if (!pool.empty())
+    {
+      e = pool.back();
+      pool.pop_back();
+    }
+    else
+      cudaEventCreate(&e);
+    return e;
+  }
+  void pre()
+  {
+    if (profile)
+    {
+      pendingStart = take();
+      cudaEventRecord(pendingStart, stream);
+    }
+  }
+  void post(const char * name)
+  {
+    ++count;
+    if (profile)
+    {
+      Rec r;
+      r.name = name;
+      r.a = pendingStart;
+      r.b = take();
+      cudaEventRecord(r.b, stream);
+      recs.push_back(r);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess && !failedKernel)
     {

@@ -125,6 +125,8 @@ struct mci_ctx
   int nPairs = 0, capPairs = 0;
   // interpolation
   DBuf dJobBlob, dArena, dScratch, dBigHist, dSlab, dNodes, dLevelCounts, dArenaTop, dTrans;
+  DBuf dWork, dItems, dLevelScratch, dHist, dDtBig, dDtCounters;
+  bool histClean = false, dtBigClean = false;
   int bigHistGrid = 0;
   int nJobs = 0;
   // error flag
@@ -176,6 +178,9 @@ check_device_error(mci_ctx * ctx)
   int z = 0;
   cudaMemcpyAsync(ctx->dErr, &z, sizeof(int), cudaMemcpyHostToDevice, ctx->L.stream);
   cudaStreamSynchronize(ctx->L.stream);
+  ctx->histClean = false;
+  ctx->dtBigClean = false;
+  ctx->bigHistGrid = 0;
   ctx->err = std::string("device: ") + (h >= 0 && h <= 8 ? names[h] : "unknown");
   return h == ERR_PIXELTYPE ? MCI_ERR_PIXELTYPE : MCI_ERR_CAPACITY;
 }
@@ -229,7 +234,8 @@ extern "C"
                       &ctx->dCounters, &ctx->dSliceBlob, &ctx->dParent, &ctx->dRootId,    &ctx->dConn,    &ctx->dRowCount,
                       &ctx->dNcomp,    &ctx->dCompBase, &ctx->dTotal,   &ctx->dStats,     &ctx->dSegBlob, &ctx->dPairTable,
                       &ctx->dPairs,    &ctx->dJobBlob,  &ctx->dArena,   &ctx->dScratch,   &ctx->dBigHist, &ctx->dSlab,
-                      &ctx->dNodes,    &ctx->dLevelCounts, &ctx->dArenaTop, &ctx->dTrans };
+                      &ctx->dNodes,    &ctx->dLevelCounts, &ctx->dArenaTop, &ctx->dTrans,
+                      &ctx->dWork, &ctx->dItems, &ctx->dLevelScratch, &ctx->dHist, &ctx->dDtBig, &ctx->dDtCounters };
     for (DBuf * b : bufs)
       b->release();
     recycle_events(ctx);
@@ -734,6 +740,7 @@ extern "C"
     int nRootNodes = 0;
     int maxDepth = 0;
     std::vector<long long> levelCap;
+    std::vector<unsigned long long> levelScratch, levelItems;
     u64 midWords = 0, maxNodeWords = 0;
 
     auto statOf = [&](int slice, int id) -> const CompStat & { return ctx->hStats[ctx->compBase[slice] + id - 1]; };
@@ -897,15 +904,24 @@ extern "C"
       int depth = depth_of_gap(gap);
       maxDepth = std::max(maxDepth, depth);
       if ((int)levelCap.size() < depth)
+      {
         levelCap.resize(depth, 0);
-      for (int d = 0; d < depth; ++d)
-        levelCap[d] += (long long)nRootsHere * std::min<long long>(1ll << std::min(d, 30), gap - 1);
+        levelScratch.resize(depth, 0);
+        levelItems.resize(depth, 0);
+      }
       const int d0 = SA.axis == 0 ? 1 : 0, d1 = SA.axis == 2 ? 1 : 2;
       long long bw = std::min<long long>(ctx->dims[d0], 2 * (ma.w + wbSum));
       long long bh = std::min<long long>(ctx->dims[d1], 2 * (ma.h + hbMax));
       u64 nodeWords = (u64)((bw + 31) / 32 + 1) * (u64)bh;
       maxNodeWords = std::max(maxNodeWords, nodeWords);
       midWords += (u64)nRootsHere * (u64)(gap - 1) * nodeWords;
+      for (int d = 0; d < depth; ++d)
+      {
+        const long long nn = (long long)nRootsHere * std::min<long long>(1ll << std::min(d, 30), gap - 1);
+        levelCap[d] += nn;
+        levelScratch[d] += (u64)nn * (3 * nodeWords + (u64)bh + 8);
+        levelItems[d] += (u64)nn * (nodeWords / 256 + 1);
+      }
     }
 
     // ---- device memory
@@ -928,22 +944,6 @@ extern "C"
     CK(ctx->dNodes.ensure(size_t(nodeTotal + 1) * sizeof(Node)));
     CK(ctx->dLevelCounts.ensure(size_t(maxDepth + 2) * sizeof(int)));
     CK(ctx->dArenaTop.ensure(8));
-    const int nodeSmem = 100 * 1024;
-    const int nodeGrid = ctx->L.sms * 2;
-    if (ctx->bigHistGrid < nodeGrid)
-    {
-      CK(ctx->dBigHist.ensure(size_t(nodeGrid) * 2 * 65536 * 4));
-      CK(cudaMemsetAsync(ctx->dBigHist.p, 0, size_t(nodeGrid) * 2 * 65536 * 4, s));
-      ctx->bigHistGrid = nodeGrid;
-    }
-    const int nArr = prm->use_distance_transform ? 3 : 6;
-    const u64 smemWords = (u64)nodeSmem / 4 - 2 * 2048;
-    u64 slabWords = 0;
-    if (maxNodeWords * nArr > smemWords)
-    {
-      slabWords = maxNodeWords * nArr;
-      CK(ctx->dSlab.ensure(size_t(nodeGrid) * slabWords * 4));
-    }
     // bitmaps of the global-scratch Align jobs must start cleared (the kernel clears them itself as well)
     std::vector<int> lc(maxDepth + 2, 0);
     lc[0] = nRootNodes;
@@ -962,16 +962,110 @@ extern "C"
     launch_make_roots(ctx->L, (RootJob *)(jb + oRoots), njobs, dRefs, (uint32_t *)ctx->dArena.p, (int2 *)ctx->dTrans.p, dNodes);
     long long off = 0;
     int * dCounts = (int *)ctx->dLevelCounts.p;
-    for (int d = 0; d < maxDepth; ++d)
+    if (prm->use_distance_transform)
     {
-      Node * cur = dNodes + off;
-      Node * nxt = dNodes + off + levelCap[d];
-      int nextCap = d + 1 < maxDepth ? (int)levelCap[d + 1] : 0;
-      launch_nodes(ctx->L, ctx->ptype, cur, dCounts + d, (int)levelCap[d], nxt, dCounts + d + 1, nextCap,
-                   (uint32_t *)ctx->dArena.p, (unsigned long long *)ctx->dArenaTop.p, arenaCap, ctx->dIn, ctx->dOut, ctx->dims,
-                   prm->use_distance_transform, prm->use_ball, (unsigned *)ctx->dBigHist.p, (uint32_t *)ctx->dSlab.p, slabWords,
-                   nodeGrid, nodeSmem, ctx->dErr);
-      off += levelCap[d];
+      // distance-transform median: six grid-wide kernels per level (mci_dt.cu)
+      long long maxLevelNodes = 0;
+      u64 scratchCap = 0, itemCap = 0;
+      for (int d = 0; d < maxDepth; ++d)
+      {
+        maxLevelNodes = std::max(maxLevelNodes, levelCap[d]);
+        scratchCap = std::max<u64>(scratchCap, levelScratch[d]);
+        itemCap = std::max<u64>(itemCap, levelItems[d]);
+      }
+      const int histSide = ctx->ptype == MCI_U8 ? 256 : (ctx->ptype == MCI_U16 ? 6560 : 3296);
+      const int histStride = 2 * histSide;
+      const int nbig = 128;
+      const size_t histBytes = size_t(maxLevelNodes) * histStride * 4;
+      const size_t bigBytes = size_t(nbig) * 2 * 65536 * 4;
+      if (ctx->dHist.cap < histBytes)
+        ctx->histClean = false;
+      CK(ctx->dHist.ensure(histBytes));
+      if (!ctx->histClean)
+      {
+        CK(cudaMemsetAsync(ctx->dHist.p, 0, ctx->dHist.cap, s));
+        ctx->histClean = true;
+      }
+      if (ctx->dDtBig.cap < bigBytes)
+        ctx->dtBigClean = false;
+      CK(ctx->dDtBig.ensure(bigBytes));
+      if (!ctx->dtBigClean)
+      {
+        CK(cudaMemsetAsync(ctx->dDtBig.p, 0, bigBytes, s));
+        ctx->dtBigClean = true;
+      }
+      CK(ctx->dWork.ensure(size_t(maxLevelNodes) * sizeof(NodeWork)));
+      CK(ctx->dItems.ensure(size_t(2 * itemCap + 2) * sizeof(DtItem)));
+      CK(ctx->dLevelScratch.ensure((scratchCap + 64) * 4));
+      // per level: [0] items, [1] write items, [2] wrapped-bin tables in use; and a 64-bit scratch top
+      CK(ctx->dDtCounters.ensure(size_t(maxDepth) * (4 * sizeof(int) + 8)));
+      CK(cudaMemsetAsync(ctx->dDtCounters.p, 0, size_t(maxDepth) * (4 * sizeof(int) + 8), s));
+      unsigned long long * tops = (unsigned long long *)ctx->dDtCounters.p;
+      int * ctrs = (int *)(tops + maxDepth);
+      for (int d = 0; d < maxDepth; ++d)
+      {
+        DtLevel lv;
+        lv.nodes = dNodes + off;
+        lv.count = dCounts + d;
+        lv.maxNodes = (int)levelCap[d];
+        lv.work = (NodeWork *)ctx->dWork.p;
+        lv.arena = (uint32_t *)ctx->dArena.p;
+        lv.arenaTop = (unsigned long long *)ctx->dArenaTop.p;
+        lv.arenaCap = arenaCap;
+        lv.scratch = (uint32_t *)ctx->dLevelScratch.p;
+        lv.scratchTop = tops + d;
+        lv.scratchCap = scratchCap;
+        lv.items = (DtItem *)ctx->dItems.p;
+        lv.itemCount = ctrs + 4 * d;
+        lv.witems = (DtItem *)ctx->dItems.p + itemCap + 1;
+        lv.witemCount = ctrs + 4 * d + 1;
+        lv.itemCap = (int)itemCap;
+        lv.hist = (unsigned *)ctx->dHist.p;
+        lv.histStride = histStride;
+        lv.histSide = histSide;
+        lv.bigHist = (unsigned *)ctx->dDtBig.p;
+        lv.bigCount = ctrs + 4 * d + 2;
+        lv.nbig = nbig;
+        lv.next = dNodes + off + levelCap[d];
+        lv.nextCount = dCounts + d + 1;
+        lv.nextCap = d + 1 < maxDepth ? (int)levelCap[d + 1] : 0;
+        lv.in = ctx->dIn;
+        lv.out = ctx->dOut;
+        for (int a = 0; a < 3; ++a)
+          lv.dims[a] = ctx->dims[a];
+        lv.err = ctx->dErr;
+        launch_dt_level(ctx->L, ctx->ptype, lv);
+        off += levelCap[d];
+      }
+    }
+    else
+    {
+      const int nodeSmem = 100 * 1024;
+      const int nodeGrid = ctx->L.sms * 2;
+      if (ctx->bigHistGrid < nodeGrid)
+      {
+        CK(ctx->dBigHist.ensure(size_t(nodeGrid) * 2 * 65536 * 4));
+        CK(cudaMemsetAsync(ctx->dBigHist.p, 0, size_t(nodeGrid) * 2 * 65536 * 4, s));
+        ctx->bigHistGrid = nodeGrid;
+      }
+      const u64 smemWords = (u64)nodeSmem / 4 - 2 * 2048;
+      u64 slabWords = 0;
+      if (maxNodeWords * 6 > smemWords)
+      {
+        slabWords = maxNodeWords * 6;
+        CK(ctx->dSlab.ensure(size_t(nodeGrid) * slabWords * 4));
+      }
+      for (int d = 0; d < maxDepth; ++d)
+      {
+        Node * cur = dNodes + off;
+        Node * nxt = dNodes + off + levelCap[d];
+        int nextCap = d + 1 < maxDepth ? (int)levelCap[d + 1] : 0;
+        launch_nodes(ctx->L, ctx->ptype, cur, dCounts + d, (int)levelCap[d], nxt, dCounts + d + 1, nextCap,
+                     (uint32_t *)ctx->dArena.p, (unsigned long long *)ctx->dArenaTop.p, arenaCap, ctx->dIn, ctx->dOut, ctx->dims,
+                     0, prm->use_ball, (unsigned *)ctx->dBigHist.p, (uint32_t *)ctx->dSlab.p, slabWords, nodeGrid, nodeSmem,
+                     ctx->dErr);
+        off += levelCap[d];
+      }
     }
     CK(cudaGetLastError());
     return MCI_OK;

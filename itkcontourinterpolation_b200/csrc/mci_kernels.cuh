@@ -72,6 +72,53 @@ dilate_word(const uint32_t * img, int h, int pitch, int r, int wi, bool ball)
   return v;
 }
 
+// nearest set bit of a bit row to column x, as squared distance, searching only while it can beat lim
+__device__ __forceinline__ int
+row_nearest_sq(const uint32_t * row, int pitch, int x, int lim)
+{
+  const int w0 = x >> 5, b = x & 31;
+  int best = lim;
+  {
+    uint32_t m = row[w0] & (0xFFFFFFFFu >> (31 - b));
+    int wl = w0;
+    for (;;)
+    {
+      if (m)
+      {
+        int dx = x - (wl * 32 + 31 - __clz(m));
+        best = min(best, dx * dx);
+        break;
+      }
+      if (--wl < 0)
+        break;
+      int dmin = x - (wl * 32 + 31);
+      if (dmin * dmin >= best)
+        break;
+      m = row[wl];
+    }
+  }
+  {
+    uint32_t m = row[w0] & (0xFFFFFFFEu << b);
+    int wr = w0;
+    for (;;)
+    {
+      if (m)
+      {
+        int dx = (wr * 32 + __ffs(m) - 1) - x;
+        best = min(best, dx * dx);
+        break;
+      }
+      if (++wr >= pitch)
+        break;
+      int dmin = wr * 32 - x;
+      if (dmin * dmin >= best)
+        break;
+      m = row[wr];
+    }
+  }
+  return best;
+}
+
 template <typename T>
 struct PixTraits;
 template <>

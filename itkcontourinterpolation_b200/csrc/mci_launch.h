@@ -68,6 +68,38 @@ struct Launch
   }
 };
 
+struct DtLevel
+{
+  const Node * nodes;
+  const int * count;
+  int maxNodes;
+  NodeWork * work;
+  uint32_t * arena;
+  unsigned long long * arenaTop;
+  unsigned long long arenaCap;
+  uint32_t * scratch;
+  unsigned long long * scratchTop;
+  unsigned long long scratchCap;
+  DtItem * items;
+  int * itemCount;
+  DtItem * witems;
+  int * witemCount;
+  int itemCap;
+  unsigned * hist;
+  int histStride, histSide;
+  unsigned * bigHist;
+  int * bigCount;
+  int nbig;
+  Node * next;
+  int * nextCount;
+  int nextCap;
+  const void * in;
+  void * out;
+  long long dims[3];
+  int * err;
+};
+void launch_dt_level(Launch & L, int ptype, const DtLevel & lv);
+
 void launch_detect(Launch & L, int ptype, const void * in, void * out, const long long dims[3], int axisSel, int * bbox, int nl,
                    uint32_t * sliceBits, int wordsPerLabel, int wo1, int wo2);
 void launch_compact_labels(Launch & L, const int * bbox, int nl, const uint32_t * sliceBits, int wordsPerLabel, int wo1, int wo2,

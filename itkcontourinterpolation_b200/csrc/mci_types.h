@@ -100,6 +100,27 @@ struct Node
   int axis, label;
 };
 
+// Per-node state of one level of the distance-transform pipeline (mci_dt.cu).
+struct NodeWork
+{
+  Node nd;
+  int ux0, uy0, w, h, pitch, words; // working region = union of the two translated shapes' regions
+  int iTx, iTy, jTx, jTy, mid;
+  int xr0, xr1;                     // first / last row holding intersection pixels
+  int maxIdx, maxBig, bigIdx;       // histogram extents; slot of the wrapped-bin table (-1: none)
+  int thr;                          // d2 threshold of the median (-1: the median is the intersection)
+  int bx0, by0, bx1, by1;           // bounding box of the clipped median
+  int alive;
+  u64 scratchOff;                   // Xb | Ib | Sb (words each) | rowInfo (h)
+  MaskRef M;                        // the mid shape
+};
+
+struct DtItem
+{
+  int node;
+  int w0; // first word of the chunk
+};
+
 struct RootJob
 {
   int kind;

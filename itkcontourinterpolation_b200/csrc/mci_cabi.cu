@@ -735,12 +735,12 @@ extern "C"
     std::vector<RootJob> roots(njobs);
     std::map<std::pair<int, int>, MaskRef> compMasks;
     u64 arenaWords = 0, scratchWords = 0;
-    const int alignSmemCap = 160 * 1024;
+    const int alignSmemCap = 150 * 1024; // bitmap + queue; the kernel adds 48 KB for staging the shapes
     int alignSmem = 0;
     int nRootNodes = 0;
     int maxDepth = 0;
     std::vector<long long> levelCap;
-    std::vector<unsigned long long> levelScratch, levelItems;
+    std::vector<unsigned long long> levelScratch, levelItems, levelHItems;
     u64 midWords = 0, maxNodeWords = 0;
 
     auto statOf = [&](int slice, int id) -> const CompStat & { return ctx->hStats[ctx->compBase[slice] + id - 1]; };
@@ -759,11 +759,17 @@ extern "C"
       m.pad = 0;
       m.off = arenaWords;
       arenaWords += (u64)m.h * m.pitch;
-      ExtractJob e;
-      e.slice = slice;
-      e.id = id;
-      e.m = m;
-      extracts.push_back(e);
+      const int tileRows = std::max(1, 256 / m.pitch);
+      for (int r0 = 0; r0 < m.h; r0 += tileRows)
+      {
+        ExtractJob e;
+        e.slice = slice;
+        e.id = id;
+        e.row0 = r0;
+        e.nrows = std::min(tileRows, m.h - r0);
+        e.m = m;
+        extracts.push_back(e);
+      }
       compMasks[key] = m;
       return m;
     };
@@ -879,7 +885,11 @@ extern "C"
       A.minIter = (long long)std::min<unsigned long long>((unsigned long long)prm->min_align_iters, nS);
       A.maxIter = (long long)std::max<unsigned long long>((unsigned long long)prm->max_align_iters,
                                                         (unsigned long long)std::sqrt((double)nS));
-      long long need = std::max<long long>(A.maxIter + 16, 8ll * (A.sw + A.sh)) + 64;
+      // ring capacity: with the heuristic on and a non-zero score at t=0 (guaranteed for shapes paired by pixel
+      // overlap) at most maxIter + 4 translations are ever pushed; otherwise two full BFS rings can be queued
+      long long need = (prm->heuristic_alignment && jb.kind != JOB_EXTRAPOLATE)
+                         ? A.maxIter + 16
+                         : std::max<long long>(A.maxIter + 16, 8ll * (A.sw + A.sh)) + 64;
       int qcap = 64;
       while (qcap < need)
         qcap <<= 1;
@@ -908,6 +918,7 @@ extern "C"
         levelCap.resize(depth, 0);
         levelScratch.resize(depth, 0);
         levelItems.resize(depth, 0);
+        levelHItems.resize(depth, 0);
       }
       const int d0 = SA.axis == 0 ? 1 : 0, d1 = SA.axis == 2 ? 1 : 2;
       long long bw = std::min<long long>(ctx->dims[d0], 2 * (ma.w + wbSum));
@@ -919,8 +930,9 @@ extern "C"
       {
         const long long nn = (long long)nRootsHere * std::min<long long>(1ll << std::min(d, 30), gap - 1);
         levelCap[d] += nn;
-        levelScratch[d] += (u64)nn * (3 * nodeWords + (u64)bh + 8);
+        levelScratch[d] += (u64)nn * (3 * nodeWords + (u64)bh + (u64)bh / 8 + 16);
         levelItems[d] += (u64)nn * (nodeWords / 256 + 1);
+        levelHItems[d] += (u64)nn * (nodeWords / 8 + 1);
       }
     }
 
@@ -966,18 +978,19 @@ extern "C"
     {
       // distance-transform median: six grid-wide kernels per level (mci_dt.cu)
       long long maxLevelNodes = 0;
-      u64 scratchCap = 0, itemCap = 0;
+      u64 scratchCap = 0, itemCap = 0, hitemCap = 0;
       for (int d = 0; d < maxDepth; ++d)
       {
         maxLevelNodes = std::max(maxLevelNodes, levelCap[d]);
         scratchCap = std::max<u64>(scratchCap, levelScratch[d]);
         itemCap = std::max<u64>(itemCap, levelItems[d]);
+        hitemCap = std::max<u64>(hitemCap, levelHItems[d]);
       }
       const int histSide = ctx->ptype == MCI_U8 ? 256 : (ctx->ptype == MCI_U16 ? 6560 : 3296);
-      const int histStride = 2 * histSide;
+      const int histStride = 2 * histSide + histSide / 32; // counts of both sides + bitmap of touched entries
       const int nbig = 128;
       const size_t histBytes = size_t(maxLevelNodes) * histStride * 4;
-      const size_t bigBytes = size_t(nbig) * 2 * 65536 * 4;
+      const size_t bigBytes = size_t(nbig) * (2 * 65536 + 2048) * 4;
       if (ctx->dHist.cap < histBytes)
         ctx->histClean = false;
       CK(ctx->dHist.ensure(histBytes));
@@ -995,7 +1008,7 @@ extern "C"
         ctx->dtBigClean = true;
       }
       CK(ctx->dWork.ensure(size_t(maxLevelNodes) * sizeof(NodeWork)));
-      CK(ctx->dItems.ensure(size_t(2 * itemCap + 2) * sizeof(DtItem)));
+      CK(ctx->dItems.ensure(size_t(2 * itemCap + hitemCap + 4) * sizeof(DtItem)));
       CK(ctx->dLevelScratch.ensure((scratchCap + 64) * 4));
       // per level: [0] items, [1] write items, [2] wrapped-bin tables in use; and a 64-bit scratch top
       CK(ctx->dDtCounters.ensure(size_t(maxDepth) * (4 * sizeof(int) + 8)));
@@ -1020,6 +1033,9 @@ extern "C"
         lv.witems = (DtItem *)ctx->dItems.p + itemCap + 1;
         lv.witemCount = ctrs + 4 * d + 1;
         lv.itemCap = (int)itemCap;
+        lv.hitems = (DtItem *)ctx->dItems.p + 2 * itemCap + 2;
+        lv.hitemCount = ctrs + 4 * d + 3;
+        lv.hitemCap = (int)hitemCap;
         lv.hist = (unsigned *)ctx->dHist.p;
         lv.histStride = histStride;
         lv.histSide = histSide;

@@ -21,6 +21,8 @@ namespace mci
 {
 
 #define DT_CHUNK 256 // words of a node's bit rows per work item (one CTA: 8 warps x 32 words)
+#define DT_HCHUNK 8  // words per histogram work item (one warp), emitted only where (i xor j) pixels exist
+#define DT_BIG_STRIDE (2 * 65536 + 2048) // wrapped-bin table: counts of both sides + bitmap of touched bins
 
 __device__ __forceinline__ uint32_t
 pack_row(int a, int b, bool single)
@@ -30,40 +32,69 @@ pack_row(int a, int b, bool single)
 
 // exact squared distance from pixel (x, r) to the nearest intersection pixel, or `cap` if not below cap.
 // rowInfo[r] packs the first / last set column of row r and whether the row is one run (then the
-// distance to the row is the distance to that interval); 0 = empty row.
+// distance to the row is the distance to that interval); 0 = empty row.  bandInfo[b] is the same
+// extent over rows 8b..8b+7: a whole band is skipped when even its nearest row and nearest column
+// cannot beat the best distance so far.
 __device__ __forceinline__ int
-dt_edt_sq(const uint32_t * __restrict__ Xb, const uint32_t * __restrict__ rowInfo, int pitch, int xr0, int xr1, int x, int r,
+dt_probe_row(const uint32_t * __restrict__ Xb, const uint32_t * __restrict__ rowInfo, int pitch, int x, int rr, int dd, int best)
+{
+  const uint32_t info = __ldg(rowInfo + rr);
+  if (!info)
+    return best;
+  const int a = info & 0x1FFF, b = (info >> 13) & 0x1FFF;
+  const int dx = x < a ? a - x : (x > b ? x - b : 0);
+  const int lo = dd + dx * dx;
+  if (lo >= best)
+    return best;
+  if ((info >> 26) & 1u)
+    return lo;
+  return min(best, dd + row_nearest_sq(Xb + (size_t)rr * pitch, pitch, x, best - dd));
+}
+
+__device__ __forceinline__ bool
+dt_band_prunable(const uint32_t * __restrict__ bandInfo, int band, int x, int dd, int best)
+{
+  const uint32_t info = __ldg(bandInfo + band);
+  if (!info)
+    return true;
+  const int a = info & 0x1FFF, b = (info >> 13) & 0x1FFF;
+  const int dx = x < a ? a - x : (x > b ? x - b : 0);
+  return dd + dx * dx >= best;
+}
+
+__device__ __forceinline__ int
+dt_edt_sq(const uint32_t * __restrict__ Xb, const uint32_t * __restrict__ rowInfo, int pitch, int h, int xr0, int xr1, int x, int r,
           int cap)
 {
+  const uint32_t * bandInfo = rowInfo + h;
   int best = cap;
-  int k = max(0, max(xr0 - r, r - xr1));
-  for (;; ++k)
+  // rows at and below r
+  for (int rr = max(r, xr0); rr <= xr1;)
   {
-    const int kk = k * k;
-    if (kk >= best)
+    const int dy = rr - r, dd = dy * dy;
+    if (dd >= best)
       break;
-    const int r1 = r - k, r2 = r + k;
-    if (r1 < xr0 && r2 > xr1)
-      break;
-#pragma unroll
-    for (int s = 0; s < 2; ++s)
+    if ((rr & 7) == 0 && dt_band_prunable(bandInfo, rr >> 3, x, dd, best))
     {
-      const int rr = s ? r2 : r1;
-      if (rr < xr0 || rr > xr1 || (s && k == 0))
-        continue;
-      const uint32_t info = __ldg(rowInfo + rr);
-      if (!info)
-        continue;
-      const int a = info & 0x1FFF, b = (info >> 13) & 0x1FFF;
-      const int dx = x < a ? a - x : (x > b ? x - b : 0);
-      const int lo = kk + dx * dx;
-      if (lo >= best)
-        continue;
-      if ((info >> 26) & 1u)
-        best = lo;
-      else
-        best = min(best, kk + row_nearest_sq(Xb + (size_t)rr * pitch, pitch, x, best - kk));
+      rr += 8;
+      continue;
     }
+    best = dt_probe_row(Xb, rowInfo, pitch, x, rr, dd, best);
+    ++rr;
+  }
+  // rows above r
+  for (int rr = min(r - 1, xr1); rr >= xr0;)
+  {
+    const int dy = r - rr, dd = dy * dy;
+    if (dd >= best)
+      break;
+    if ((rr & 7) == 7 && dt_band_prunable(bandInfo, rr >> 3, x, dd, best))
+    {
+      rr -= 8;
+      continue;
+    }
+    best = dt_probe_row(Xb, rowInfo, pitch, x, rr, dd, best);
+    --rr;
   }
   return best;
 }
@@ -92,7 +123,7 @@ dt_bin(int d2, int * err)
 __global__ void __launch_bounds__(256)
 k_dt_prep(const Node * __restrict__ nodes, const int * __restrict__ count, NodeWork * work, const uint32_t * __restrict__ arena,
           uint32_t * scratch, unsigned long long * scratchTop, unsigned long long scratchCap, DtItem * items, int * itemCount,
-          int itemCap, int * err)
+          int itemCap, DtItem * hitems, int * hitemCount, int hitemCap, int * err)
 {
   __shared__ int s_r0, s_r1;
   __shared__ unsigned long long s_off;
@@ -134,12 +165,12 @@ k_dt_prep(const Node * __restrict__ nodes, const int * __restrict__ count, NodeW
     {
       s_r0 = 0x7FFFFFFF;
       s_r1 = -1;
-      s_off = atomicAdd(scratchTop, (unsigned long long)(3 * (size_t)words + h));
+      s_off = atomicAdd(scratchTop, (unsigned long long)(3 * (size_t)words + h + (h + 7) / 8));
     }
     __syncthreads();
     const unsigned long long off = s_off;
     NodeWork * W = work + nidx;
-    if (off + 3ull * words + h > scratchCap || w > 8191)
+    if (off + 3ull * words + h + (h + 7) / 8 > scratchCap || w > 8191)
     {
       if (tid == 0)
       {
@@ -210,6 +241,52 @@ k_dt_prep(const Node * __restrict__ nodes, const int * __restrict__ count, NodeW
       atomicMax(&s_r1, r1);
     }
     __syncthreads();
+    // extents of 8-row bands
+    for (int bnd = tid; bnd < (h + 7) / 8; bnd += 256)
+    {
+      int a = 0x7FFFFFFF, b = -1;
+      for (int q = 0; q < 8 && bnd * 8 + q < h; ++q)
+      {
+        const uint32_t info = rowInfo[bnd * 8 + q];
+        if (info)
+        {
+          a = min(a, (int)(info & 0x1FFF));
+          b = max(b, (int)((info >> 13) & 0x1FFF));
+        }
+      }
+      rowInfo[h + bnd] = b >= 0 ? pack_row(a, b, false) : 0u;
+    }
+    // histogram work items: 8-word chunks that hold (i xor j) pixels (skipped when the intersection is empty)
+    if (s_r1 >= 0)
+    {
+      const int nChunks = (words + DT_HCHUNK - 1) / DT_HCHUNK;
+      for (int cb = 0; cb < nChunks; cb += 256)
+      {
+        const int c = cb + tid;
+        bool any = false;
+        if (c < nChunks)
+          for (int q = 0; q < DT_HCHUNK && c * DT_HCHUNK + q < words; ++q)
+            any |= Sb[c * DT_HCHUNK + q] != 0u;
+        const unsigned vote = __ballot_sync(0xFFFFFFFFu, any);
+        int base = 0;
+        if (lane == 0 && vote)
+          base = atomicAdd(hitemCount, __popc(vote));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (any)
+        {
+          const int pos = base + __popc(vote & ((1u << lane) - 1u));
+          if (pos < hitemCap)
+          {
+            DtItem it;
+            it.node = nidx;
+            it.w0 = c * DT_HCHUNK;
+            hitems[pos] = it;
+          }
+          else
+            atomicMax(err, ERR_SCRATCH);
+        }
+      }
+    }
     if (tid == 0)
     {
       NodeWork nw;
@@ -284,53 +361,88 @@ dt_get_big(NodeWork * W, int * bigCount, int nbig, int * err)
   return bi;
 }
 
+// Enumerates the set bits of a warp's 32 words (lane i holds word i) so that every lane gets its own
+// pixel: returns, for pixel number p (0-based, < total), the lane holding its word and the bit position.
+__device__ __forceinline__ void
+warp_pixel(uint32_t myWord, int incl, int p, int & srcLane, int & bit)
+{
+  int lo = 0; // smallest lane whose inclusive count exceeds p
+#pragma unroll
+  for (int step = 16; step > 0; step >>= 1)
+  {
+    int probe = lo + step - 1;
+    int v = __shfl_sync(0xFFFFFFFFu, incl, probe);
+    if (v <= p)
+      lo += step;
+  }
+  lo = min(lo, 31);
+  srcLane = lo;
+  const uint32_t w = __shfl_sync(0xFFFFFFFFu, myWord, lo);
+  const int inclSrc = __shfl_sync(0xFFFFFFFFu, incl, lo);
+  const int before = inclSrc - __popc(w);
+  bit = __fns(w, 0, max(1, p - before + 1));
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_dt_hist(NodeWork * work, const DtItem * __restrict__ items, const int * __restrict__ itemCount, const uint32_t * __restrict__ scratch,
-          unsigned * hist, int histStride, int histSide, unsigned * bigHist, int * bigCount, int nbig, int * err)
+k_dt_hist(NodeWork * work, const DtItem * __restrict__ items, const int * __restrict__ itemCount, int itemCap,
+          const uint32_t * __restrict__ scratch, unsigned * hist, int histStride, int histSide, unsigned * bigHist, int * bigCount,
+          int nbig, int * err)
 {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nItems = *itemCount;
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const int nItems = min(*itemCount, itemCap);
   constexpr bool kBinsOnly = sizeof(T) == 1; // uchar: 256 wrapped bins, indexed directly
   constexpr int kSmall = PixTraits<T>::kNoWrapD2;
-  for (int it = blockIdx.x; it < nItems; it += gridDim.x)
+  for (int it = gw; it < nItems; it += nw) // one warp per item
   {
     const DtItem item = items[it];
     NodeWork * W = work + item.node;
-    const int pitch = W->pitch, words = W->words, xr0 = W->xr0, xr1 = W->xr1;
+    const int pitch = W->pitch, words = W->words, xr0 = W->xr0, xr1 = W->xr1, nodeH = W->h;
     const uint32_t * Xb = scratch + W->scratchOff;
     const uint32_t * Ib = Xb + words;
     const uint32_t * Sb = Ib + words;
     const uint32_t * rowInfo = Sb + words;
     unsigned * h0 = hist + (size_t)item.node * histStride;
     int maxSmall = -1, maxBig = -1;
-    const int wBeg = item.w0 + warp * 32, wEnd = min(words, wBeg + 32);
-    for (int idx = wBeg; idx < wEnd; ++idx)
+    const int wBeg = item.w0;
+    // lane i < 8 owns word wBeg+i; the pixels of the chunk are dealt out one per lane
+    const int myIdx = wBeg + lane;
+    const bool mine = lane < DT_HCHUNK && myIdx < words;
+    const uint32_t myS = mine ? __ldg(Sb + myIdx) : 0u;
+    const uint32_t myI = mine ? __ldg(Ib + myIdx) : 0u;
+    int incl = __popc(myS);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
     {
-      const uint32_t s = __ldg(Sb + idx);
-      if (!s)
-        continue; // warp-uniform
-      const bool on = (s >> lane) & 1u;
+      int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o)
+        incl += t;
+    }
+    const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    for (int base = 0; base < total; base += 32)
+    {
+      const int p = base + lane;
+      const bool on = p < total;
+      int src, bit;
+      warp_pixel(myS, incl, on ? p : total - 1, src, bit);
+      const uint32_t iw = __shfl_sync(0xFFFFFFFFu, myI, src);
       int d2 = 0, side = 0;
-      if (on)
-      {
-        const int r = idx / pitch, wi = idx - r * pitch;
-        d2 = dt_edt_sq(Xb, rowInfo, pitch, xr0, xr1, wi * 32 + lane, r, 0x7FFFFFFF);
-        side = (__ldg(Ib + idx) >> lane) & 1u ? 0 : 1;
-      }
       bool over = false;
       if (on)
       {
-        if (kBinsOnly)
+        const int idx = wBeg + src;
+        const int r = idx / pitch, wi = idx - r * pitch;
+        d2 = dt_edt_sq(Xb, rowInfo, pitch, nodeH, xr0, xr1, wi * 32 + bit, r, 0x7FFFFFFF);
+        side = (iw >> bit) & 1u ? 0 : 1;
+        const int direct = kBinsOnly ? dt_bin<T>(d2, err) : d2;
+        if (kBinsOnly || d2 <= kSmall)
         {
-          int bin = dt_bin<T>(d2, err);
-          atomicAdd(&h0[side * histSide + bin], 1u);
-          maxSmall = max(maxSmall, bin);
-        }
-        else if (d2 <= kSmall)
-        {
-          atomicAdd(&h0[side * histSide + d2], 1u);
-          maxSmall = max(maxSmall, d2);
+          atomicAdd(&h0[side * histSide + direct], 1u);
+          unsigned * tw = h0 + 2 * histSide + (direct >> 5); // bitmap of touched entries
+          if (!(__ldcg(tw) & (1u << (direct & 31))))
+            atomicOr(tw, 1u << (direct & 31));
+          maxSmall = max(maxSmall, direct);
         }
         else
           over = true;
@@ -346,7 +458,11 @@ k_dt_hist(NodeWork * work, const DtItem * __restrict__ items, const int * __rest
         if (over)
         {
           int bin = dt_bin<T>(d2, err);
-          atomicAdd(&bigHist[(size_t)bi * 2 * 65536 + side * 65536 + bin], 1u);
+          unsigned * bh = bigHist + (size_t)bi * DT_BIG_STRIDE;
+          atomicAdd(&bh[side * 65536 + bin], 1u);
+          unsigned * tw = bh + 2 * 65536 + (bin >> 5);
+          if (!(__ldcg(tw) & (1u << (bin & 31))))
+            atomicOr(tw, 1u << (bin & 31));
           maxBig = max(maxBig, bin);
         }
       }
@@ -368,6 +484,9 @@ k_dt_hist(NodeWork * work, const DtItem * __restrict__ items, const int * __rest
 }
 
 // ---------------------------------------------------------------------------------------------------
+// One CTA per node.  Both histogram tables carry a bitmap of touched entries; only those can change the
+// score (X:481-494), so each thread walks the set bits of its own bitmap words and a block-wide scan
+// supplies the running sums: constant depth whatever the table length.
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_dt_scan(NodeWork * work, const int * __restrict__ count, unsigned * hist, int histStride, int histSide, unsigned * bigHist)
@@ -383,90 +502,131 @@ k_dt_scan(NodeWork * work, const int * __restrict__ count, unsigned * hist, int 
     if (!W->alive)
       continue;
     unsigned * hs = hist + (size_t)nidx * histStride;
-    const int maxSmall = W->maxIdx, maxBig = W->maxBig, bi = W->bigIdx;
+    unsigned * hsBm = hs + 2 * histSide;
+    const int smallWords = histSide / 32;
+    const int bi = W->bigIdx;
     const bool big = bi >= 0;
-    unsigned * hi = hs;
-    unsigned * hj = hs + histSide;
-    int len; // histogram length (maxSize, X:462), in the index domain being scanned
+    unsigned * cntI = hs;
+    unsigned * cntJ = hs + histSide;
+    unsigned * bm = hsBm;
+    int wpt = 1; // bitmap words per thread (contiguous, so thread order = bin order)
     __syncthreads();
     if (big)
     {
-      // some distance wrapped (or exceeded the direct table): work in the wrapped-bin domain of X:431.
-      // fold the directly indexed part in (bin = 10*d2 below the wrap)
-      unsigned * bh = bigHist + (size_t)bi * 2 * 65536;
-      int top = maxBig;
-      for (int k = tid; k <= maxSmall; k += 256)
+      // Some distance wrapped (or exceeded the directly indexed table): work in the wrapped-bin domain of
+      // X:431; fold the directly indexed part in (bin = 10*d2 below the wrap).
+      unsigned * bh = bigHist + (size_t)bi * DT_BIG_STRIDE;
+      unsigned * bbm = bh + 2 * 65536;
+      for (int wI = tid; wI < smallWords; wI += 256)
       {
-        unsigned ci = hs[k], cj = hs[histSide + k];
-        if (ci)
-          atomicAdd(&bh[10 * k], ci);
-        if (cj)
-          atomicAdd(&bh[65536 + 10 * k], cj);
-        hs[k] = 0u;
-        hs[histSide + k] = 0u;
+        unsigned bits = hsBm[wI];
+        if (!bits)
+          continue;
+        hsBm[wI] = 0u;
+        while (bits)
+        {
+          int b = __ffs(bits) - 1;
+          bits &= bits - 1;
+          const int k = wI * 32 + b;
+          const int bin = kBinsOnly ? k : 10 * k;
+          atomicAdd(&bh[bin], hs[k]);
+          atomicAdd(&bh[65536 + bin], hs[histSide + k]);
+          atomicOr(&bbm[bin >> 5], 1u << (bin & 31));
+          hs[k] = 0u;
+          hs[histSide + k] = 0u;
+        }
       }
-      if (maxSmall >= 0)
-        top = max(top, 10 * maxSmall);
-      len = top + 1;
-      hi = bh;
-      hj = bh + 65536;
       __syncthreads();
+      cntI = bh;
+      cntJ = bh + 65536;
+      bm = bbm;
+      wpt = 8;
     }
-    else
-      len = maxSmall + 1;
-    int thr = -1; // -1: no pixel outside the intersection, the median is the intersection (X:463-466)
-    if (len > 0)
-    {
-      const int chunk = (len + 255) / 256;
-      const int lo = min(len, tid * chunk), hiEnd = min(len, lo + chunk);
-      long long ci = 0, cj = 0;
-      for (int k = lo; k < hiEnd; ++k)
-      {
-        ci += hi[k];
-        cj += hj[k];
-      }
-      long long sa = ci, sb = cj;
+    const int nWords = big ? 2048 : smallWords;
+    unsigned myBits[8];
+    long long li = 0, lj = 0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1)
+    for (int q = 0; q < 8; ++q)
+    {
+      const int wI = tid * wpt + q;
+      myBits[q] = (q < wpt && wI < nWords) ? bm[wI] : 0u;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+    {
+      unsigned bits = myBits[q];
+      while (bits)
       {
-        long long ta = __shfl_up_sync(0xFFFFFFFFu, sa, o), tb = __shfl_up_sync(0xFFFFFFFFu, sb, o);
-        if (lane >= o)
-        {
-          sa += ta;
-          sb += tb;
-        }
+        int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int k = (tid * wpt + q) * 32 + b;
+        li += cntI[k];
+        lj += cntJ[k];
       }
-      if (lane == 31)
+    }
+    // block exclusive scan of (li, lj)
+    long long sa = li, sb = lj;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      long long ta = __shfl_up_sync(0xFFFFFFFFu, sa, o), tb = __shfl_up_sync(0xFFFFFFFFu, sb, o);
+      if (lane >= o)
       {
-        redA[warp] = sa;
-        redB[warp] = sb;
+        sa += ta;
+        sb += tb;
       }
-      __syncthreads();
-      long long oa = 0, ob = 0, iTot = 0, jTot = 0;
-      for (int k = 0; k < 8; ++k)
+    }
+    if (lane == 31)
+    {
+      redA[warp] = sa;
+      redB[warp] = sb;
+    }
+    __syncthreads();
+    long long oa = 0, ob = 0, iTot = 0, jTot = 0;
+    for (int k = 0; k < 8; ++k)
+    {
+      if (k < warp)
       {
-        if (k < warp)
-        {
-          oa += redA[k];
-          ob += redB[k];
-        }
-        iTot += redA[k];
-        jTot += redB[k];
+        oa += redA[k];
+        ob += redB[k];
       }
-      long long si = oa + sa - ci, sj = ob + sb - cj;
+      iTot += redA[k];
+      jTot += redB[k];
+    }
+    int thr = -1; // -1: no pixel outside the intersection, the median is the intersection (X:463-466)
+    if (iTot + jTot > 0) // block-uniform
+    {
+      long long si = oa + sa - li, sj = ob + sb - lj;
       long long bd = 0x7FFFFFFFFFFFFFFFll;
       int bidx = 0x7FFFFFFF;
-      for (int k = lo; k < hiEnd; ++k)
+      if (tid == 0 && !(myBits[0] & 1u))
       {
-        si += hi[k];
-        sj += hj[k];
-        long long a = llabs(iTot - si + sj), b = llabs(jTot - sj + si);
-        long long d = llabs(a - b);
-        if (d < bd)
+        // bin 0 is always visited by the reference (bestDiff starts at LLONG_MAX, X:482-494)
+        bd = llabs(llabs(iTot) - llabs(jTot));
+        bidx = 0;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+      {
+        unsigned bits = myBits[q];
+        while (bits)
         {
-          bd = d;
-          bidx = k;
+          int b = __ffs(bits) - 1;
+          bits &= bits - 1;
+          const int k = (tid * wpt + q) * 32 + b;
+          si += cntI[k];
+          sj += cntJ[k];
+          long long d = llabs(llabs(iTot - si + sj) - llabs(jTot - sj + si));
+          if (d < bd)
+          {
+            bd = d;
+            bidx = k;
+          }
+          cntI[k] = 0u; // leave the tables clean for the next user
+          cntJ[k] = 0u;
         }
+        if (myBits[q])
+          bm[tid * wpt + q] = 0u;
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1)
@@ -493,18 +653,8 @@ k_dt_scan(NodeWork * work, const int * __restrict__ count, unsigned * hist, int 
           bd = bestD[k];
           bidx = bestI[k];
         }
-      // threshold `sdf <= float(bestBin) / 10` on integer d2 (X:497-508)
-      if (big || kBinsOnly)
-        thr = (int)floorf(__fdiv_rn((float)bidx, 10.0f));
-      else
-        thr = bidx; // bestBin = 10 * d2
-      __syncthreads();
-      // leave the tables clean for the next user
-      for (int k = tid; k < len; k += 256)
-      {
-        hi[k] = 0u;
-        hj[k] = 0u;
-      }
+      // threshold `sdf <= float(bestBin) / 10` on integer d2 (X:497-508); directly indexed: bestBin = 10 * d2
+      thr = (big || kBinsOnly) ? (int)floorf(__fdiv_rn((float)bidx, 10.0f)) : bidx;
     }
     if (tid == 0)
       W->thr = thr;
@@ -512,6 +662,14 @@ k_dt_scan(NodeWork * work, const int * __restrict__ count, unsigned * hist, int 
 }
 
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t
+bit_range(int lo, int hi) // bits lo..hi (0 <= lo <= hi <= 31)
+{
+  return (0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (31 - hi));
+}
+
+// With the threshold known, {d2 <= thr} is a union of horizontally dilated intersection rows:
+// row r+k contributes its pixels widened by floor(sqrt(thr - k*k)).  Bit-parallel per 32-pixel word.
 __global__ void __launch_bounds__(256)
 k_dt_median(NodeWork * work, const DtItem * __restrict__ items, const int * __restrict__ itemCount, uint32_t * scratch, int SU0,
             int SU1, int SU2, int * err)
@@ -529,25 +687,65 @@ k_dt_median(NodeWork * work, const DtItem * __restrict__ items, const int * __re
     const int axis = W->nd.axis;
     const int SU = axis == 0 ? SU1 : SU0, SV = axis == 2 ? SU1 : SU2; // slice extents (X:681-693)
     const int ux0 = W->ux0, uy0 = W->uy0;
+    const int myIdx = item.w0 + warp * 32 + lane;
     int bx0 = 0x7FFFFFFF, bx1 = -0x7FFFFFFF, by0 = 0x7FFFFFFF, by1 = -0x7FFFFFFF;
-    const int wBeg = item.w0 + warp * 32, wEnd = min(words, wBeg + 32);
-    for (int idx = wBeg; idx < wEnd; ++idx)
+    if (myIdx < words)
     {
-      const uint32_t s = Sb[idx];
-      const uint32_t x = __ldg(Xb + idx);
-      if (!(s | x))
-        continue; // warp-uniform
-      const int r = idx / pitch, wi = idx - r * pitch;
-      uint32_t m = x;
-      if (s && thr >= 0)
+      const uint32_t myS = Sb[myIdx];
+      uint32_t m = __ldg(Xb + myIdx);
+      const int r = myIdx / pitch, wi = myIdx - r * pitch;
+      if (thr >= 0 && myS)
       {
-        bool pass = false;
-        if ((s >> lane) & 1u)
-          pass = dt_edt_sq(Xb, rowInfo, pitch, xr0, xr1, wi * 32 + lane, r, thr + 1) <= thr;
-        m |= __ballot_sync(0xFFFFFFFFu, pass);
+        const int x0 = wi * 32;
+        uint32_t pass = 0;
+        int R = (int)sqrtf((float)thr) + 1; // widened below to floor(sqrt(thr - k*k)) exactly
+        for (int k = 0; k * k <= thr; ++k)
+        {
+          while (R * R + k * k > thr)
+            --R;
+#pragma unroll
+          for (int sgn = 0; sgn < 2; ++sgn)
+          {
+            if (sgn && k == 0)
+              continue;
+            const int rr = sgn ? r + k : r - k;
+            if (rr < xr0 || rr > xr1)
+              continue;
+            const uint32_t info = __ldg(rowInfo + rr);
+            if (!info)
+              continue;
+            const int a = info & 0x1FFF, b = (info >> 13) & 0x1FFF;
+            if (a - R > x0 + 31 || b + R < x0)
+              continue;
+            if ((info >> 26) & 1u)
+              pass |= bit_range(max(a - R, x0) - x0, min(b + R, x0 + 31) - x0);
+            else
+            {
+              // several runs in this row: widen each piece that can reach the word
+              const uint32_t * row = Xb + (size_t)rr * pitch;
+              const int wlo = max(0, (x0 - R) >> 5), whi = min(pitch - 1, (x0 + 31 + R) >> 5);
+              for (int ws = wlo; ws <= whi; ++ws)
+              {
+                uint32_t wv = __ldg(row + ws);
+                while (wv)
+                {
+                  const int sbit = __ffs(wv) - 1;
+                  const uint32_t t = ~(wv >> sbit);
+                  const int len = t ? __ffs(t) - 1 : 32 - sbit;
+                  const int lo = ws * 32 + sbit - R, hi = ws * 32 + sbit + len - 1 + R;
+                  if (hi >= x0 && lo <= x0 + 31)
+                    pass |= bit_range(max(lo, x0) - x0, min(hi, x0 + 31) - x0);
+                  wv = (len >= 32) ? 0u : (wv & ~(((1u << len) - 1u) << sbit));
+                }
+              }
+            }
+          }
+          if ((pass & myS) == myS)
+            break;
+        }
+        m |= pass & myS;
       }
-      if (lane == 0)
-        Sb[idx] = m;
+      Sb[myIdx] = m;
       // bounding box of the part that lies inside the slice (X:679-712)
       const int y = uy0 + r;
       if (m && y >= 0 && y < SV)
@@ -560,12 +758,19 @@ k_dt_median(NodeWork * work, const DtItem * __restrict__ items, const int * __re
           c = (xa >= SU) ? 0u : (c & (0xFFFFFFFFu >> (xa + 32 - SU)));
         if (c)
         {
-          bx0 = min(bx0, xa + __ffs(c) - 1);
-          bx1 = max(bx1, xa + 31 - __clz(c));
-          by0 = min(by0, y);
-          by1 = max(by1, y);
+          bx0 = xa + __ffs(c) - 1;
+          bx1 = xa + 31 - __clz(c);
+          by0 = by1 = y;
         }
       }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      bx0 = min(bx0, __shfl_xor_sync(0xFFFFFFFFu, bx0, o));
+      by0 = min(by0, __shfl_xor_sync(0xFFFFFFFFu, by0, o));
+      bx1 = max(bx1, __shfl_xor_sync(0xFFFFFFFFu, bx1, o));
+      by1 = max(by1, __shfl_xor_sync(0xFFFFFFFFu, by1, o));
     }
     if (lane == 0 && by1 >= by0)
     {
@@ -670,14 +875,49 @@ k_dt_alloc(NodeWork * work, const int * __restrict__ count, unsigned long long *
 }
 
 // ---------------------------------------------------------------------------------------------------
+// max rule on VPQ voxels at once (one aligned 8-byte group): out = max(out, label) where the bit is set and
+// the input voxel is 0 (X:754-763 with the final overwrite of X:1623-1636 folded in)
+template <typename T>
+__device__ __forceinline__ void
+write_group(const T * __restrict__ in, T * out, unsigned long long g /* first voxel, multiple of VPQ */, unsigned bits, T label)
+{
+  constexpr int VPQ = 8 / sizeof(T);
+  union Q
+  {
+    unsigned long long u;
+    T v[VPQ];
+  };
+  Q qi, qo, qn;
+  qi.u = __ldg(reinterpret_cast<const unsigned long long *>(in + g));
+  unsigned long long * po = reinterpret_cast<unsigned long long *>(out + g);
+  qo.u = *po;
+  for (;;)
+  {
+    qn = qo;
+#pragma unroll
+    for (int k = 0; k < VPQ; ++k)
+      if (((bits >> k) & 1u) && qi.v[k] == 0 && qo.v[k] < label)
+        qn.v[k] = label;
+    if (qn.u == qo.u)
+      return;
+    unsigned long long prev = atomicCAS(po, qo.u, qn.u);
+    if (prev == qo.u)
+      return;
+    qo.u = prev;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_dt_emit(const NodeWork * __restrict__ work, const DtItem * __restrict__ witems, const int * __restrict__ witemCount,
           const uint32_t * __restrict__ scratch, uint32_t * arena, const T * __restrict__ in, T * out, long long VX, long long VY,
           long long VZ)
 {
+  constexpr int VPQ = 8 / sizeof(T);       // voxels per aligned 8-byte group
+  constexpr int GPW = 32 / VPQ + 1;        // groups a 32-pixel word can touch
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nItems = *witemCount;
+  const unsigned long long nvox = (unsigned long long)VX * VY * VZ;
   for (int it = blockIdx.x; it < nItems; it += gridDim.x)
   {
     const DtItem item = witems[it];
@@ -708,26 +948,77 @@ k_dt_emit(const NodeWork * __restrict__ work, const DtItem * __restrict__ witems
     }
     const int mwords = M.h * M.pitch;
     const int wBeg = item.w0 + warp * 32, wEnd = min(mwords, wBeg + 32);
-    for (int cell = wBeg; cell < wEnd; ++cell)
+    if (wBeg >= mwords)
+      continue;
+    // lane i crops word wBeg+i of the mid shape out of the median rows and stores it
+    uint32_t myM = 0;
     {
-      const int r = cell / M.pitch, wi = cell - r * M.pitch;
-      const int y = M.y0 + r, x = M.x0 + 32 * wi;
-      const uint32_t * row = Sb + (size_t)(y - uy0) * pitch;
-      const int rx = x - ux0; // >= 0
-      const int sw = rx >> 5, shf = rx & 31;
-      const uint32_t lo = __ldg(row + sw);
-      const uint32_t hi = sw + 1 < pitch ? __ldg(row + sw + 1) : 0u;
-      uint32_t m = __funnelshift_r(lo, hi, shf);
-      const int valid = M.w - 32 * wi;
-      if (valid < 32)
-        m &= (1u << valid) - 1u;
-      if (lane == 0)
-        arena[M.off + cell] = m;
-      if ((m >> lane) & 1u)
+      const int cell = wBeg + lane;
+      if (cell < wEnd)
       {
-        const unsigned long long a = vbase + (unsigned long long)((long long)(x + lane) * su + (long long)y * sv);
-        if (in[a] == 0)
-          atomic_max_pixel(out + a, label);
+        const int r = cell / M.pitch, wi = cell - r * M.pitch;
+        const int y = M.y0 + r, x = M.x0 + 32 * wi;
+        const uint32_t * row = Sb + (size_t)(y - uy0) * pitch;
+        const int rx = x - ux0; // >= 0
+        const int sw = rx >> 5, shf = rx & 31;
+        const uint32_t lo = __ldg(row + sw);
+        const uint32_t hi = sw + 1 < pitch ? __ldg(row + sw + 1) : 0u;
+        myM = __funnelshift_r(lo, hi, shf);
+        const int valid = M.w - 32 * wi;
+        if (valid < 32)
+          myM &= (1u << valid) - 1u;
+        arena[M.off + cell] = myM;
+      }
+    }
+    if (su == 1)
+    {
+      // x runs along the bits: aligned 8-byte groups, one per lane
+      const int nTasks = (wEnd - wBeg) * GPW;
+      for (int tb = 0; tb < nTasks; tb += 32)
+      {
+        const int task = tb + lane;
+        const int c = min(task / GPW, wEnd - wBeg - 1), q = task % GPW;
+        const uint32_t m = __shfl_sync(0xFFFFFFFFu, myM, c);
+        if (task < nTasks && m)
+        {
+          const int cell = wBeg + c;
+          const int r = cell / M.pitch, wi = cell - r * M.pitch;
+          const unsigned long long a0 = vbase + (unsigned long long)((long long)(M.x0 + 32 * wi) + (long long)(M.y0 + r) * sv);
+          const unsigned long long g = (a0 & ~(unsigned long long)(VPQ - 1)) + (unsigned long long)q * VPQ;
+          // bits of this group: voxel g+k <-> bit (g + k - a0)
+          const long long sh = (long long)g - (long long)a0; // in (-VPQ, 32]
+          unsigned bits;
+          if (sh >= 32)
+            bits = 0u;
+          else if (sh >= 0)
+            bits = (m >> sh) & ((1u << VPQ) - 1u);
+          else
+            bits = (m << (-sh)) & ((1u << VPQ) - 1u);
+          if (bits && g + VPQ <= nvox)
+            write_group<T>(in, out, g, bits, label);
+          else if (bits)
+          {
+            for (int k = 0; k < VPQ; ++k)
+              if (((bits >> k) & 1u) && g + k < nvox && in[g + k] == 0)
+                atomic_max_pixel(out + g + k, label);
+          }
+        }
+      }
+    }
+    else
+    {
+      for (int c = 0; c < wEnd - wBeg; ++c)
+      {
+        const uint32_t m = __shfl_sync(0xFFFFFFFFu, myM, c);
+        if ((m >> lane) & 1u)
+        {
+          const int cell = wBeg + c;
+          const int r = cell / M.pitch, wi = cell - r * M.pitch;
+          const unsigned long long a =
+            vbase + (unsigned long long)((long long)(M.x0 + 32 * wi + lane) * su + (long long)(M.y0 + r) * sv);
+          if (in[a] == 0)
+            atomic_max_pixel(out + a, label);
+        }
       }
     }
   }
@@ -741,23 +1032,24 @@ launch_dt_level(Launch & L, int ptype, const DtLevel & lv)
     return;
   const int nodeGrid = std::max(1, std::min(lv.maxNodes, L.sms * 8));
   const int itemGrid = std::max(1, std::min(lv.itemCap, L.sms * 8));
+  const int histGrid = std::max(1, std::min((lv.hitemCap + 7) / 8, L.sms * 8));
   L.pre();
   k_dt_prep<<<nodeGrid, 256, 0, L.stream>>>(lv.nodes, lv.count, lv.work, lv.arena, lv.scratch, lv.scratchTop, lv.scratchCap,
-                                             lv.items, lv.itemCount, lv.itemCap, lv.err);
+                                             lv.items, lv.itemCount, lv.itemCap, lv.hitems, lv.hitemCount, lv.hitemCap, lv.err);
   L.post("k_dt_prep");
   L.pre();
   switch (ptype)
   {
     case MCI_U8:
-      k_dt_hist<uint8_t><<<itemGrid, 256, 0, L.stream>>>(lv.work, lv.items, lv.itemCount, lv.scratch, lv.hist, lv.histStride,
+      k_dt_hist<uint8_t><<<histGrid, 256, 0, L.stream>>>(lv.work, lv.hitems, lv.hitemCount, lv.hitemCap, lv.scratch, lv.hist, lv.histStride,
                                                           lv.histSide, lv.bigHist, lv.bigCount, lv.nbig, lv.err);
       break;
     case MCI_U16:
-      k_dt_hist<uint16_t><<<itemGrid, 256, 0, L.stream>>>(lv.work, lv.items, lv.itemCount, lv.scratch, lv.hist, lv.histStride,
+      k_dt_hist<uint16_t><<<histGrid, 256, 0, L.stream>>>(lv.work, lv.hitems, lv.hitemCount, lv.hitemCap, lv.scratch, lv.hist, lv.histStride,
                                                            lv.histSide, lv.bigHist, lv.bigCount, lv.nbig, lv.err);
       break;
     default:
-      k_dt_hist<int16_t><<<itemGrid, 256, 0, L.stream>>>(lv.work, lv.items, lv.itemCount, lv.scratch, lv.hist, lv.histStride,
+      k_dt_hist<int16_t><<<histGrid, 256, 0, L.stream>>>(lv.work, lv.hitems, lv.hitemCount, lv.hitemCap, lv.scratch, lv.hist, lv.histStride,
                                                           lv.histSide, lv.bigHist, lv.bigCount, lv.nbig, lv.err);
   }
   L.post("k_dt_hist");

@@ -644,9 +644,10 @@ k_extract(const SliceDev * __restrict__ slices, const ExtractJob * __restrict__ 
   const ExtractJob J = jobs[blockIdx.x];
   const SliceDev S = slices[J.slice];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int cells = J.m.h * J.m.pitch;
-  for (int cell = warp; cell < cells; cell += nwarps)
+  const int cells = J.nrows * J.m.pitch;
+  for (int c = warp; c < cells; c += nwarps)
   {
+    const int cell = J.row0 * J.m.pitch + c;
     const int r = cell / J.m.pitch, wi = cell % J.m.pitch;
     const int x = wi * 32 + lane;
     bool on = false;
@@ -677,21 +678,30 @@ launch_extract(Launch & L, const SliceDev * slices, const ExtractJob * jobs, int
 // queued-but-unscored entries are scored in parallel (one warp each); one thread then replays the
 // reference's sequential pop / compare / expand logic over those scores, which pushes the next wave.
 // ================================================================================================
+#define ALIGN_THREADS 512
+#define ALIGN_MASK_WORDS 12288 // shared-memory budget (words) for staging the shapes of one job
+
+// score of one translation, computed by `nl` cooperating lanes (a whole warp); data pointers may be shared memory
 __device__ __forceinline__ unsigned
-align_score(const AlignJob & J, const MaskRef * __restrict__ refs, const uint32_t * __restrict__ arena, int tx, int ty, int lane)
+align_score(const AlignJob & J, const MaskRef & A, const uint32_t * Ad, const MaskRef * __restrict__ refs,
+            const uint32_t * const * Bd, int tx, int ty, int lane)
 {
-  const MaskRef A = refs[J.aRef];
   if (J.kind == JOB_EXTRAPOLATE)
-    return mask_bit(arena, A, J.phx - tx, J.phy - ty) ? 1u : 0u;
+  {
+    int rx = J.phx - tx - A.x0, ry = J.phy - ty - A.y0;
+    if ((unsigned)rx >= (unsigned)A.w || (unsigned)ry >= (unsigned)A.h)
+      return 0u;
+    return (Ad[(size_t)ry * A.pitch + (rx >> 5)] >> (rx & 31)) & 1u;
+  }
   unsigned total = 0;
   for (int k = 0; k < J.nB; ++k)
   {
     const MaskRef B = refs[J.bRef + k];
+    const uint32_t * Bk = Bd[k];
     int ylo = max(A.y0, B.y0 - ty), yhi = min(A.y0 + A.h, B.y0 + B.h - ty);
     unsigned c = 0;
     if (yhi > ylo)
     {
-      // columns of A that can meet B
       int wlo = max(0, (B.x0 - tx - A.x0) >> 5), whi = min(A.pitch, ((B.x0 + B.w - tx - A.x0 + 31) >> 5));
       int nw = whi - wlo;
       if (nw > 0)
@@ -699,11 +709,11 @@ align_score(const AlignJob & J, const MaskRef * __restrict__ refs, const uint32_
         int cells = (yhi - ylo) * nw;
         for (int cell = lane; cell < cells; cell += 32)
         {
-          int r = cell / nw, wi = wlo + cell % nw;
+          int r = cell / nw, wi = wlo + cell - r * nw;
           int y = ylo + r;
-          uint32_t a = arena[A.off + (u64)(y - A.y0) * (u64)A.pitch + wi];
+          uint32_t a = Ad[(size_t)(y - A.y0) * A.pitch + wi];
           if (a)
-            c += __popc(a & mask_word(arena, B, y + ty, A.x0 + 32 * wi + tx));
+            c += __popc(a & mask_word_p(Bk, B, y + ty, A.x0 + 32 * wi + tx));
         }
       }
     }
@@ -717,29 +727,62 @@ align_score(const AlignJob & J, const MaskRef * __restrict__ refs, const uint32_
   return total;
 }
 
-__global__ void __launch_bounds__(256)
+#define ALIGN_MAX_STAGED 8 // components of the other slice whose data pointers are kept per job
+
+__global__ void __launch_bounds__(ALIGN_THREADS)
 k_align(const AlignJob * __restrict__ jobs, int njobs, const MaskRef * __restrict__ refs, const uint32_t * __restrict__ arena,
         uint32_t * gscratch, int heuristic, int2 * result, int * err)
 {
   extern __shared__ uint32_t smem[];
   __shared__ int s_head, s_tail, s_scored, s_done;
+  __shared__ const uint32_t * s_B[ALIGN_MAX_STAGED];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int jb = blockIdx.x; jb < njobs; jb += gridDim.x)
   {
     const AlignJob J = jobs[jb];
+    const MaskRef A = refs[J.aRef];
     const int bpitch = (J.sw + 31) >> 5;
     const int bwords = bpitch * J.sh;
-    uint32_t * bitmap = J.useSmem ? smem : gscratch + J.bitmapOff;
-    uint32_t * qbuf = J.useSmem ? smem + bwords : gscratch + J.queueOff;
+    // shared memory: [staged shapes][visited bitmap][queue]; the last two move to global scratch for huge searches
+    uint32_t * stage = smem;
+    uint32_t * bitmap = J.useSmem ? smem + ALIGN_MASK_WORDS : gscratch + J.bitmapOff;
+    uint32_t * qbuf = J.useSmem ? smem + ALIGN_MASK_WORDS + bwords : gscratch + J.queueOff;
     int * qx = (int *)qbuf;
     int * qy = qx + J.qcap;
     unsigned * qs = (unsigned *)(qy + J.qcap);
     const int qmask = J.qcap - 1;
     __syncthreads();
+    // stage the shapes when they fit
+    const int aWords = A.h * A.pitch;
+    int used = 0;
+    const uint32_t * Ad = arena + A.off;
+    if (aWords <= ALIGN_MASK_WORDS)
+    {
+      for (int k = threadIdx.x; k < aWords; k += blockDim.x)
+        stage[k] = arena[A.off + k];
+      Ad = stage;
+      used = aWords;
+    }
+    const bool listOk = J.nB <= ALIGN_MAX_STAGED;
+    for (int q = 0; q < J.nB && q < ALIGN_MAX_STAGED; ++q)
+    {
+      const MaskRef B = refs[J.bRef + q];
+      const int bW = B.h * B.pitch;
+      const uint32_t * src = arena + B.off;
+      if (used + bW <= ALIGN_MASK_WORDS)
+      {
+        for (int k = threadIdx.x; k < bW; k += blockDim.x)
+          stage[used + k] = src[k];
+        if (threadIdx.x == 0)
+          s_B[q] = stage + used;
+        used += bW;
+      }
+      else if (threadIdx.x == 0)
+        s_B[q] = src;
+    }
     for (int k = threadIdx.x; k < bwords; k += blockDim.x)
       bitmap[k] = 0u;
     __syncthreads();
-    // replay state lives in registers of thread 0
     unsigned maxScore = 0;
     long long iter = 0;
     int bestx = 0, besty = 0;
@@ -763,7 +806,27 @@ k_align(const AlignJob * __restrict__ jobs, int njobs, const MaskRef * __restric
       const int from = s_scored, to = s_tail;
       for (int e = from + warp; e < to; e += nwarps)
       {
-        unsigned sc = align_score(J, refs, arena, qx[e & qmask], qy[e & qmask], lane);
+        unsigned sc;
+        if (listOk)
+          sc = align_score(J, A, Ad, refs, s_B, qx[e & qmask], qy[e & qmask], lane);
+        else
+        {
+          // many components on the other side: walk them straight from the arena
+          unsigned total = 0;
+          bool ok = true;
+          for (int k = 0; k < J.nB && ok; ++k)
+          {
+            AlignJob one = J;
+            one.nB = 1;
+            one.bRef = J.bRef + k;
+            const uint32_t * bp = arena + refs[J.bRef + k].off;
+            unsigned c = align_score(one, A, Ad, refs, &bp, qx[e & qmask], qy[e & qmask], lane);
+            if (c == 0)
+              ok = false;
+            total += c;
+          }
+          sc = ok ? total : 0u;
+        }
         if (lane == 0)
           qs[e & qmask] = sc;
       }
@@ -841,7 +904,8 @@ launch_align(Launch & L, const AlignJob * jobs, int njobs, const MaskRef * refs,
   }
   int grid = std::min(njobs, L.sms * 8);
   L.pre();
-  k_align<<<grid, 256, smemBytes, L.stream>>>(jobs, njobs, refs, arena, gscratch, heuristic, result, err);
+  k_align<<<grid, ALIGN_THREADS, smemBytes + ALIGN_MASK_WORDS * 4, L.stream>>>(jobs, njobs, refs, arena, gscratch, heuristic,
+                                                                              result, err);
   L.post("k_align");
 }
 
@@ -849,60 +913,78 @@ launch_align(Launch & L, const AlignJob * jobs, int njobs, const MaskRef * refs,
 // K9  1-to-N split: synchronous multi-source geodesic growth inside the mask, ties to the
 //     lowest index (Interpolate1toN, X:824-986)
 // ================================================================================================
-__global__ void __launch_bounds__(256)
+#define SPLIT_THREADS 1024
+__global__ void __launch_bounds__(SPLIT_THREADS)
 k_split(const SplitJob * __restrict__ jobs, const MaskRef * __restrict__ refs, uint32_t * arena, uint32_t * gscratch,
-        const int2 * __restrict__ trans, int ball, int * err)
+        const int2 * __restrict__ trans, int ball, int smemWords, int * err)
 {
+  extern __shared__ uint32_t smem[];
   const SplitJob J = jobs[blockIdx.x];
   const MaskRef A = refs[J.aRef];
   const int2 t = trans[J.job];
   const int words = A.h * A.pitch;
+  const int nB = J.nB;
+  // planes: mask | cur[nB] | nxt[nB]; in shared memory when they fit, else mask in the arena and the
+  // ping-pong planes in the arena (final home) and global scratch
+  const bool inSmem = (long long)(1 + 2 * nB) * words <= smemWords;
   const uint32_t * mask = arena + A.off;
+  uint32_t * cur = inSmem ? smem + words : nullptr;
+  uint32_t * nxt = inSmem ? smem + (size_t)(1 + nB) * words : nullptr;
+  if (inSmem)
+  {
+    for (int idx = threadIdx.x; idx < words; idx += blockDim.x)
+      smem[idx] = arena[A.off + idx];
+    mask = smem;
+  }
+  auto plane = [&](bool wantCur, bool curIsFirst, int k) -> uint32_t * {
+    if (inSmem)
+      return (wantCur == curIsFirst ? cur : nxt) + (size_t)k * words;
+    // global: "first" buffer = arena planes, "second" = scratch
+    return (wantCur == curIsFirst) ? arena + refs[J.outRef + k].off : gscratch + J.scratchOff + (u64)k * words;
+  };
+  __syncthreads();
   // seeds: pixels of the mask whose translate lies in component k of the other slice (X:871-892)
   for (int idx = threadIdx.x; idx < words; idx += blockDim.x)
   {
     int r = idx / A.pitch, wi = idx % A.pitch;
     uint32_t m = mask[idx];
-    for (int k = 0; k < J.nB; ++k)
+    for (int k = 0; k < nB; ++k)
     {
       const MaskRef B = refs[J.bRef + k];
-      arena[refs[J.outRef + k].off + idx] = m ? (m & mask_word(arena, B, A.y0 + r + t.y, A.x0 + 32 * wi + t.x)) : 0u;
+      plane(true, true, k)[idx] = m ? (m & mask_word(arena, B, A.y0 + r + t.y, A.x0 + 32 * wi + t.x)) : 0u;
     }
   }
   __syncthreads();
-  // growth (X:905-963).  cur = planes in the arena (final home), nxt = scratch; swapped every step.
-  bool curIsArena = true;
+  // growth (X:905-963): every blob dilates inside the mask at once; a free pixel reached by several blobs in
+  // the same step goes to the lowest index
+  bool curIsFirst = true;
   for (int step = 0;; ++step)
   {
-    int pending = 0, grew = 0;
+    int flags = 0; // bit 0: free pixels remain, bit 1: something grew
     for (int idx = threadIdx.x; idx < words; idx += blockDim.x)
     {
       int r = idx / A.pitch, wi = idx % A.pitch;
       uint32_t m = mask[idx];
       uint32_t owned = 0;
-      for (int k = 0; k < J.nB; ++k)
-      {
-        const uint32_t * cur = curIsArena ? arena + refs[J.outRef + k].off : gscratch + J.scratchOff + (u64)k * words;
-        owned |= cur[idx];
-      }
+      for (int k = 0; k < nB; ++k)
+        owned |= plane(true, curIsFirst, k)[idx];
       uint32_t freeBits = m & ~owned;
       uint32_t taken = 0;
-      for (int k = 0; k < J.nB; ++k)
+      for (int k = 0; k < nB; ++k)
       {
-        const uint32_t * cur = curIsArena ? arena + refs[J.outRef + k].off : gscratch + J.scratchOff + (u64)k * words;
-        uint32_t * nxt = curIsArena ? gscratch + J.scratchOff + (u64)k * words : arena + refs[J.outRef + k].off;
-        uint32_t c = freeBits ? (dilate_word(cur, A.h, A.pitch, r, wi, ball != 0) & freeBits & ~taken) : 0u;
-        nxt[idx] = cur[idx] | c;
-        taken |= c;
+        const uint32_t * c = plane(true, curIsFirst, k);
+        uint32_t g = freeBits ? (dilate_word(c, A.h, A.pitch, r, wi, ball != 0) & freeBits & ~taken) : 0u;
+        plane(false, curIsFirst, k)[idx] = c[idx] | g;
+        taken |= g;
       }
       if (freeBits & ~taken)
-        pending = 1;
+        flags |= 1;
       if (taken)
-        grew = 1;
+        flags |= 2;
     }
-    pending = __syncthreads_or(pending);
-    grew = __syncthreads_or(grew);
-    curIsArena = !curIsArena;
+    const int pending = __syncthreads_or(flags & 1); // (returns a truth value, not the OR of the bits)
+    const int grew = __syncthreads_or(flags & 2);
+    curIsFirst = !curIsFirst;
     if (!pending)
       break;
     if (!grew)
@@ -912,11 +994,12 @@ k_split(const SplitJob * __restrict__ jobs, const MaskRef * __restrict__ refs, u
       break;
     }
   }
-  if (!curIsArena)
+  // final planes -> arena
+  if (inSmem || !curIsFirst)
   {
     for (int idx = threadIdx.x; idx < words; idx += blockDim.x)
-      for (int k = 0; k < J.nB; ++k)
-        arena[refs[J.outRef + k].off + idx] = gscratch[J.scratchOff + (u64)k * words + idx];
+      for (int k = 0; k < nB; ++k)
+        arena[refs[J.outRef + k].off + idx] = plane(true, curIsFirst, k)[idx];
   }
 }
 
@@ -926,8 +1009,15 @@ launch_split(Launch & L, const SplitJob * jobs, int njobs, const MaskRef * refs,
 {
   if (njobs == 0)
     return;
+  static bool attr = false;
+  if (!attr)
+  {
+    cudaFuncSetAttribute(k_split, cudaFuncAttributeMaxDynamicSharedMemorySize, L.maxSmem - 1024);
+    attr = true;
+  }
+  const int smemBytes = 160 * 1024;
   L.pre();
-  k_split<<<njobs, 256, 0, L.stream>>>(jobs, refs, arena, gscratch, trans, ball, err);
+  k_split<<<njobs, SPLIT_THREADS, smemBytes, L.stream>>>(jobs, refs, arena, gscratch, trans, ball, smemBytes / 4, err);
   L.post("k_split");
 }
 

@@ -31,6 +31,22 @@ mask_word(const uint32_t * __restrict__ arena, const MaskRef & m, int y, int X)
   return __funnelshift_r(lo, hi, sh);
 }
 
+// same, with `data` pointing at the first word of the mask (global or shared memory)
+__device__ __forceinline__ uint32_t
+mask_word_p(const uint32_t * data, const MaskRef & m, int y, int X)
+{
+  int ry = y - m.y0;
+  if ((unsigned)ry >= (unsigned)m.h)
+    return 0u;
+  int rx = X - m.x0;
+  int wi = rx >> 5;
+  int sh = rx & 31;
+  const uint32_t * row = data + (size_t)ry * m.pitch;
+  uint32_t lo = ((unsigned)wi < (unsigned)m.pitch) ? row[wi] : 0u;
+  uint32_t hi = ((unsigned)(wi + 1) < (unsigned)m.pitch) ? row[wi + 1] : 0u;
+  return __funnelshift_r(lo, hi, sh);
+}
+
 __device__ __forceinline__ bool
 mask_bit(const uint32_t * __restrict__ arena, const MaskRef & m, int x, int y)
 {

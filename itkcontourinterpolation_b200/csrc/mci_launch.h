@@ -85,6 +85,9 @@ struct DtLevel
   DtItem * witems;
   int * witemCount;
   int itemCap;
+  DtItem * hitems; // histogram work items (8-word chunks holding xor pixels)
+  int * hitemCount;
+  int hitemCap;
   unsigned * hist;
   int histStride, histSide;
   unsigned * bigHist;

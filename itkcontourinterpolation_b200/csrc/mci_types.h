@@ -54,6 +54,7 @@ struct CompStat
 struct ExtractJob
 {
   int slice, id;
+  int row0, nrows; // tile of the mask's rows
   MaskRef m;
 };
 

@@ -213,8 +213,28 @@ launch_compact_labels(Launch & L, const int * bbox, int nl, const uint32_t * sli
 // Union-find on pixels with the smaller index as parent, so every root is its component's
 // raster-first pixel; consecutive ids = rank of the root in raster order.
 // ================================================================================================
+// representative of p with intermediate pointer jumping (path halving): every value written is an
+// ancestor of the cell it is written to, and parents only ever decrease, so racing writers are harmless
 __device__ __forceinline__ uint32_t
 uf_find(volatile uint32_t * parent, uint32_t p)
+{
+  uint32_t curr = parent[p];
+  if (curr != p)
+  {
+    uint32_t prev = p, next;
+    while (curr > (next = parent[curr]))
+    {
+      parent[prev] = next;
+      prev = curr;
+      curr = next;
+    }
+  }
+  return curr;
+}
+// read-only walk to the root (used once all unions are done: the flatten pass must leave every pixel
+// pointing at its ROOT, which racing path-halving writes could undo)
+__device__ __forceinline__ uint32_t
+uf_root(const volatile uint32_t * parent, uint32_t p)
 {
   uint32_t q;
   while ((q = parent[p]) != p)
@@ -330,7 +350,7 @@ k_cc_flatten(const SliceDev * __restrict__ slices, const RowTile * __restrict__ 
       const uint32_t p = (uint32_t)y * (uint32_t)S.w + (uint32_t)x;
       if (parent[p] != MCI_NOLABEL)
       {
-        uint32_t r = uf_find(parent, p);
+        uint32_t r = uf_root(parent, p);
         root = r == p;
         if (!root)
           parent[p] = r;
@@ -727,6 +747,38 @@ align_score(const AlignJob & J, const MaskRef & A, const uint32_t * Ad, const Ma
   return total;
 }
 
+// one slice (part of nparts) of the overlap count between A and a single component B at translation (tx, ty)
+__device__ __forceinline__ unsigned
+align_score_part(const MaskRef & A, const uint32_t * Ad, const MaskRef & B, const uint32_t * Bk, int tx, int ty, int part,
+                 int nparts, int lane)
+{
+  const int ylo = max(A.y0, B.y0 - ty), yhi = min(A.y0 + A.h, B.y0 + B.h - ty);
+  unsigned c = 0;
+  if (yhi > ylo)
+  {
+    const int wlo = max(0, (B.x0 - tx - A.x0) >> 5), whi = min(A.pitch, ((B.x0 + B.w - tx - A.x0 + 31) >> 5));
+    const int nw = whi - wlo;
+    if (nw > 0)
+    {
+      const int cells = (yhi - ylo) * nw;
+      const int c0 = (int)((long long)cells * part / nparts), c1 = (int)((long long)cells * (part + 1) / nparts);
+#pragma unroll 4
+      for (int cell = c0 + lane; cell < c1; cell += 32)
+      {
+        const int r = cell / nw, wi = wlo + cell - r * nw;
+        const int y = ylo + r;
+        const uint32_t a = Ad[(size_t)(y - A.y0) * A.pitch + wi];
+        if (a)
+          c += __popc(a & mask_word_p(Bk, B, y + ty, A.x0 + 32 * wi + tx));
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+  return c;
+}
+
 #define ALIGN_MAX_STAGED 8 // components of the other slice whose data pointers are kept per job
 
 __global__ void __launch_bounds__(ALIGN_THREADS)
@@ -792,6 +844,7 @@ k_align(const AlignJob * __restrict__ jobs, int njobs, const MaskRef * __restric
       qy[0] = 0;
       qx[1] = J.indx;
       qy[1] = J.indy;
+      qs[0] = qs[1] = 0u;
       bitmap[(0 - J.sy0) * bpitch + ((0 - J.sx0) >> 5)] |= 1u << ((0 - J.sx0) & 31);
       if ((unsigned)(J.indx - J.sx0) < (unsigned)J.sw && (unsigned)(J.indy - J.sy0) < (unsigned)J.sh)
         bitmap[(J.indy - J.sy0) * bpitch + ((J.indx - J.sx0) >> 5)] |= 1u << ((J.indx - J.sx0) & 31);
@@ -804,6 +857,21 @@ k_align(const AlignJob * __restrict__ jobs, int njobs, const MaskRef * __restric
     for (;;)
     {
       const int from = s_scored, to = s_tail;
+      if (J.kind == JOB_ONE_TO_ONE && to - from < nwarps)
+      {
+        // few translations queued: several warps share one evaluation, partial counts meet in the queue slot
+        // (slots are zeroed when pushed)
+        const int nE = to - from, G = nwarps / nE;
+        const MaskRef B0 = refs[J.bRef];
+        for (int task = warp; task < nE * G; task += nwarps)
+        {
+          const int e = from + task / G, part = task % G;
+          unsigned c = align_score_part(A, Ad, B0, s_B[0], qx[e & qmask], qy[e & qmask], part, G, lane);
+          if (lane == 0 && c)
+            atomicAdd(&qs[e & qmask], c);
+        }
+      }
+      else
       for (int e = from + warp; e < to; e += nwarps)
       {
         unsigned sc;
@@ -868,6 +936,7 @@ k_align(const AlignJob * __restrict__ jobs, int njobs, const MaskRef * __restric
                   {
                     qx[tail & qmask] = nx;
                     qy[tail & qmask] = ny;
+                    qs[tail & qmask] = 0u;
                     ++tail;
                   }
                   ++iter;
@@ -956,13 +1025,32 @@ k_split(const SplitJob * __restrict__ jobs, const MaskRef * __restrict__ refs, u
   }
   __syncthreads();
   // growth (X:905-963): every blob dilates inside the mask at once; a free pixel reached by several blobs in
-  // the same step goes to the lowest index
-  bool curIsFirst = true;
-  for (int step = 0;; ++step)
+  // the same step goes to the lowest index.  A connected mask of P pixels fills in at most P steps; if free
+  // pixels remain after that no seed can reach them (the reference would loop forever).
+  __shared__ int s_pixels;
+  if (threadIdx.x == 0)
+    s_pixels = 0;
+  __syncthreads();
   {
-    int flags = 0; // bit 0: free pixels remain, bit 1: something grew
+    int c = 0;
     for (int idx = threadIdx.x; idx < words; idx += blockDim.x)
+      c += __popc(mask[idx]);
+    if (c)
+      atomicAdd(&s_pixels, c);
+  }
+  __syncthreads();
+  const int maxSteps = s_pixels + 1;
+  bool curIsFirst = true;
+  unsigned settled = 0; // bit j: my j-th word has no free pixel left and both buffers hold its final planes
+  int pending = 1;
+  for (int step = 0; step < maxSteps && pending; ++step)
+  {
+    int flag = 0;
+    int j = 0;
+    for (int idx = threadIdx.x; idx < words; idx += blockDim.x, ++j)
     {
+      if (j < 32 && ((settled >> j) & 1u))
+        continue;
       int r = idx / A.pitch, wi = idx % A.pitch;
       uint32_t m = mask[idx];
       uint32_t owned = 0;
@@ -978,22 +1066,15 @@ k_split(const SplitJob * __restrict__ jobs, const MaskRef * __restrict__ refs, u
         taken |= g;
       }
       if (freeBits & ~taken)
-        flags |= 1;
-      if (taken)
-        flags |= 2;
+        flag = 1;
+      if (!freeBits && j < 32)
+        settled |= 1u << j;
     }
-    const int pending = __syncthreads_or(flags & 1); // (returns a truth value, not the OR of the bits)
-    const int grew = __syncthreads_or(flags & 2);
+    pending = __syncthreads_or(flag);
     curIsFirst = !curIsFirst;
-    if (!pending)
-      break;
-    if (!grew)
-    {
-      if (threadIdx.x == 0)
-        atomicMax(err, ERR_SPLIT_STUCK); // reference would loop forever: a mask pixel no seed can reach
-      break;
-    }
   }
+  if (pending && threadIdx.x == 0)
+    atomicMax(err, ERR_SPLIT_STUCK);
   // final planes -> arena
   if (inSmem || !curIsFirst)
   {

@@ -172,6 +172,8 @@ int mci_interpolate(mci_ctx * ctx, int32_t n_jobs, const mci_job * jobs, const i
                     const mci_params * params);
 /* translations chosen by Align, 2 ints per job (parity tests) */
 int mci_get_translations(mci_ctx * ctx, int32_t * t /* [2*n_jobs] */);
+/* per job: translations popped, scoring waves, SM clock cycles, kind*1000 + n_b (diagnostics) */
+int mci_get_align_stats(mci_ctx * ctx, int32_t * out /* [4*n_jobs] */);
 
 /* ---- host scheduler (layer 2): the filter itself --------------------------------------------
  * Mirrors the setters of H:85-165 and GenerateData (X:1559-1637). */

@@ -102,6 +102,7 @@ SYMBOLS = [
     ("mci_get_pairs", _I, [_P, _P]),
     ("mci_interpolate", _I, [_P, ctypes.c_int32, _P, _P, ctypes.c_int32, ctypes.POINTER(Params)]),
     ("mci_get_translations", _I, [_P, _P]),
+    ("mci_get_align_stats", _I, [_P, _P]),
     ("mci_filter_default_options", None, [ctypes.POINTER(FilterOptions)]),
     ("mci_filter_run", _I, [_P, ctypes.POINTER(FilterOptions), _P, _P, ctypes.POINTER(ctypes.c_int64), _I, _P,
                             ctypes.c_int64, ctypes.POINTER(FilterStats)]),

@@ -949,7 +949,7 @@ extern "C"
     MaskRef * dRefs = (MaskRef *)(jb + oRefs);
     CK(ctx->dArena.ensure(arenaCap * 4));
     CK(ctx->dScratch.ensure((scratchWords + 64) * 4));
-    CK(ctx->dTrans.ensure(size_t(njobs) * sizeof(int2)));
+    CK(ctx->dTrans.ensure(size_t(njobs) * (sizeof(int2) + sizeof(int4)) + 64));
     long long nodeTotal = 0;
     for (long long c : levelCap)
       nodeTotal += c;
@@ -967,7 +967,8 @@ extern "C"
     launch_extract(ctx->L, ctx->dSlices, (ExtractJob *)(jb + oExtract), (int)extracts.size(), (uint16_t *)ctx->dConn.p,
                    (uint32_t *)ctx->dArena.p);
     launch_align(ctx->L, (AlignJob *)(jb + oAlign), njobs, dRefs, (uint32_t *)ctx->dArena.p, (uint32_t *)ctx->dScratch.p,
-                 prm->heuristic_alignment, (int2 *)ctx->dTrans.p, alignSmem, ctx->dErr);
+                 prm->heuristic_alignment, (int2 *)ctx->dTrans.p,
+                 (int4 *)((uint8_t *)ctx->dTrans.p + ((size_t(njobs) * sizeof(int2) + 15) & ~size_t(15))), alignSmem, ctx->dErr);
     launch_split(ctx->L, (SplitJob *)(jb + oSplit), (int)splits.size(), dRefs, (uint32_t *)ctx->dArena.p,
                  (uint32_t *)ctx->dScratch.p, (int2 *)ctx->dTrans.p, prm->use_ball, ctx->dErr);
     Node * dNodes = (Node *)ctx->dNodes.p;
@@ -1084,6 +1085,21 @@ extern "C"
       }
     }
     CK(cudaGetLastError());
+    return MCI_OK;
+  }
+
+  // per job: pops, waves, clock cycles, kind*1000 + n_b (performance diagnostics)
+  int mci_get_align_stats(mci_ctx * ctx, int32_t * out /* [4*n_jobs] */)
+  {
+    if (!ctx || !out)
+      return MCI_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->nJobs)
+    {
+      CK(cudaMemcpyAsync(out, (uint8_t *)ctx->dTrans.p + ((size_t(ctx->nJobs) * sizeof(int2) + 15) & ~size_t(15)),
+                         size_t(ctx->nJobs) * 16, cudaMemcpyDeviceToHost, ctx->L.stream));
+      CK(cudaStreamSynchronize(ctx->L.stream));
+    }
     return MCI_OK;
   }
 

@@ -700,76 +700,61 @@ launch_extract(Launch & L, const SliceDev * slices, const ExtractJob * jobs, int
 // ================================================================================================
 #define ALIGN_THREADS 512
 #define ALIGN_MASK_WORDS 12288 // shared-memory budget (words) for staging the shapes of one job
+#define ALIGN_MAX_STAGED 8     // components of the other slice kept staged / addressed per job
 
-// score of one translation, computed by `nl` cooperating lanes (a whole warp); data pointers may be shared memory
-__device__ __forceinline__ unsigned
-align_score(const AlignJob & J, const MaskRef & A, const uint32_t * Ad, const MaskRef * __restrict__ refs,
-            const uint32_t * const * Bd, int tx, int ty, int lane)
+// a shape as the scoring loop sees it: geometry + where its rows live (arena or shared memory) + row pitch there
+struct AlignShape
 {
-  if (J.kind == JOB_EXTRAPOLATE)
-  {
-    int rx = J.phx - tx - A.x0, ry = J.phy - ty - A.y0;
-    if ((unsigned)rx >= (unsigned)A.w || (unsigned)ry >= (unsigned)A.h)
-      return 0u;
-    return (Ad[(size_t)ry * A.pitch + (rx >> 5)] >> (rx & 31)) & 1u;
-  }
-  unsigned total = 0;
-  for (int k = 0; k < J.nB; ++k)
-  {
-    const MaskRef B = refs[J.bRef + k];
-    const uint32_t * Bk = Bd[k];
-    int ylo = max(A.y0, B.y0 - ty), yhi = min(A.y0 + A.h, B.y0 + B.h - ty);
-    unsigned c = 0;
-    if (yhi > ylo)
-    {
-      int wlo = max(0, (B.x0 - tx - A.x0) >> 5), whi = min(A.pitch, ((B.x0 + B.w - tx - A.x0 + 31) >> 5));
-      int nw = whi - wlo;
-      if (nw > 0)
-      {
-        int cells = (yhi - ylo) * nw;
-        for (int cell = lane; cell < cells; cell += 32)
-        {
-          int r = cell / nw, wi = wlo + cell - r * nw;
-          int y = ylo + r;
-          uint32_t a = Ad[(size_t)(y - A.y0) * A.pitch + wi];
-          if (a)
-            c += __popc(a & mask_word_p(Bk, B, y + ty, A.x0 + 32 * wi + tx));
-        }
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-      c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
-    if (c == 0)
-      return 0u; // iConn must intersect every listed component of jConn (X:1068-1075)
-    total += c;
-  }
-  return total;
-}
+  int x0, y0, w, h, words; // words = valid words per row
+  int pitch;               // row stride where the data lives (odd in shared memory: conflict-free row-per-lane access)
+  const uint32_t * data;
+  const uint32_t * rowInfo; // staged shapes: per row first | last<<13 | single-run<<26 | nonempty<<27 (else null)
+};
 
-// one slice (part of nparts) of the overlap count between A and a single component B at translation (tx, ty)
+// overlap count |{p in A : p + t in B}| over a slice of A's rows; one lane per row, words walked with a
+// running funnel shift (no per-word address arithmetic)
 __device__ __forceinline__ unsigned
-align_score_part(const MaskRef & A, const uint32_t * Ad, const MaskRef & B, const uint32_t * Bk, int tx, int ty, int part,
-                 int nparts, int lane)
+align_count(const AlignShape & A, const AlignShape & B, int tx, int ty, int part, int nparts, int lane)
 {
   const int ylo = max(A.y0, B.y0 - ty), yhi = min(A.y0 + A.h, B.y0 + B.h - ty);
   unsigned c = 0;
   if (yhi > ylo)
   {
-    const int wlo = max(0, (B.x0 - tx - A.x0) >> 5), whi = min(A.pitch, ((B.x0 + B.w - tx - A.x0 + 31) >> 5));
-    const int nw = whi - wlo;
-    if (nw > 0)
+    const int dx0 = A.x0 + tx - B.x0; // column of B under column 0 of A's first word
+    const int wlo = max(0, (-dx0) >> 5), whi = min(A.words, ((B.w - dx0 + 31) >> 5));
+    if (whi > wlo)
     {
-      const int cells = (yhi - ylo) * nw;
-      const int c0 = (int)((long long)cells * part / nparts), c1 = (int)((long long)cells * (part + 1) / nparts);
-#pragma unroll 4
-      for (int cell = c0 + lane; cell < c1; cell += 32)
+      const int rows = yhi - ylo;
+      const int r0 = (int)((long long)rows * part / nparts), r1 = (int)((long long)rows * (part + 1) / nparts);
+      const int off = dx0 >> 5, sh = dx0 & 31;
+      for (int r = r0 + lane; r < r1; r += 32)
       {
-        const int r = cell / nw, wi = wlo + cell - r * nw;
         const int y = ylo + r;
-        const uint32_t a = Ad[(size_t)(y - A.y0) * A.pitch + wi];
-        if (a)
-          c += __popc(a & mask_word_p(Bk, B, y + ty, A.x0 + 32 * wi + tx));
+        if (A.rowInfo && B.rowInfo)
+        {
+          // run-length shortcut: rows that are one run each overlap in an interval
+          const uint32_t ia = A.rowInfo[y - A.y0], ib = B.rowInfo[y + ty - B.y0];
+          if (!ia || !ib)
+            continue;
+          if ((ia >> 26) & (ib >> 26) & 1u)
+          {
+            const int a1 = A.x0 + (int)(ia & 0x1FFF), a2 = A.x0 + (int)((ia >> 13) & 0x1FFF);
+            const int b1 = B.x0 + (int)(ib & 0x1FFF) - tx, b2 = B.x0 + (int)((ib >> 13) & 0x1FFF) - tx;
+            c += (unsigned)max(0, min(a2, b2) - max(a1, b1) + 1);
+            continue;
+          }
+        }
+        const uint32_t * Arow = A.data + (size_t)(y - A.y0) * A.pitch;
+        const uint32_t * Brow = B.data + (size_t)(y + ty - B.y0) * B.pitch;
+        int bi = wlo + off;
+        uint32_t lo = ((unsigned)bi < (unsigned)B.words) ? Brow[bi] : 0u;
+        for (int wi = wlo; wi < whi; ++wi)
+        {
+          ++bi;
+          const uint32_t hi = ((unsigned)bi < (unsigned)B.words) ? Brow[bi] : 0u;
+          c += __popc(Arow[wi] & __funnelshift_r(lo, hi, sh));
+          lo = hi;
+        }
       }
     }
   }
@@ -779,20 +764,194 @@ align_score_part(const MaskRef & A, const uint32_t * Ad, const MaskRef & B, cons
   return c;
 }
 
-#define ALIGN_MAX_STAGED 8 // components of the other slice whose data pointers are kept per job
+__device__ __forceinline__ AlignShape
+align_shape(const MaskRef & m, const uint32_t * arena)
+{
+  AlignShape s;
+  s.x0 = m.x0;
+  s.y0 = m.y0;
+  s.w = m.w;
+  s.h = m.h;
+  s.words = m.pitch;
+  s.pitch = m.pitch;
+  s.data = arena + m.off;
+  s.rowInfo = nullptr;
+  return s;
+}
+
+// The breadth-first search itself.  Force-inlined and instantiated twice by k_align: once with pointers
+// that provably live in shared memory (LDS / STS / ATOMS), once with global scratch for huge searches.
+struct AlignBfsShared
+{
+  int head, tail, scored, done;
+};
+__device__ __forceinline__ void
+align_bfs(const AlignJob & J, const AlignShape & A, const AlignShape * sB, const MaskRef * __restrict__ refs,
+          const uint32_t * __restrict__ arena, uint32_t * bitmap, int * qx, int * qy, unsigned * qs, int bpitch, int heuristic,
+          volatile AlignBfsShared * st, int & bestx, int & besty, int & nWaves, int * err)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int qmask = J.qcap - 1;
+    unsigned maxScore = 0;
+    long long iter = 0;
+    bestx = 0;
+    besty = 0;
+    if (threadIdx.x == 0)
+    {
+      qx[0] = 0;
+      qy[0] = 0;
+      qx[1] = J.indx;
+      qy[1] = J.indy;
+      qs[0] = qs[1] = 0u;
+      bitmap[(0 - J.sy0) * bpitch + ((0 - J.sx0) >> 5)] |= 1u << ((0 - J.sx0) & 31);
+      if ((unsigned)(J.indx - J.sx0) < (unsigned)J.sw && (unsigned)(J.indy - J.sy0) < (unsigned)J.sh)
+        bitmap[(J.indy - J.sy0) * bpitch + ((J.indx - J.sx0) >> 5)] |= 1u << ((J.indx - J.sx0) & 31);
+      st->head = 0;
+      st->tail = 2;
+      st->scored = 0;
+      st->done = 0;
+    }
+    __syncthreads();
+    for (;;)
+    {
+      const int from = st->scored, to = st->tail;
+      ++nWaves;
+      if (J.kind == JOB_EXTRAPOLATE)
+      {
+        // the other shape is the phantom point: score = is the point, moved back by t, inside the shape (X:239-240)
+        for (int e = from + threadIdx.x; e < to; e += blockDim.x)
+        {
+          const int rx = J.phx - qx[e & qmask] - A.x0, ry = J.phy - qy[e & qmask] - A.y0;
+          unsigned sc = 0;
+          if ((unsigned)rx < (unsigned)A.w && (unsigned)ry < (unsigned)A.h)
+            sc = (A.data[(size_t)ry * A.pitch + (rx >> 5)] >> (rx & 31)) & 1u;
+          qs[e & qmask] = sc;
+        }
+      }
+      else if (J.nB == 1)
+      {
+        // several warps share one evaluation when few translations are queued; partial counts meet in the
+        // queue slot (slots are zeroed when pushed)
+        const int nE = to - from, G = max(1, nwarps / max(nE, 1));
+        for (int task = warp; task < nE * G; task += nwarps)
+        {
+          const int e = from + task / G, part = task % G;
+          unsigned c = align_count(A, sB[0], qx[e & qmask], qy[e & qmask], part, G, lane);
+          if (lane == 0 && c)
+            atomicAdd(&qs[e & qmask], c);
+        }
+      }
+      else
+      {
+        for (int e = from + warp; e < to; e += nwarps)
+        {
+          // iConn must intersect every listed component of jConn, else the score is 0 (X:1068-1075)
+          unsigned total = 0;
+          bool ok = true;
+          for (int k = 0; k < J.nB && ok; ++k)
+          {
+            unsigned c;
+            if (k < ALIGN_MAX_STAGED)
+              c = align_count(A, sB[k], qx[e & qmask], qy[e & qmask], 0, 1, lane);
+            else
+            {
+              const AlignShape Bk = align_shape(refs[J.bRef + k], arena);
+              c = align_count(A, Bk, qx[e & qmask], qy[e & qmask], 0, 1, lane);
+            }
+            ok = c != 0;
+            total += c;
+          }
+          if (lane == 0)
+            qs[e & qmask] = ok ? total : 0u;
+        }
+      }
+      __syncthreads();
+      if (warp == 0)
+      {
+        // the reference's sequential pop / compare / expand (X:1186-1219), replayed by one warp: all lanes
+        // carry the same state, lanes 0..3 test the four neighbours ("left", "right" per dimension, in order)
+        int head = st->head, tail = to;
+        while (head < to)
+        {
+          const int tx = qx[head & qmask], ty = qy[head & qmask];
+          const unsigned sc = qs[head & qmask];
+          ++head;
+          if (sc > maxScore)
+          {
+            maxScore = sc;
+            bestx = tx;
+            besty = ty;
+          }
+          // `score > maxScore * 0.9` in double (X:1198) == 10*score > 9*maxScore for integer scores below 2^32
+          const bool expand = !heuristic || maxScore == 0 || iter <= J.minIter ||
+                              (10ull * sc > 9ull * maxScore && iter <= J.maxIter);
+          if (expand)
+          {
+            bool isNew = false;
+            int nx = tx, ny = ty;
+            if (lane < 4)
+            {
+              nx = tx + (lane == 0 ? -1 : (lane == 1 ? 1 : 0));
+              ny = ty + (lane == 2 ? -1 : (lane == 3 ? 1 : 0));
+              const int rx = nx - J.sx0, ry = ny - J.sy0;
+              if ((unsigned)rx < (unsigned)J.sw && (unsigned)ry < (unsigned)J.sh)
+              {
+                const uint32_t bit = 1u << (rx & 31);
+                isNew = !(atomicOr(&bitmap[ry * bpitch + (rx >> 5)], bit) & bit);
+              }
+            }
+            const unsigned vote = __ballot_sync(0xFFFFFFFFu, isNew);
+            const int nNew = __popc(vote);
+            if (nNew)
+            {
+              if (tail + nNew - head > J.qcap)
+              {
+                if (lane == 0)
+                  atomicMax(err, ERR_QUEUE);
+              }
+              else
+              {
+                if (isNew)
+                {
+                  const int pos = (tail + __popc(vote & ((1u << lane) - 1u))) & qmask;
+                  qx[pos] = nx;
+                  qy[pos] = ny;
+                  qs[pos] = 0u;
+                }
+                tail += nNew;
+              }
+              iter += nNew;
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0)
+        {
+          st->head = head;
+          st->scored = to;
+          st->tail = tail;
+          st->done = (head == tail);
+        }
+      }
+      __syncthreads();
+      if (st->done)
+        break;
+    }
+}
 
 __global__ void __launch_bounds__(ALIGN_THREADS)
 k_align(const AlignJob * __restrict__ jobs, int njobs, const MaskRef * __restrict__ refs, const uint32_t * __restrict__ arena,
-        uint32_t * gscratch, int heuristic, int2 * result, int * err)
+        uint32_t * gscratch, int heuristic, int2 * result, int4 * dbg, int * err)
 {
   extern __shared__ uint32_t smem[];
-  __shared__ int s_head, s_tail, s_scored, s_done;
-  __shared__ const uint32_t * s_B[ALIGN_MAX_STAGED];
+  __shared__ AlignBfsShared s_bfs;
+  __shared__ AlignShape s_A, s_B[ALIGN_MAX_STAGED];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int jb = blockIdx.x; jb < njobs; jb += gridDim.x)
   {
     const AlignJob J = jobs[jb];
-    const MaskRef A = refs[J.aRef];
+    const long long t_begin = clock64();
+    int nWaves = 0;
     const int bpitch = (J.sw + 31) >> 5;
     const int bwords = bpitch * J.sh;
     // shared memory: [staged shapes][visited bitmap][queue]; the last two move to global scratch for huge searches
@@ -804,164 +963,118 @@ k_align(const AlignJob * __restrict__ jobs, int njobs, const MaskRef * __restric
     unsigned * qs = (unsigned *)(qy + J.qcap);
     const int qmask = J.qcap - 1;
     __syncthreads();
-    // stage the shapes when they fit
-    const int aWords = A.h * A.pitch;
-    int used = 0;
-    const uint32_t * Ad = arena + A.off;
-    if (aWords <= ALIGN_MASK_WORDS)
+    // stage the shapes when they fit (rows re-pitched to an odd stride)
+    if (threadIdx.x == 0)
     {
-      for (int k = threadIdx.x; k < aWords; k += blockDim.x)
-        stage[k] = arena[A.off + k];
-      Ad = stage;
-      used = aWords;
-    }
-    const bool listOk = J.nB <= ALIGN_MAX_STAGED;
-    for (int q = 0; q < J.nB && q < ALIGN_MAX_STAGED; ++q)
-    {
-      const MaskRef B = refs[J.bRef + q];
-      const int bW = B.h * B.pitch;
-      const uint32_t * src = arena + B.off;
-      if (used + bW <= ALIGN_MASK_WORDS)
+      int used = 0;
+      for (int q = -1; q < J.nB && q < ALIGN_MAX_STAGED; ++q)
       {
-        for (int k = threadIdx.x; k < bW; k += blockDim.x)
-          stage[used + k] = src[k];
-        if (threadIdx.x == 0)
-          s_B[q] = stage + used;
-        used += bW;
+        AlignShape s = align_shape(refs[q < 0 ? J.aRef : J.bRef + q], arena);
+        const int sp = s.words | 1;
+        if (used + sp * s.h + s.h <= ALIGN_MASK_WORDS)
+        {
+          s.pitch = -sp; // negative: "to be staged at stage + used"; fixed up below
+          s.data = stage + used;
+          s.rowInfo = stage + used + sp * s.h;
+          used += sp * s.h + s.h;
+        }
+        if (q < 0)
+          s_A = s;
+        else
+          s_B[q] = s;
       }
-      else if (threadIdx.x == 0)
-        s_B[q] = src;
+    }
+    __syncthreads();
+    for (int q = -1; q < J.nB && q < ALIGN_MAX_STAGED; ++q)
+    {
+      AlignShape * sp = q < 0 ? &s_A : &s_B[q];
+      if (sp->pitch < 0)
+      {
+        const int p = -sp->pitch, wv = sp->words, total = wv * sp->h;
+        const uint32_t * src = arena + refs[q < 0 ? J.aRef : J.bRef + q].off;
+        uint32_t * dst = const_cast<uint32_t *>(sp->data);
+        for (int k = threadIdx.x; k < total; k += blockDim.x)
+        {
+          const int r = k / wv, c = k - r * wv;
+          dst[r * p + c] = src[k];
+        }
+      }
     }
     for (int k = threadIdx.x; k < bwords; k += blockDim.x)
       bitmap[k] = 0u;
     __syncthreads();
-    unsigned maxScore = 0;
-    long long iter = 0;
-    int bestx = 0, besty = 0;
-    if (threadIdx.x == 0)
+    // run summary of every staged row (one warp per row)
+    for (int q = -1; q < J.nB && q < ALIGN_MAX_STAGED; ++q)
     {
-      qx[0] = 0;
-      qy[0] = 0;
-      qx[1] = J.indx;
-      qy[1] = J.indy;
-      qs[0] = qs[1] = 0u;
-      bitmap[(0 - J.sy0) * bpitch + ((0 - J.sx0) >> 5)] |= 1u << ((0 - J.sx0) & 31);
-      if ((unsigned)(J.indx - J.sx0) < (unsigned)J.sw && (unsigned)(J.indy - J.sy0) < (unsigned)J.sh)
-        bitmap[(J.indy - J.sy0) * bpitch + ((J.indx - J.sx0) >> 5)] |= 1u << ((J.indx - J.sx0) & 31);
-      s_head = 0;
-      s_tail = 2;
-      s_scored = 0;
-      s_done = 0;
-    }
-    __syncthreads();
-    for (;;)
-    {
-      const int from = s_scored, to = s_tail;
-      if (J.kind == JOB_ONE_TO_ONE && to - from < nwarps)
+      const AlignShape * sp = q < 0 ? &s_A : &s_B[q];
+      if (sp->pitch >= 0)
+        continue;
+      const int p = -sp->pitch, wv = sp->words;
+      uint32_t * info = const_cast<uint32_t *>(sp->rowInfo);
+      for (int r = warp; r < sp->h; r += nwarps)
       {
-        // few translations queued: several warps share one evaluation, partial counts meet in the queue slot
-        // (slots are zeroed when pushed)
-        const int nE = to - from, G = nwarps / nE;
-        const MaskRef B0 = refs[J.bRef];
-        for (int task = warp; task < nE * G; task += nwarps)
+        int first = 0x7FFFFFFF, last = -1, runs = 0;
+        uint32_t prevTop = 0;
+        for (int wb = 0; wb < wv; wb += 32)
         {
-          const int e = from + task / G, part = task % G;
-          unsigned c = align_score_part(A, Ad, B0, s_B[0], qx[e & qmask], qy[e & qmask], part, G, lane);
-          if (lane == 0 && c)
-            atomicAdd(&qs[e & qmask], c);
-        }
-      }
-      else
-      for (int e = from + warp; e < to; e += nwarps)
-      {
-        unsigned sc;
-        if (listOk)
-          sc = align_score(J, A, Ad, refs, s_B, qx[e & qmask], qy[e & qmask], lane);
-        else
-        {
-          // many components on the other side: walk them straight from the arena
-          unsigned total = 0;
-          bool ok = true;
-          for (int k = 0; k < J.nB && ok; ++k)
+          const int wi = wb + lane;
+          const uint32_t xw = wi < wv ? sp->data[r * p + wi] : 0u;
+          uint32_t below = __shfl_up_sync(0xFFFFFFFFu, xw, 1);
+          if (lane == 0)
+            below = prevTop;
+          runs += __popc(xw & ~((xw << 1) | (below >> 31)));
+          if (xw)
           {
-            AlignJob one = J;
-            one.nB = 1;
-            one.bRef = J.bRef + k;
-            const uint32_t * bp = arena + refs[J.bRef + k].off;
-            unsigned c = align_score(one, A, Ad, refs, &bp, qx[e & qmask], qy[e & qmask], lane);
-            if (c == 0)
-              ok = false;
-            total += c;
+            first = min(first, 32 * wi + __ffs(xw) - 1);
+            last = max(last, 32 * wi + 31 - __clz(xw));
           }
-          sc = ok ? total : 0u;
+          prevTop = __shfl_sync(0xFFFFFFFFu, xw, 31);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+          first = min(first, __shfl_xor_sync(0xFFFFFFFFu, first, o));
+          last = max(last, __shfl_xor_sync(0xFFFFFFFFu, last, o));
+          runs += __shfl_xor_sync(0xFFFFFFFFu, runs, o);
         }
         if (lane == 0)
-          qs[e & qmask] = sc;
+          info[r] = last >= 0 ? ((uint32_t)first | ((uint32_t)last << 13) | (runs == 1 ? (1u << 26) : 0u) | (1u << 27)) : 0u;
       }
-      __syncthreads();
-      if (threadIdx.x == 0)
-      {
-        int head = s_head, tail = to;
-        while (head < to)
-        {
-          int tx = qx[head & qmask], ty = qy[head & qmask];
-          unsigned sc = qs[head & qmask];
-          ++head;
-          if (sc > maxScore)
-          {
-            maxScore = sc;
-            bestx = tx;
-            besty = ty;
-          }
-          if (!heuristic || maxScore == 0 || iter <= J.minIter || ((double)sc > (double)maxScore * 0.9 && iter <= J.maxIter))
-          {
-#pragma unroll
-            for (int d = 0; d < 4; ++d)
-            {
-              int nx = tx + (d == 0 ? -1 : (d == 1 ? 1 : 0));
-              int ny = ty + (d == 2 ? -1 : (d == 3 ? 1 : 0));
-              int rx = nx - J.sx0, ry = ny - J.sy0;
-              if ((unsigned)rx < (unsigned)J.sw && (unsigned)ry < (unsigned)J.sh)
-              {
-                uint32_t * w = &bitmap[ry * bpitch + (rx >> 5)];
-                uint32_t bit = 1u << (rx & 31);
-                if (!(*w & bit))
-                {
-                  *w |= bit;
-                  if (tail - head >= J.qcap)
-                  {
-                    atomicMax(err, ERR_QUEUE);
-                  }
-                  else
-                  {
-                    qx[tail & qmask] = nx;
-                    qy[tail & qmask] = ny;
-                    qs[tail & qmask] = 0u;
-                    ++tail;
-                  }
-                  ++iter;
-                }
-              }
-            }
-          }
-        }
-        s_head = head;
-        s_scored = to;
-        s_tail = tail;
-        s_done = (head == tail);
-      }
-      __syncthreads();
-      if (s_done)
-        break;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      if (s_A.pitch < 0)
+        s_A.pitch = -s_A.pitch;
+      for (int q = 0; q < J.nB && q < ALIGN_MAX_STAGED; ++q)
+        if (s_B[q].pitch < 0)
+          s_B[q].pitch = -s_B[q].pitch;
+    }
+    __syncthreads(); // pitches fixed up above
+    int bestx = 0, besty = 0;
+    {
+      const AlignShape A = s_A;
+      if (J.useSmem)
+        align_bfs(J, A, s_B, refs, arena, smem + ALIGN_MASK_WORDS, (int *)(smem + ALIGN_MASK_WORDS + bwords),
+                  (int *)(smem + ALIGN_MASK_WORDS + bwords) + J.qcap, (unsigned *)(smem + ALIGN_MASK_WORDS + bwords) + 2 * J.qcap,
+                  bpitch, heuristic, &s_bfs, bestx, besty, nWaves, err);
+      else
+        align_bfs(J, A, s_B, refs, arena, gscratch + J.bitmapOff, (int *)(gscratch + J.queueOff),
+                  (int *)(gscratch + J.queueOff) + J.qcap, (unsigned *)(gscratch + J.queueOff) + 2 * J.qcap, bpitch, heuristic,
+                  &s_bfs, bestx, besty, nWaves, err);
     }
     if (threadIdx.x == 0)
+    {
       result[jb] = make_int2(bestx, besty);
+      if (dbg)
+        dbg[jb] = make_int4(s_bfs.head, nWaves, (int)(clock64() - t_begin), J.kind * 1000 + J.nB);
+    }
   }
 }
 
 void
 launch_align(Launch & L, const AlignJob * jobs, int njobs, const MaskRef * refs, const uint32_t * arena, uint32_t * gscratch,
-             int heuristic, int2 * result, int smemBytes, int * err)
+             int heuristic, int2 * result, int4 * dbg, int smemBytes, int * err)
 {
   if (njobs == 0)
     return;
@@ -974,7 +1087,7 @@ launch_align(Launch & L, const AlignJob * jobs, int njobs, const MaskRef * refs,
   int grid = std::min(njobs, L.sms * 8);
   L.pre();
   k_align<<<grid, ALIGN_THREADS, smemBytes + ALIGN_MASK_WORDS * 4, L.stream>>>(jobs, njobs, refs, arena, gscratch, heuristic,
-                                                                              result, err);
+                                                                              result, dbg, err);
   L.post("k_align");
 }
 

@@ -114,7 +114,7 @@ void launch_pairs(Launch & L, const SliceDev * slices, const SegDev * segs, cons
                   u64 * table, uint32_t tableMask, mci_pair * pairs, int capPairs, int * nPairs, int * err);
 void launch_extract(Launch & L, const SliceDev * slices, const ExtractJob * jobs, int njobs, const uint16_t * conn, uint32_t * arena);
 void launch_align(Launch & L, const AlignJob * jobs, int njobs, const MaskRef * refs, const uint32_t * arena, uint32_t * gscratch,
-                  int heuristic, int2 * result, int smemBytes, int * err);
+                  int heuristic, int2 * result, int4 * dbg, int smemBytes, int * err);
 void launch_split(Launch & L, const SplitJob * jobs, int njobs, const MaskRef * refs, uint32_t * arena, uint32_t * gscratch,
                   const int2 * trans, int ball, int * err);
 void launch_make_roots(Launch & L, const RootJob * roots, int nroots, MaskRef * refs, uint32_t * arena, const int2 * trans,

@@ -175,6 +175,10 @@ int mci_get_translations(mci_ctx * ctx, int32_t * t /* [2*n_jobs] */);
 /* per job: translations popped, scoring waves, SM clock cycles, kind*1000 + n_b (diagnostics) */
 int mci_get_align_stats(mci_ctx * ctx, int32_t * out /* [4*n_jobs] */);
 
+/* dst[i] = max(dst[i], src[i]) over n pixels of the context's pixel type: the write rule (X:754-763) applied to
+ * partial outputs of sharded runs (device pointers; runs on the context's stream) */
+int mci_combine_max(mci_ctx * ctx, void * dev_dst, const void * dev_src, int64_t n_pixels, int pixel_type);
+
 /* ---- host scheduler (layer 2): the filter itself --------------------------------------------
  * Mirrors the setters of H:85-165 and GenerateData (X:1559-1637). */
 typedef struct
@@ -186,6 +190,9 @@ typedef struct
   int32_t use_ball_structuring_element; /* default 0                  H:233     */
   int32_t use_custom_slice_positions; /* default 0                    H:234     */
   int32_t use_extrapolation;          /* default 1                    H:235     */
+  /* multi-GPU: this run interpolates only segments k with k % shard_count == shard_index, k counting the
+   * segments of InterpolateAlong (X:1456-1521) in (axis, label, slice) order.  Defaults 0 / 1 = everything. */
+  int32_t shard_index, shard_count;
 } mci_filter_options;
 typedef struct
 {

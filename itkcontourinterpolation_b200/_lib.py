@@ -57,7 +57,8 @@ class Params(ctypes.Structure):
 class FilterOptions(ctypes.Structure):
     _fields_ = [("label", ctypes.c_int64), ("axis", ctypes.c_int32), ("heuristic_alignment", ctypes.c_int32),
                 ("use_distance_transform", ctypes.c_int32), ("use_ball_structuring_element", ctypes.c_int32),
-                ("use_custom_slice_positions", ctypes.c_int32), ("use_extrapolation", ctypes.c_int32)]
+                ("use_custom_slice_positions", ctypes.c_int32), ("use_extrapolation", ctypes.c_int32),
+                ("shard_index", ctypes.c_int32), ("shard_count", ctypes.c_int32)]
 
 
 class KernelTime(ctypes.Structure):
@@ -103,6 +104,7 @@ SYMBOLS = [
     ("mci_interpolate", _I, [_P, ctypes.c_int32, _P, _P, ctypes.c_int32, ctypes.POINTER(Params)]),
     ("mci_get_translations", _I, [_P, _P]),
     ("mci_get_align_stats", _I, [_P, _P]),
+    ("mci_combine_max", _I, [_P, _P, _P, ctypes.c_int64, _I]),
     ("mci_filter_default_options", None, [ctypes.POINTER(FilterOptions)]),
     ("mci_filter_run", _I, [_P, ctypes.POINTER(FilterOptions), _P, _P, ctypes.POINTER(ctypes.c_int64), _I, _P,
                             ctypes.c_int64, ctypes.POINTER(FilterStats)]),

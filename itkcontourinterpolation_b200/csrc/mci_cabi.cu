@@ -399,6 +399,17 @@ extern "C"
     return MCI_OK;
   }
 
+  int mci_combine_max(mci_ctx * ctx, void * dst, const void * src, int64_t n, int ptype)
+  {
+    if (!ctx || !dst || !src || n < 0 || ptype < MCI_U8 || ptype > MCI_I16)
+      return MCI_ERR_ARG;
+    if ((reinterpret_cast<size_t>(dst) & 15) || (reinterpret_cast<size_t>(src) & 15))
+      return fail(ctx, MCI_ERR_ARG, "buffers must be 16-byte aligned");
+    CK(cudaSetDevice(ctx->device));
+    launch_combine_max(ctx->L, ptype, dst, src, n);
+    return MCI_OK;
+  }
+
   // ---- slice detection ------------------------------------------------------------------------
   int mci_detect_slices(mci_ctx * ctx, int axis, int32_t * n_labels, int32_t * n_labeled_slices)
   {

@@ -352,6 +352,34 @@ run_core(mci_ctx * ctx, const mci_filter_options * opt, const int64_t dims[3], c
       }
     }
   }
+  if (opt->shard_count > 1)
+  {
+    // multi-GPU: keep every shard_count-th segment; slices no kept segment touches are dropped from the batch
+    if (opt->shard_index < 0 || opt->shard_index >= opt->shard_count)
+      return MCI_ERR_ARG;
+    std::vector<Segment> mine;
+    std::vector<mci_slice_desc> keptDescs;
+    std::map<int, int> remap;
+    for (size_t k = 0; k < segments.size(); ++k)
+    {
+      if ((int)(k % (size_t)opt->shard_count) != opt->shard_index)
+        continue;
+      Segment s = segments[k];
+      for (int * idx : { &s.si, &s.sj })
+      {
+        auto f = remap.find(*idx);
+        if (f == remap.end())
+        {
+          keptDescs.push_back(sliceDescs[(size_t)*idx]);
+          f = remap.insert(std::make_pair(*idx, (int)keptDescs.size() - 1)).first;
+        }
+        *idx = f->second;
+      }
+      mine.push_back(s);
+    }
+    segments.swap(mine);
+    sliceDescs.swap(keptDescs);
+  }
   stats->n_segments = (int64_t)segments.size();
   if (segments.empty())
     return MCI_OK;
@@ -423,6 +451,8 @@ extern "C"
     opt->use_ball_structuring_element = 0;
     opt->use_custom_slice_positions = 0;
     opt->use_extrapolation = 1;
+    opt->shard_index = 0;
+    opt->shard_count = 1;
   }
 
   int mci_filter_run(mci_ctx * ctx, const mci_filter_options * opt, const void * host_in, void * host_out, const int64_t dims[3],

@@ -207,6 +207,58 @@ launch_compact_labels(Launch & L, const int * bbox, int nl, const uint32_t * sli
 }
 
 // ================================================================================================
+// max-combine of partial outputs (sharded runs): the write rule of X:754-763 applied voxel-wise
+// ================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) k_combine_max(T * __restrict__ dst, const T * __restrict__ src, long long n)
+{
+  constexpr int VEC = 16 / sizeof(T);
+  const long long nv = n / VEC;
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < nv; c += (long long)gridDim.x * blockDim.x)
+  {
+    uint4 a = reinterpret_cast<uint4 *>(dst)[c];
+    const uint4 b = __ldg(reinterpret_cast<const uint4 *>(src) + c);
+    T * pa = reinterpret_cast<T *>(&a);
+    const T * pb = reinterpret_cast<const T *>(&b);
+    bool changed = false;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e)
+      if (pb[e] > pa[e])
+      {
+        pa[e] = pb[e];
+        changed = true;
+      }
+    if (changed)
+      reinterpret_cast<uint4 *>(dst)[c] = a;
+  }
+  for (long long i = nv * VEC + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (src[i] > dst[i])
+      dst[i] = src[i];
+}
+
+void
+launch_combine_max(Launch & L, int ptype, void * dst, const void * src, long long n)
+{
+  if (n <= 0)
+    return;
+  const int elt = ptype == MCI_U8 ? 1 : 2;
+  int grid = (int)std::max<long long>(1, std::min<long long>((n / (16 / elt) + 255) / 256, (long long)L.sms * 16));
+  L.pre();
+  switch (ptype)
+  {
+    case MCI_U8:
+      k_combine_max<uint8_t><<<grid, 256, 0, L.stream>>>((uint8_t *)dst, (const uint8_t *)src, n);
+      break;
+    case MCI_U16:
+      k_combine_max<uint16_t><<<grid, 256, 0, L.stream>>>((uint16_t *)dst, (const uint16_t *)src, n);
+      break;
+    default:
+      k_combine_max<int16_t><<<grid, 256, 0, L.stream>>>((int16_t *)dst, (const int16_t *)src, n);
+  }
+  L.post("k_combine_max");
+}
+
+// ================================================================================================
 // K1/K2/K4  batched 2-D connected components on the annotated slices
 //           (RegionedConnectedComponents, X:1224-1238; numbering of ITK ConnectedComponentImageFilter:
 //            ids 1..n by raster position of each component's first pixel; Centroid sums X:1101-1134)

@@ -103,6 +103,7 @@ struct DtLevel
 };
 void launch_dt_level(Launch & L, int ptype, const DtLevel & lv);
 
+void launch_combine_max(Launch & L, int ptype, void * dst, const void * src, long long n);
 void launch_detect(Launch & L, int ptype, const void * in, void * out, const long long dims[3], int axisSel, int * bbox, int nl,
                    uint32_t * sliceBits, int wordsPerLabel, int wo1, int wo2);
 void launch_compact_labels(Launch & L, const int * bbox, int nl, const uint32_t * sliceBits, int wordsPerLabel, int wo1, int wo2,

@@ -350,6 +350,7 @@ struct Params
   int32_t use_extrapolation;
   int32_t use_custom_slice_positions;
   int32_t threads;
+  int32_t shard_index, shard_count; // interpolate only segments k with k % shard_count == shard_index (0/1 = all)
 };
 
 struct Stats
@@ -1152,6 +1153,12 @@ public:
 
   double tCC = 0, tInterp = 0;
   int64_t nSegments = 0;
+  int64_t globalSegment = 0;
+  bool keepSegment()
+  {
+    int64_t k = globalSegment++;
+    return P.shard_count <= 1 || (k % P.shard_count) == P.shard_index;
+  }
 
   // X:1449-1539
   void InterpolateAlong(int axis)
@@ -1188,7 +1195,7 @@ public:
           Box3 rj = ri;
           rj.idx[axis] = *next;
           ConnPtr jconn = RegionedConnectedComponents(rj, axis, it->first, cnt);
-          if (*prev + 1 < *next)
+          if (*prev + 1 < *next && keepSegment())
           {
             Segment s;
             s.axis = axis;

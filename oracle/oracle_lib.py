@@ -25,6 +25,8 @@ class Params(ctypes.Structure):
         ("use_extrapolation", ctypes.c_int32),
         ("use_custom_slice_positions", ctypes.c_int32),
         ("threads", ctypes.c_int32),
+        ("shard_index", ctypes.c_int32),
+        ("shard_count", ctypes.c_int32),
     ]
 
 
@@ -79,14 +81,14 @@ class OracleError(RuntimeError):
 
 
 def interpolate(vol, label=0, axis=-1, heuristic_alignment=True, use_distance_transform=True, use_ball=False,
-                use_extrapolation=True, custom_slices=None, threads=1, return_stats=False):
+                use_extrapolation=True, custom_slices=None, threads=1, return_stats=False, shard_index=0, shard_count=1):
     """Run the restated filter on `vol` (numpy array indexed [z, y, x], x fastest)."""
     vol = np.ascontiguousarray(vol)
     assert vol.ndim == 3 and vol.dtype in PTYPES
     out = np.empty_like(vol)
     dims = (ctypes.c_int64 * 3)(vol.shape[2], vol.shape[1], vol.shape[0])
     p = Params(int(label), int(axis), int(heuristic_alignment), int(use_distance_transform), int(use_ball),
-               int(use_extrapolation), int(custom_slices is not None), int(threads))
+               int(use_extrapolation), int(custom_slices is not None), int(threads), int(shard_index), int(shard_count))
     st = Stats()
     cust = None
     ncust = 0

@@ -35,7 +35,7 @@ def test_struct_layouts_match_header_sizes():
     assert ctypes.sizeof(L.Pair) == 8
     assert ctypes.sizeof(L.Job) == 32
     assert ctypes.sizeof(L.Params) == 20
-    assert ctypes.sizeof(L.FilterOptions) == 32
+    assert ctypes.sizeof(L.FilterOptions) == 40
     assert ctypes.sizeof(L.FilterStats) == 14 * 8
 
 
@@ -44,7 +44,7 @@ def test_default_options_mirror_reference_defaults():
     o = L.FilterOptions()
     L.lib().mci_filter_default_options(ctypes.byref(o))
     assert (o.label, o.axis, o.heuristic_alignment, o.use_distance_transform, o.use_ball_structuring_element,
-            o.use_custom_slice_positions, o.use_extrapolation) == (0, -1, 1, 1, 0, 0, 1)
+            o.use_custom_slice_positions, o.use_extrapolation, o.shard_index, o.shard_count) == (0, -1, 1, 1, 0, 0, 1, 0, 1)
 
 
 def test_no_cpu_fallback_without_device():

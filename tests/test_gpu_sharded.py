@@ -1,0 +1,56 @@
+"""Sharded runs on one GPU: every shard of a 3-way split is computed in turn by the CUDA path, the partial
+outputs are merged with mci_combine_max, and the result must equal the unsharded oracle output bit for bit.
+(The N-process NCCL version of the same flow is tools/run_sharded.py; its exchange logic is covered on
+gloo by tests/test_distributed_cpu.py.)"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from itkcontourinterpolation_b200 import _lib as L
+from oracle import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,kw_gpu,kw_cpu", [
+    ("C4", dict(use_distance_transform=0, use_ball_structuring_element=1), dict(use_distance_transform=False, use_ball=True)),
+    ("C3", dict(axis=2), dict(axis=2)),
+    ("Branching", dict(axis=2), dict(axis=2)),
+])
+def test_three_shards_combine_to_the_full_result(name, kw_gpu, kw_cpu):
+    vol, _ = cases.synthetic_small()[name]
+    lib = L.lib()
+    ctx = ctypes.c_void_p()
+    assert lib.mci_create(ctypes.byref(ctx), 0) == 0
+    try:
+        opt = L.FilterOptions()
+        lib.mci_filter_default_options(ctypes.byref(opt))
+        for k, v in kw_gpu.items():
+            setattr(opt, k, v)
+        dims = (ctypes.c_int64 * 3)(vol.shape[2], vol.shape[1], vol.shape[0])
+        d_in = torch.from_numpy(vol.view(np.int16)).cuda()
+        acc = None
+        nseg = 0
+        for r in range(3):
+            opt.shard_index, opt.shard_count = r, 3
+            part = torch.empty_like(d_in)
+            assert lib.mci_attach_device_volume(ctx, d_in.data_ptr(), part.data_ptr(), dims, L.U16) == 0
+            st = L.FilterStats()
+            rc = lib.mci_filter_run_resident(ctx, ctypes.byref(opt), None, 0, ctypes.byref(st))
+            assert rc == 0, lib.mci_last_error(ctx)
+            nseg += st.n_segments
+            ref_part = O.interpolate(vol, shard_index=r, shard_count=3, **kw_cpu)
+            assert np.array_equal(part.cpu().numpy().view(np.uint16), ref_part), "shard %d" % r
+            if acc is None:
+                acc = part
+            else:
+                assert lib.mci_combine_max(ctx, acc.data_ptr(), part.data_ptr(), acc.numel(), L.U16) == 0
+                assert lib.mci_synchronize(ctx) == 0
+        full, st_full = O.interpolate(vol, return_stats=True, **kw_cpu)
+        assert nseg == st_full["segments"]
+        assert np.array_equal(acc.cpu().numpy().view(np.uint16), full)
+    finally:
+        lib.mci_destroy(ctx)

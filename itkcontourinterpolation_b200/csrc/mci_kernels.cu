@@ -61,57 +61,170 @@ detect_voxel(const T * __restrict__ in, long long i, long long x, long long y, l
   }
 }
 
+// Non-zero chunk whose VEC voxels lie in one row and whose row length is a multiple of VEC: the y / z
+// neighbours come as four aligned vector loads, the x neighbours from registers, and the table updates are
+// issued once per run of equal labels instead of once per voxel.
 template <typename T>
-__global__ void __launch_bounds__(256) k_detect_copy(const T * __restrict__ in, T * __restrict__ out, long long X, long long Y,
+__device__ __noinline__ void
+detect_chunk(const T * __restrict__ in, long long i0, uint4 q, long long X, long long Y, long long Z, int axisSel, int * bbox,
+             int nl, uint32_t * sliceBits, int wordsPerLabel, int wo1, int wo2)
+{
+  constexpr int VEC = 16 / sizeof(T);
+  const long long XY = X * Y;
+  const long long z = i0 / XY;
+  const long long rem = i0 - z * XY;
+  const long long y = rem / X;
+  const long long x0 = rem - y * X;
+  T v[VEC];
+  *reinterpret_cast<uint4 *>(v) = q;
+  if ((X % VEC) != 0 || x0 + VEC > X)
+  {
+    long long x = x0, yy = y, zz = z;
+    for (int e = 0; e < VEC; ++e)
+    {
+      if (v[e] != 0)
+        detect_voxel<T>(in, i0 + e, x, yy, zz, X, Y, Z, v[e], axisSel, bbox, nl, sliceBits, wordsPerLabel, wo1, wo2);
+      if (++x == X)
+      {
+        x = 0;
+        if (++yy == Y)
+        {
+          yy = 0;
+          ++zz;
+        }
+      }
+    }
+    return;
+  }
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  T up[VEC], dn[VEC], fr[VEC], bk[VEC];
+  *reinterpret_cast<uint4 *>(up) = y > 0 ? __ldg(reinterpret_cast<const uint4 *>(in + i0 - X)) : zero;
+  *reinterpret_cast<uint4 *>(dn) = y + 1 < Y ? __ldg(reinterpret_cast<const uint4 *>(in + i0 + X)) : zero;
+  *reinterpret_cast<uint4 *>(fr) = z > 0 ? __ldg(reinterpret_cast<const uint4 *>(in + i0 - XY)) : zero;
+  *reinterpret_cast<uint4 *>(bk) = z + 1 < Z ? __ldg(reinterpret_cast<const uint4 *>(in + i0 + XY)) : zero;
+  const T xm = x0 > 0 ? in[i0 - 1] : T(0);
+  const T xp = x0 + VEC < X ? in[i0 + VEC] : T(0);
+  int e = 0;
+  while (e < VEC)
+  {
+    const T val = v[e];
+    if (val == 0)
+    {
+      ++e;
+      continue;
+    }
+    // run of equal labels [e, f)
+    int f = e + 1;
+    while (f < VEC && v[f] == val)
+      ++f;
+    unsigned mark[3] = { 0u, 0u, 0u }; // per axis: does some voxel of the run mark its slice (X:161-197)
+    for (int g = e; g < f; ++g)
+    {
+      const T nb[6] = { g > 0 ? v[g - 1] : xm, g + 1 < VEC ? v[g + 1] : xp, up[g], dn[g], fr[g], bk[g] };
+      int cTrue = 0, cAdj = 0, axis = 0;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+      {
+        if (nb[2 * a] == 0 && nb[2 * a + 1] == 0)
+        {
+          axis = a;
+          ++cTrue;
+        }
+        else if (nb[2 * a] == val && nb[2 * a + 1] == val)
+          ++cAdj;
+      }
+      if (cTrue == 1 && cAdj == 2 && (axisSel == -1 || axisSel == axis))
+      {
+        if (axis == 0)
+        {
+          // x slices differ per voxel of the run
+          const int c = (int)x0 + g;
+          const unsigned li0 = (unsigned)(typename std::make_unsigned<T>::type)val;
+          uint32_t * w = sliceBits + (size_t)li0 * wordsPerLabel + (c >> 5);
+          const uint32_t bit = 1u << (c & 31);
+          if (!(__ldcg(w) & bit))
+            atomicOr(w, bit);
+        }
+        else
+          mark[axis] = 1u;
+      }
+    }
+    const unsigned li = (unsigned)(typename std::make_unsigned<T>::type)val;
+    // bounding box (X:148-159), once per run
+    const int lo[3] = { (int)x0 + e, (int)y, (int)z }, hi[3] = { (int)x0 + f - 1, (int)y, (int)z };
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+    {
+      int * mn = bbox + (size_t)a * nl + li;
+      int * mx = bbox + (size_t)(3 + a) * nl + li;
+      if (lo[a] < __ldcg(mn))
+        atomicMin(mn, lo[a]);
+      if (hi[a] > __ldcg(mx))
+        atomicMax(mx, hi[a]);
+    }
+#pragma unroll
+    for (int a = 1; a < 3; ++a)
+      if (mark[a])
+      {
+        const int c = a == 1 ? (int)y : (int)z;
+        uint32_t * w = sliceBits + (size_t)li * wordsPerLabel + (a == 1 ? wo1 : wo2) + (c >> 5);
+        const uint32_t bit = 1u << (c & 31);
+        if (!(__ldcg(w) & bit))
+          atomicOr(w, bit);
+      }
+    e = f;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 4) k_detect_copy(const T * __restrict__ in, T * __restrict__ out, long long X, long long Y,
                                                      long long Z, int axisSel, int * bbox, int nl, uint32_t * sliceBits,
                                                      int wordsPerLabel, int wo1, int wo2)
 {
   constexpr int VEC = 16 / sizeof(T);
+  constexpr int UNROLL = 4; // independent 16-byte loads in flight per thread
   const long long n = X * Y * Z;
-  const long long nchunks = (n + VEC - 1) / VEC;
-  const long long XY = X * Y;
-  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < nchunks; c += (long long)gridDim.x * blockDim.x)
+  const long long nfull = n / VEC;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const uint4 * __restrict__ in4 = reinterpret_cast<const uint4 *>(in);
+  uint4 * __restrict__ out4 = reinterpret_cast<uint4 *>(out);
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < nfull; c += UNROLL * stride)
   {
-    const long long i0 = c * VEC;
-    T v[VEC];
-    bool any = false;
-    if (i0 + VEC <= n)
-    {
-      uint4 q = __ldg(reinterpret_cast<const uint4 *>(in + i0));
-      if (out)
-        *reinterpret_cast<uint4 *>(out + i0) = q;
-      any = (q.x | q.y | q.z | q.w) != 0u;
-      *reinterpret_cast<uint4 *>(v) = q;
-    }
-    else
-    {
-      for (int e = 0; e < VEC; ++e)
-      {
-        v[e] = (i0 + e < n) ? in[i0 + e] : T(0);
-        if (out && i0 + e < n)
-          out[i0 + e] = v[e];
-        any |= v[e] != 0;
-      }
-    }
-    if (!any)
-      continue;
-    long long z = i0 / XY;
-    long long rem = i0 - z * XY;
-    long long y = rem / X;
-    long long x = rem - y * X;
+    uint4 q[UNROLL];
 #pragma unroll
-    for (int e = 0; e < VEC; ++e)
+    for (int k = 0; k < UNROLL; ++k)
     {
-      if (v[e] != 0)
-        detect_voxel<T>(in, i0 + e, x, y, z, X, Y, Z, v[e], axisSel, bbox, nl, sliceBits, wordsPerLabel, wo1, wo2);
-      if (++x == X)
+      const long long ci = c + k * stride;
+      q[k] = ci < nfull ? __ldg(in4 + ci) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int k = 0; k < UNROLL; ++k)
+    {
+      const long long ci = c + k * stride;
+      if (ci < nfull && out)
+        out4[ci] = q[k];
+    }
+#pragma unroll
+    for (int k = 0; k < UNROLL; ++k)
+    {
+      const long long ci = c + k * stride;
+      if (ci < nfull && (q[k].x | q[k].y | q[k].z | q[k].w) != 0u)
+        detect_chunk<T>(in, ci * VEC, q[k], X, Y, Z, axisSel, bbox, nl, sliceBits, wordsPerLabel, wo1, wo2);
+    }
+  }
+  // the last n % VEC voxels
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    const long long XY = X * Y;
+    for (long long i = nfull * VEC; i < n; ++i)
+    {
+      const T val = in[i];
+      if (out)
+        out[i] = val;
+      if (val != 0)
       {
-        x = 0;
-        if (++y == Y)
-        {
-          y = 0;
-          ++z;
-        }
+        const long long z = i / XY, rem = i - z * XY, y = rem / X, x = rem - y * X;
+        detect_voxel<T>(in, i, x, y, z, X, Y, Z, val, axisSel, bbox, nl, sliceBits, wordsPerLabel, wo1, wo2);
       }
     }
   }
@@ -172,8 +285,8 @@ launch_detect(Launch & L, int ptype, const void * in, void * out, const long lon
   const int elt = ptype == MCI_U8 ? 1 : 2;
   long long n = dims[0] * dims[1] * dims[2];
   long long nchunks = (n + (16 / elt) - 1) / (16 / elt);
-  long long want = (nchunks + 255) / 256;
-  int grid = (int)std::min<long long>(want, (long long)L.sms * 16);
+  long long want = (nchunks + 4 * 256 - 1) / (4 * 256);
+  int grid = (int)std::min<long long>(want, (long long)L.sms * 8);
   if (grid < 1)
     grid = 1;
   switch (ptype)

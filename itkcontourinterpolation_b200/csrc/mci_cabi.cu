@@ -129,6 +129,9 @@ struct mci_ctx
   bool histClean = false, dtBigClean = false;
   int bigHistGrid = 0;
   int nJobs = 0;
+  // second stream: 1-to-N splits run beside the alignment of the other jobs
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t evAlignedSplits = nullptr, evSplitDone = nullptr;
   // error flag
   int * dErr = nullptr;
 };
@@ -219,6 +222,9 @@ extern "C"
       return MCI_ERR_CUDA;
     }
     cudaMemset(ctx->dErr, 0, sizeof(int));
+    cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->evAlignedSplits, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->evSplitDone, cudaEventDisableTiming);
     *out = ctx;
     return MCI_OK;
   }
@@ -243,6 +249,12 @@ extern "C"
       cudaEventDestroy(e);
     ctx->hStage.release();
     cudaFree(ctx->dErr);
+    if (ctx->stream2)
+      cudaStreamDestroy(ctx->stream2);
+    if (ctx->evAlignedSplits)
+      cudaEventDestroy(ctx->evAlignedSplits);
+    if (ctx->evSplitDone)
+      cudaEventDestroy(ctx->evSplitDone);
     cudaStreamDestroy(ctx->L.stream);
     delete ctx;
   }
@@ -799,6 +811,7 @@ extern "C"
       std::memset(&A, 0, sizeof(A));
       std::memset(&R, 0, sizeof(R));
       A.kind = R.kind = jb.kind;
+      A.out = k;
       R.job = k;
       R.posA = jb.pos_a;
       R.posB = jb.pos_b;
@@ -947,6 +960,10 @@ extern "C"
       }
     }
 
+    // alignment jobs of the 1-to-N kind go first (their splits overlap the rest of the alignment)
+    std::stable_partition(aligns.begin(), aligns.end(), [](const AlignJob & a) { return a.kind == JOB_ONE_TO_N; });
+    const int nSplitJobs = (int)splits.size();
+
     // ---- device memory
     const u64 arenaCap = arenaWords + midWords + 64;
     Blob blob;
@@ -977,11 +994,24 @@ extern "C"
     // ---- launches
     launch_extract(ctx->L, ctx->dSlices, (ExtractJob *)(jb + oExtract), (int)extracts.size(), (uint16_t *)ctx->dConn.p,
                    (uint32_t *)ctx->dArena.p);
-    launch_align(ctx->L, (AlignJob *)(jb + oAlign), njobs, dRefs, (uint32_t *)ctx->dArena.p, (uint32_t *)ctx->dScratch.p,
-                 prm->heuristic_alignment, (int2 *)ctx->dTrans.p,
-                 (int4 *)((uint8_t *)ctx->dTrans.p + ((size_t(njobs) * sizeof(int2) + 15) & ~size_t(15))), alignSmem, ctx->dErr);
-    launch_split(ctx->L, (SplitJob *)(jb + oSplit), (int)splits.size(), dRefs, (uint32_t *)ctx->dArena.p,
-                 (uint32_t *)ctx->dScratch.p, (int2 *)ctx->dTrans.p, prm->use_ball, ctx->dErr);
+    // Align the 1-to-N jobs first; their splits then run on a second stream beside the alignment of the rest
+    int4 * dDbg = (int4 *)((uint8_t *)ctx->dTrans.p + ((size_t(njobs) * sizeof(int2) + 15) & ~size_t(15)));
+    launch_align(ctx->L, (AlignJob *)(jb + oAlign), nSplitJobs, dRefs, (uint32_t *)ctx->dArena.p, (uint32_t *)ctx->dScratch.p,
+                 prm->heuristic_alignment, (int2 *)ctx->dTrans.p, dDbg, alignSmem, ctx->dErr);
+    if (!splits.empty())
+    {
+      CK(cudaEventRecord(ctx->evAlignedSplits, s));
+      CK(cudaStreamWaitEvent(ctx->stream2, ctx->evAlignedSplits, 0));
+      ctx->L.stream = ctx->stream2;
+      launch_split(ctx->L, (SplitJob *)(jb + oSplit), (int)splits.size(), dRefs, (uint32_t *)ctx->dArena.p,
+                   (uint32_t *)ctx->dScratch.p, (int2 *)ctx->dTrans.p, prm->use_ball, ctx->dErr);
+      ctx->L.stream = s;
+      CK(cudaEventRecord(ctx->evSplitDone, ctx->stream2));
+    }
+    launch_align(ctx->L, (AlignJob *)(jb + oAlign) + nSplitJobs, njobs - nSplitJobs, dRefs, (uint32_t *)ctx->dArena.p,
+                 (uint32_t *)ctx->dScratch.p, prm->heuristic_alignment, (int2 *)ctx->dTrans.p, dDbg, alignSmem, ctx->dErr);
+    if (!splits.empty())
+      CK(cudaStreamWaitEvent(s, ctx->evSplitDone, 0));
     Node * dNodes = (Node *)ctx->dNodes.p;
     launch_make_roots(ctx->L, (RootJob *)(jb + oRoots), njobs, dRefs, (uint32_t *)ctx->dArena.p, (int2 *)ctx->dTrans.p, dNodes);
     long long off = 0;

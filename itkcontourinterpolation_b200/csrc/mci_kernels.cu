@@ -71,10 +71,23 @@ detect_chunk(const T * __restrict__ in, long long i0, uint4 q, long long X, long
 {
   constexpr int VEC = 16 / sizeof(T);
   const long long XY = X * Y;
-  const long long z = i0 / XY;
-  const long long rem = i0 - z * XY;
-  const long long y = rem / X;
-  const long long x0 = rem - y * X;
+  long long z, y, x0;
+  if (i0 + VEC <= 0xFFFFFFFFll)
+  {
+    // 32-bit division is several times cheaper than 64-bit and covers volumes up to 4 Gi voxels
+    const unsigned iu = (unsigned)i0, xyu = (unsigned)XY, xu = (unsigned)X;
+    const unsigned zu = iu / xyu, ru = iu - zu * xyu, yu = ru / xu;
+    z = zu;
+    y = yu;
+    x0 = ru - yu * xu;
+  }
+  else
+  {
+    z = i0 / XY;
+    const long long rem = i0 - z * XY;
+    y = rem / X;
+    x0 = rem - y * X;
+  }
   T v[VEC];
   *reinterpret_cast<uint4 *>(v) = q;
   if ((X % VEC) != 0 || x0 + VEC > X)
@@ -1230,9 +1243,9 @@ k_align(const AlignJob * __restrict__ jobs, int njobs, const MaskRef * __restric
     }
     if (threadIdx.x == 0)
     {
-      result[jb] = make_int2(bestx, besty);
+      result[J.out] = make_int2(bestx, besty);
       if (dbg)
-        dbg[jb] = make_int4(s_bfs.head, nWaves, (int)(clock64() - t_begin), J.kind * 1000 + J.nB);
+        dbg[J.out] = make_int4(s_bfs.head, nWaves, (int)(clock64() - t_begin), J.kind * 1000 + J.nB);
     }
   }
 }

@@ -76,6 +76,8 @@ struct AlignJob
   int phx, phy; // phantom pixel (EXTRAPOLATE)
   int qcap; // ring capacity (power of two)
   int useSmem;
+  int out;  // index of the job this translation belongs to (jobs are launched in two groups)
+  int pad0;
   long long minIter, maxIter;
   u64 bitmapOff; // global scratch (words) when !useSmem
   u64 queueOff;  // global scratch (words) when !useSmem: qcap*3 words

@@ -1496,7 +1496,7 @@ edt_sq(const uint32_t * Xb, int pitch, int xr0, int xr1, int x, int r, int cap)
   return best;
 }
 
-#define MCI_NODE_THREADS 256
+#define MCI_NODE_THREADS 512
 #define MCI_SMALL_HIST 2048
 
 struct NodeShared
@@ -1770,20 +1770,26 @@ dilation_sequence(NodeShared & sh, const uint32_t * Xb, const uint32_t * maskb, 
   int steps = 0; // number of growth steps so far
   uint32_t * a = D;
   uint32_t * b = Dn;
+  unsigned settled = 0; // bit j: my j-th word is full (equals the mask) in both buffers: nothing left to do there
   while (stopAt < 0 || steps < stopAt)
   {
     if (tid == 0)
       sh.cnt = 0;
     __syncthreads();
     int changed = 0, cnt = 0;
-    for (int idx = tid; idx < words; idx += MCI_NODE_THREADS)
+    int j = 0;
+    for (int idx = tid; idx < words; idx += MCI_NODE_THREADS, ++j)
     {
+      if (j < 32 && ((settled >> j) & 1u))
+        continue;
       const int r = idx / pitch, wi = idx % pitch;
       uint32_t old = a[idx];
       uint32_t m = maskb[idx];
       uint32_t v = old;
       if (m & ~old)
         v = old | (dilate_word(a, h, pitch, r, wi, ball) & m);
+      else if (j < 32)
+        settled |= 1u << j; // after this copy both buffers hold the final word
       b[idx] = v;
       uint32_t diff = v & ~old;
       if (diff)
@@ -1929,7 +1935,7 @@ median_dilations(NodeShared & sh, const uint32_t * Xb, const uint32_t * Ib, cons
 }
 
 template <typename T>
-__global__ void __launch_bounds__(MCI_NODE_THREADS)
+__global__ void __launch_bounds__(MCI_NODE_THREADS, 2)
 k_nodes(const Node * __restrict__ nodes, const int * __restrict__ count, Node * next, int * nextCount, int nextCap,
         uint32_t * arena, unsigned long long * arenaTop, unsigned long long arenaCap, const T * __restrict__ in, T * out,
         long long VX, long long VY, long long VZ, int useDT, int ball, unsigned * bigHistAll, uint32_t * slabAll,

@@ -195,3 +195,21 @@ def test_ball_dilation_medium(flt):
     vol, _, cfg = make_config("C4", 0.25)
     out = run_gpu(flt, vol, use_distance_transform=False, use_ball=True)
     assert_same(out, O.interpolate(vol, use_distance_transform=False, use_ball=True, threads=os.cpu_count() or 1), "C4/4 ball")
+
+
+def test_full_size_c4_ball_dilations_three_axes(flt):
+    # BASELINE.json configs[3]: 1024x1024x512, sparse along all three axes, UseDistanceTransform=off, ball
+    vol, dense, cfg = make_config("C4")
+    del dense
+    out = run_gpu(flt, vol, use_distance_transform=False, use_ball=True)
+    assert np.array_equal(out[vol != 0], vol[vol != 0])
+    assert_same(out, O.interpolate(vol, use_distance_transform=False, use_ball=True, threads=os.cpu_count() or 1), "C4 full size")
+
+
+@pytest.mark.skipif(os.environ.get("MCI_TEST_C5", "0") != "1", reason="set MCI_TEST_C5=1 (needs ~40 GB host RAM, ~1 min)")
+def test_full_size_c5_on_one_gpu(flt):
+    # BASELINE.json configs[4]: 2048x2048x1024 uint16, 200 labels (here on ONE GPU; sharding is tested separately)
+    vol, dense, cfg = make_config("C5")
+    del dense
+    out = run_gpu(flt, vol, axis=2)
+    assert_same(out, O.interpolate(vol, axis=2, threads=os.cpu_count() or 1), "C5 full size")

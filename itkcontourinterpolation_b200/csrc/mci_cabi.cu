@@ -106,7 +106,7 @@ struct mci_ctx
   void * dOut = nullptr;
   DBuf ownIn, ownOut;
   // detection
-  DBuf dBBox, dSliceBits, dLabels, dLabeledSlices, dCounters;
+  DBuf dBBox, dSliceBits, dLabels, dLabeledSlices, dCounters, dChunkBits;
   HBuf hStage;
   int nLabels = 0, nLabeledSlices = 0;
   bool detected = false;
@@ -241,7 +241,8 @@ extern "C"
                       &ctx->dNcomp,    &ctx->dCompBase, &ctx->dTotal,   &ctx->dStats,     &ctx->dSegBlob, &ctx->dPairTable,
                       &ctx->dPairs,    &ctx->dJobBlob,  &ctx->dArena,   &ctx->dScratch,   &ctx->dBigHist, &ctx->dSlab,
                       &ctx->dNodes,    &ctx->dLevelCounts, &ctx->dArenaTop, &ctx->dTrans,
-                      &ctx->dWork, &ctx->dItems, &ctx->dLevelScratch, &ctx->dHist, &ctx->dDtBig, &ctx->dDtCounters };
+                      &ctx->dWork, &ctx->dItems, &ctx->dLevelScratch, &ctx->dHist, &ctx->dDtBig, &ctx->dDtCounters,
+                      &ctx->dChunkBits };
     for (DBuf * b : bufs)
       b->release();
     recycle_events(ctx);
@@ -439,13 +440,14 @@ extern "C"
     CK(ctx->dLabels.ensure(size_t(nl) * sizeof(mci_label_info)));
     CK(ctx->dLabeledSlices.ensure(size_t(capSlices) * sizeof(mci_labeled_slice)));
     CK(ctx->dCounters.ensure(2 * sizeof(int)));
+    CK(ctx->dChunkBits.ensure((ctx->nvox / (ctx->ptype == MCI_U8 ? 16 : 8) / 32 + 2) * 4));
     cudaStream_t s = ctx->L.stream;
     CK(cudaMemsetAsync(ctx->dBBox.p, 0x7F, size_t(3) * nl * sizeof(int), s));
     CK(cudaMemsetAsync((int *)ctx->dBBox.p + size_t(3) * nl, 0xFF, size_t(3) * nl * sizeof(int), s));
     CK(cudaMemsetAsync(ctx->dSliceBits.p, 0, size_t(nl) * wpl * sizeof(uint32_t), s));
     CK(cudaMemsetAsync(ctx->dCounters.p, 0, 2 * sizeof(int), s));
     launch_detect(ctx->L, ctx->ptype, ctx->dIn, ctx->dOut, ctx->dims, axis, (int *)ctx->dBBox.p, nl, (uint32_t *)ctx->dSliceBits.p,
-                  wpl, wo1, wo2);
+                  wpl, wo1, wo2, (uint32_t *)ctx->dChunkBits.p);
     launch_compact_labels(ctx->L, (int *)ctx->dBBox.p, nl, (uint32_t *)ctx->dSliceBits.p, wpl, wo1, wo2, ctx->ptype == MCI_I16,
                           (mci_label_info *)ctx->dLabels.p, (mci_labeled_slice *)ctx->dLabeledSlices.p, capSlices,
                           (int *)ctx->dCounters.p);

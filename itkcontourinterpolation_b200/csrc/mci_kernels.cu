@@ -64,10 +64,49 @@ detect_voxel(const T * __restrict__ in, long long i, long long x, long long y, l
 // Non-zero chunk whose VEC voxels lie in one row and whose row length is a multiple of VEC: the y / z
 // neighbours come as four aligned vector loads, the x neighbours from registers, and the table updates are
 // issued once per run of equal labels instead of once per voxel.
+struct ChunkSummary
+{
+  unsigned label; // label index + 1 of the chunk's first run, 0 = none
+  int x0, x1, y, z;
+  unsigned marks; // bit 0: the run marks its y slice, bit 1: its z slice
+};
+
+// per-label bounding box (X:148-159) and slice bitmap updates: test first (the tables rarely change), then atomics
+__device__ __forceinline__ void
+detect_update_tables(int * bbox, int nl, uint32_t * sliceBits, int wordsPerLabel, int wo1, int wo2, unsigned li, int x0, int x1, int y0,
+                     int y1, int z0, int z1, unsigned markY, unsigned markZ, int ySlice, int zSlice)
+{
+  const int lo[3] = { x0, y0, z0 }, hi[3] = { x1, y1, z1 };
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+  {
+    int * mn = bbox + (size_t)a * nl + li;
+    int * mx = bbox + (size_t)(3 + a) * nl + li;
+    if (lo[a] < __ldcg(mn))
+      atomicMin(mn, lo[a]);
+    if (hi[a] > __ldcg(mx))
+      atomicMax(mx, hi[a]);
+  }
+  if (markY)
+  {
+    uint32_t * w = sliceBits + (size_t)li * wordsPerLabel + wo1 + (ySlice >> 5);
+    const uint32_t bit = 1u << (ySlice & 31);
+    if (!(__ldcg(w) & bit))
+      atomicOr(w, bit);
+  }
+  if (markZ)
+  {
+    uint32_t * w = sliceBits + (size_t)li * wordsPerLabel + wo2 + (zSlice >> 5);
+    const uint32_t bit = 1u << (zSlice & 31);
+    if (!(__ldcg(w) & bit))
+      atomicOr(w, bit);
+  }
+}
+
 template <typename T>
 __device__ __noinline__ void
 detect_chunk(const T * __restrict__ in, long long i0, uint4 q, long long X, long long Y, long long Z, int axisSel, int * bbox,
-             int nl, uint32_t * sliceBits, int wordsPerLabel, int wo1, int wo2)
+             int nl, uint32_t * sliceBits, int wordsPerLabel, int wo1, int wo2, ChunkSummary * sum)
 {
   constexpr int VEC = 16 / sizeof(T);
   const long long XY = X * Y;
@@ -110,13 +149,82 @@ detect_chunk(const T * __restrict__ in, long long i0, uint4 q, long long X, long
     return;
   }
   const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-  T up[VEC], dn[VEC], fr[VEC], bk[VEC];
-  *reinterpret_cast<uint4 *>(up) = y > 0 ? __ldg(reinterpret_cast<const uint4 *>(in + i0 - X)) : zero;
-  *reinterpret_cast<uint4 *>(dn) = y + 1 < Y ? __ldg(reinterpret_cast<const uint4 *>(in + i0 + X)) : zero;
-  *reinterpret_cast<uint4 *>(fr) = z > 0 ? __ldg(reinterpret_cast<const uint4 *>(in + i0 - XY)) : zero;
-  *reinterpret_cast<uint4 *>(bk) = z + 1 < Z ? __ldg(reinterpret_cast<const uint4 *>(in + i0 + XY)) : zero;
+  const uint4 qu = y > 0 ? __ldg(reinterpret_cast<const uint4 *>(in + i0 - X)) : zero;
+  const uint4 qd = y + 1 < Y ? __ldg(reinterpret_cast<const uint4 *>(in + i0 + X)) : zero;
+  const uint4 qf = z > 0 ? __ldg(reinterpret_cast<const uint4 *>(in + i0 - XY)) : zero;
+  const uint4 qb = z + 1 < Z ? __ldg(reinterpret_cast<const uint4 *>(in + i0 + XY)) : zero;
   const T xm = x0 > 0 ? in[i0 - 1] : T(0);
   const T xp = x0 + VEC < X ? in[i0 + VEC] : T(0);
+  if (sum)
+  {
+    // Common case -- every labelled voxel of the chunk carries the same label: the whole 6-neighbour test
+    // (X:161-197) runs as SIMD-in-register compares on the packed pixels, no per-voxel loop.
+    constexpr int BITS = 8 * sizeof(T), EPW = 4 / sizeof(T);
+    const unsigned c[4] = { q.x, q.y, q.z, q.w };
+    const unsigned u[4] = { qu.x, qu.y, qu.z, qu.w }, d[4] = { qd.x, qd.y, qd.z, qd.w };
+    const unsigned f4[4] = { qf.x, qf.y, qf.z, qf.w }, b4[4] = { qb.x, qb.y, qb.z, qb.w };
+    auto eq = [](unsigned a, unsigned b) { return sizeof(T) == 2 ? __vcmpeq2(a, b) : __vcmpeq4(a, b); };
+    int w0 = 0;
+    while (w0 < 3 && !c[w0])
+      ++w0;
+    const int e0 = (__ffs(c[w0]) - 1) / BITS;
+    const unsigned lab = (c[w0] >> (e0 * BITS)) & ((1u << BITS) - 1u);
+    const unsigned L = sizeof(T) == 2 ? (lab | (lab << 16)) : lab * 0x01010101u;
+    unsigned nz[4], my = 0, mz = 0, other = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w)
+    {
+      nz[w] = ~eq(c[w], 0u);
+      other |= nz[w] & ~eq(c[w], L);
+    }
+    if (!other)
+    {
+      const unsigned xmW = (unsigned)(typename std::make_unsigned<T>::type)xm, xpW = (unsigned)(typename std::make_unsigned<T>::type)xp;
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+      {
+        const unsigned prevHi = w > 0 ? (c[w - 1] >> (32 - BITS)) : xmW;
+        const unsigned nextLo = w < 3 ? (c[w + 1] << (32 - BITS)) : (xpW << (32 - BITS));
+        const unsigned P = (c[w] << BITS) | prevHi, N = (c[w] >> BITS) | nextLo;
+        const unsigned ex = eq(P, 0u) & eq(N, 0u), sx = eq(P, c[w]) & eq(N, c[w]);
+        const unsigned ey = eq(u[w], 0u) & eq(d[w], 0u), sy = eq(u[w], c[w]) & eq(d[w], c[w]);
+        const unsigned ez = eq(f4[w], 0u) & eq(b4[w], 0u), sz = eq(f4[w], c[w]) & eq(b4[w], c[w]);
+        my |= ey & sx & sz & nz[w];
+        mz |= ez & sx & sy & nz[w];
+        if ((axisSel == -1 || axisSel == 0) && (ex & sy & sz & nz[w]))
+        {
+          unsigned m = ex & sy & sz & nz[w];
+          for (int e = 0; e < EPW; ++e)
+            if ((m >> (e * BITS)) & 1u)
+            {
+              const int cx = (int)x0 + w * EPW + e;
+              uint32_t * ww = sliceBits + (size_t)lab * wordsPerLabel + (cx >> 5);
+              const uint32_t bit = 1u << (cx & 31);
+              if (!(__ldcg(ww) & bit))
+                atomicOr(ww, bit);
+            }
+        }
+      }
+      int w1 = 3;
+      while (w1 > 0 && !nz[w1])
+        --w1;
+      int wf = 0;
+      while (wf < 3 && !nz[wf])
+        ++wf;
+      sum->label = lab + 1;
+      sum->x0 = (int)x0 + wf * EPW + (__ffs(nz[wf]) - 1) / BITS;
+      sum->x1 = (int)x0 + w1 * EPW + (31 - __clz(nz[w1])) / BITS;
+      sum->y = (int)y;
+      sum->z = (int)z;
+      sum->marks = ((my != 0u && (axisSel == -1 || axisSel == 1)) ? 1u : 0u) | ((mz != 0u && (axisSel == -1 || axisSel == 2)) ? 2u : 0u);
+      return;
+    }
+  }
+  T up[VEC], dn[VEC], fr[VEC], bk[VEC];
+  *reinterpret_cast<uint4 *>(up) = qu;
+  *reinterpret_cast<uint4 *>(dn) = qd;
+  *reinterpret_cast<uint4 *>(fr) = qf;
+  *reinterpret_cast<uint4 *>(bk) = qb;
   int e = 0;
   while (e < VEC)
   {
@@ -163,66 +271,105 @@ detect_chunk(const T * __restrict__ in, long long i0, uint4 q, long long X, long
       }
     }
     const unsigned li = (unsigned)(typename std::make_unsigned<T>::type)val;
-    // bounding box (X:148-159), once per run
-    const int lo[3] = { (int)x0 + e, (int)y, (int)z }, hi[3] = { (int)x0 + f - 1, (int)y, (int)z };
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
+    if (sum && !sum->label)
     {
-      int * mn = bbox + (size_t)a * nl + li;
-      int * mx = bbox + (size_t)(3 + a) * nl + li;
-      if (lo[a] < __ldcg(mn))
-        atomicMin(mn, lo[a]);
-      if (hi[a] > __ldcg(mx))
-        atomicMax(mx, hi[a]);
+      // first run of the chunk: handed back so that the warp can merge it with its neighbours' runs
+      sum->label = li + 1;
+      sum->x0 = (int)x0 + e;
+      sum->x1 = (int)x0 + f - 1;
+      sum->y = (int)y;
+      sum->z = (int)z;
+      sum->marks = mark[1] | (mark[2] << 1);
     }
-#pragma unroll
-    for (int a = 1; a < 3; ++a)
-      if (mark[a])
-      {
-        const int c = a == 1 ? (int)y : (int)z;
-        uint32_t * w = sliceBits + (size_t)li * wordsPerLabel + (a == 1 ? wo1 : wo2) + (c >> 5);
-        const uint32_t bit = 1u << (c & 31);
-        if (!(__ldcg(w) & bit))
-          atomicOr(w, bit);
-      }
+    else
+      detect_update_tables(bbox, nl, sliceBits, wordsPerLabel, wo1, wo2, li, (int)x0 + e, (int)x0 + f - 1, (int)y, (int)y, (int)z,
+                           (int)z, mark[1], mark[2], (int)y, (int)z);
     e = f;
   }
 }
 
+// Streaming pass: out := in with 16-byte vectors, four independent loads in flight per thread, and one
+// ballot word per warp-load saying which of its 32 chunks hold labels.  Nothing else: this kernel is the
+// HBM-bound part of the path (2*s*N algorithmic bytes) and must not carry the per-voxel logic's registers.
 template <typename T>
-__global__ void __launch_bounds__(256, 4) k_detect_copy(const T * __restrict__ in, T * __restrict__ out, long long X, long long Y,
-                                                     long long Z, int axisSel, int * bbox, int nl, uint32_t * sliceBits,
-                                                     int wordsPerLabel, int wo1, int wo2)
+__global__ void __launch_bounds__(256) k_copy_flag(const T * __restrict__ in, T * __restrict__ out, long long n,
+                                                   uint32_t * __restrict__ chunkBits)
 {
   constexpr int VEC = 16 / sizeof(T);
-  constexpr int UNROLL = 4; // independent 16-byte loads in flight per thread
-  const long long n = X * Y * Z;
+  constexpr int UNROLL = 4;
   const long long nfull = n / VEC;
-  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long stride = (long long)gridDim.x * blockDim.x; // multiple of 32: a warp-load covers one bitmap word
   const uint4 * __restrict__ in4 = reinterpret_cast<const uint4 *>(in);
   uint4 * __restrict__ out4 = reinterpret_cast<uint4 *>(out);
-  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < nfull; c += UNROLL * stride)
+  const int lane = threadIdx.x & 31;
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c - lane < nfull; c += UNROLL * stride)
   {
     uint4 q[UNROLL];
 #pragma unroll
     for (int k = 0; k < UNROLL; ++k)
     {
       const long long ci = c + k * stride;
-      q[k] = ci < nfull ? __ldg(in4 + ci) : make_uint4(0u, 0u, 0u, 0u);
+      q[k] = ci < nfull ? __ldcs(in4 + ci) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
     for (int k = 0; k < UNROLL; ++k)
     {
       const long long ci = c + k * stride;
       if (ci < nfull && out)
-        out4[ci] = q[k];
+        __stcs(out4 + ci, q[k]);
+      const unsigned vote = __ballot_sync(0xFFFFFFFFu, (q[k].x | q[k].y | q[k].z | q[k].w) != 0u);
+      if (lane == 0 && ci < nfull)
+        chunkBits[ci >> 5] = vote;
     }
-#pragma unroll
-    for (int k = 0; k < UNROLL; ++k)
+  }
+}
+
+// Per-voxel logic of DetermineSliceOrientations on the chunks flagged by k_copy_flag: one warp per bitmap word,
+// one lane per 16-byte chunk, so a warp works on up to 256 consecutive voxels of a row.
+template <typename T>
+__global__ void __launch_bounds__(256) k_detect_marked(const T * __restrict__ in, T * __restrict__ out, long long X, long long Y,
+                                                       long long Z, int axisSel, int * bbox, int nl, uint32_t * sliceBits,
+                                                       int wordsPerLabel, int wo1, int wo2, const uint32_t * __restrict__ chunkBits)
+{
+  constexpr int VEC = 16 / sizeof(T);
+  const long long n = X * Y * Z;
+  const long long nfull = n / VEC;
+  const long long nWords = (nfull + 31) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  // a warp visits words gw, gw + nw, gw + 2 nw, ...: lane i fetches the i-th of them, so the (mostly empty)
+  // bitmap costs one load per 32 words instead of one dependent load per word
+  for (long long wb = gw; wb < nWords; wb += 32 * nw)
+  {
+    const long long mine = wb + (long long)lane * nw;
+    const uint32_t myBits = mine < nWords ? __ldg(chunkBits + mine) : 0u;
+    unsigned nonEmpty = __ballot_sync(0xFFFFFFFFu, myBits != 0u);
+    while (nonEmpty)
     {
-      const long long ci = c + k * stride;
-      if (ci < nfull && (q[k].x | q[k].y | q[k].z | q[k].w) != 0u)
-        detect_chunk<T>(in, ci * VEC, q[k], X, Y, Z, axisSel, bbox, nl, sliceBits, wordsPerLabel, wo1, wo2);
+    const int src = __ffs(nonEmpty) - 1;
+    nonEmpty &= nonEmpty - 1;
+    const long long w = wb + (long long)src * nw;
+    const uint32_t bits = __shfl_sync(0xFFFFFFFFu, myBits, src);
+    ChunkSummary sum;
+    sum.label = 0;
+    sum.x0 = sum.x1 = sum.y = sum.z = 0;
+    sum.marks = 0;
+    if ((bits >> lane) & 1u)
+    {
+      const long long ci = w * 32 + lane;
+      const uint4 q = __ldg(reinterpret_cast<const uint4 *>(in) + ci);
+      detect_chunk<T>(in, ci * VEC, q, X, Y, Z, axisSel, bbox, nl, sliceBits, wordsPerLabel, wo1, wo2, &sum);
+    }
+    // lanes whose first run has the same label in the same row are merged: one table update per group
+    const unsigned long long key =
+      sum.label ? ((unsigned long long)sum.label | ((unsigned long long)(unsigned)sum.y << 17) | ((unsigned long long)(unsigned)sum.z << 30))
+                : ~0ull; // label + 1 <= 2^16 (17 bits), y and z < 2^13
+    const unsigned grp = __match_any_sync(0xFFFFFFFFu, key);
+    const int gx0 = __reduce_min_sync(grp, sum.x0), gx1 = __reduce_max_sync(grp, sum.x1);
+    const unsigned gm = __reduce_or_sync(grp, sum.marks);
+    if (sum.label && lane == __ffs(grp) - 1)
+      detect_update_tables(bbox, nl, sliceBits, wordsPerLabel, wo1, wo2, sum.label - 1, gx0, gx1, sum.y, sum.y, sum.z, sum.z, gm & 1u,
+                           (gm >> 1) & 1u, sum.y, sum.z);
     }
   }
   // the last n % VEC voxels
@@ -293,33 +440,43 @@ k_compact_labels(const int * __restrict__ bbox, int nl, const uint32_t * __restr
 
 void
 launch_detect(Launch & L, int ptype, const void * in, void * out, const long long dims[3], int axisSel, int * bbox, int nl,
-              uint32_t * sliceBits, int wordsPerLabel, int wo1, int wo2)
+              uint32_t * sliceBits, int wordsPerLabel, int wo1, int wo2, uint32_t * chunkBits)
 {
   const int elt = ptype == MCI_U8 ? 1 : 2;
-  long long n = dims[0] * dims[1] * dims[2];
-  long long nchunks = (n + (16 / elt) - 1) / (16 / elt);
-  long long want = (nchunks + 4 * 256 - 1) / (4 * 256);
-  int grid = (int)std::min<long long>(want, (long long)L.sms * 8);
-  if (grid < 1)
-    grid = 1;
+  const long long n = dims[0] * dims[1] * dims[2];
+  const long long nchunks = n / (16 / elt);
+  const long long nWords = (nchunks + 31) / 32;
+  int gridA = (int)std::max<long long>(1, std::min<long long>((nchunks + 4 * 256 - 1) / (4 * 256), (long long)L.sms * 8));
+  int gridB = (int)std::max<long long>(1, std::min<long long>((nWords + 7) / 8, (long long)L.sms * 8));
+  L.pre();
   switch (ptype)
   {
     case MCI_U8:
-      L.pre();
-      k_detect_copy<uint8_t><<<grid, 256, 0, L.stream>>>((const uint8_t *)in, (uint8_t *)out, dims[0], dims[1], dims[2], axisSel,
-                                                         bbox, nl, sliceBits, wordsPerLabel, wo1, wo2);
+      k_copy_flag<uint8_t><<<gridA, 256, 0, L.stream>>>((const uint8_t *)in, (uint8_t *)out, n, chunkBits);
       break;
     case MCI_U16:
-      L.pre();
-      k_detect_copy<uint16_t><<<grid, 256, 0, L.stream>>>((const uint16_t *)in, (uint16_t *)out, dims[0], dims[1], dims[2],
-                                                          axisSel, bbox, nl, sliceBits, wordsPerLabel, wo1, wo2);
+      k_copy_flag<uint16_t><<<gridA, 256, 0, L.stream>>>((const uint16_t *)in, (uint16_t *)out, n, chunkBits);
       break;
     default:
-      L.pre();
-      k_detect_copy<int16_t><<<grid, 256, 0, L.stream>>>((const int16_t *)in, (int16_t *)out, dims[0], dims[1], dims[2], axisSel,
-                                                         bbox, nl, sliceBits, wordsPerLabel, wo1, wo2);
+      k_copy_flag<int16_t><<<gridA, 256, 0, L.stream>>>((const int16_t *)in, (int16_t *)out, n, chunkBits);
   }
-  L.post("k_detect_copy");
+  L.post("k_copy_flag");
+  L.pre();
+  switch (ptype)
+  {
+    case MCI_U8:
+      k_detect_marked<uint8_t><<<gridB, 256, 0, L.stream>>>((const uint8_t *)in, (uint8_t *)out, dims[0], dims[1], dims[2], axisSel,
+                                                            bbox, nl, sliceBits, wordsPerLabel, wo1, wo2, chunkBits);
+      break;
+    case MCI_U16:
+      k_detect_marked<uint16_t><<<gridB, 256, 0, L.stream>>>((const uint16_t *)in, (uint16_t *)out, dims[0], dims[1], dims[2],
+                                                             axisSel, bbox, nl, sliceBits, wordsPerLabel, wo1, wo2, chunkBits);
+      break;
+    default:
+      k_detect_marked<int16_t><<<gridB, 256, 0, L.stream>>>((const int16_t *)in, (int16_t *)out, dims[0], dims[1], dims[2], axisSel,
+                                                            bbox, nl, sliceBits, wordsPerLabel, wo1, wo2, chunkBits);
+  }
+  L.post("k_detect_marked");
 }
 
 void

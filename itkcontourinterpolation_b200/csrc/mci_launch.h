@@ -105,7 +105,7 @@ void launch_dt_level(Launch & L, int ptype, const DtLevel & lv);
 
 void launch_combine_max(Launch & L, int ptype, void * dst, const void * src, long long n);
 void launch_detect(Launch & L, int ptype, const void * in, void * out, const long long dims[3], int axisSel, int * bbox, int nl,
-                   uint32_t * sliceBits, int wordsPerLabel, int wo1, int wo2);
+                   uint32_t * sliceBits, int wordsPerLabel, int wo1, int wo2, uint32_t * chunkBits);
 void launch_compact_labels(Launch & L, const int * bbox, int nl, const uint32_t * sliceBits, int wordsPerLabel, int wo1, int wo2,
                            int signedLabels, mci_label_info * labels, mci_labeled_slice * slices, int capSlices, int * counters);
 void launch_cc(Launch & L, int ptype, const void * in, const SliceDev * slices, int nslices, const RowTile * tiles, int ntiles,

@@ -117,7 +117,7 @@ struct mci_ctx
   int totalComp = 0;
   bool statsOnHost = false;
   std::vector<CompStat> hStats;
-  DBuf dSliceBlob, dParent, dRootId, dConn, dRowCount, dNcomp, dCompBase, dTotal, dStats;
+  DBuf dSliceBlob, dBits, dWordRun, dRunComp, dRunScratch, dConn, dNcomp, dCompBase, dTotal, dStats;
   SliceDev * dSlices = nullptr;
   int statCap = 0;
   // pairs
@@ -237,7 +237,7 @@ extern "C"
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->L.stream);
     DBuf * bufs[] = { &ctx->ownIn,     &ctx->ownOut,   &ctx->dBBox,     &ctx->dSliceBits, &ctx->dLabels,  &ctx->dLabeledSlices,
-                      &ctx->dCounters, &ctx->dSliceBlob, &ctx->dParent, &ctx->dRootId,    &ctx->dConn,    &ctx->dRowCount,
+                      &ctx->dCounters, &ctx->dSliceBlob, &ctx->dBits, &ctx->dWordRun,    &ctx->dConn,    &ctx->dRunComp, &ctx->dRunScratch,
                       &ctx->dNcomp,    &ctx->dCompBase, &ctx->dTotal,   &ctx->dStats,     &ctx->dSegBlob, &ctx->dPairTable,
                       &ctx->dPairs,    &ctx->dJobBlob,  &ctx->dArena,   &ctx->dScratch,   &ctx->dBigHist, &ctx->dSlab,
                       &ctx->dNodes,    &ctx->dLevelCounts, &ctx->dArenaTop, &ctx->dTrans,
@@ -515,8 +515,9 @@ extern "C"
     if (n == 0)
       return MCI_OK;
     const long long X = ctx->dims[0], Y = ctx->dims[1];
-    u64 pix = 0;
+    u64 pix = 0, bitWords = 0, runTotal = 0;
     long long rows = 0;
+    int maxRows = 0;
     std::vector<int> ws(n), hs(n);
     u64 compBound = 0;
     for (int k = 0; k < n; ++k)
@@ -537,8 +538,13 @@ extern "C"
       S.v0 = d.v0;
       S.w = d.w;
       S.h = d.h;
-      S.rowOff = (int)rows;
       S.pixOff = pix;
+      S.bitOff = bitWords;
+      S.runOff = runTotal;
+      S.runCap = (int)std::min<u64>((u64)(d.w / 2 + 1) * (u64)d.h, 4u << 20);
+      bitWords += (u64)((d.w + 31) / 32) * d.h;
+      runTotal += (u64)S.runCap;
+      maxRows = std::max(maxRows, d.h);
       if (d.axis == 2)
       {
         S.su = 1;
@@ -575,28 +581,28 @@ extern "C"
     ctx->dSlices = (SliceDev *)((uint8_t *)ctx->dSliceBlob.p + oS);
     RowTile * dTiles = (RowTile *)((uint8_t *)ctx->dSliceBlob.p + oT);
     ctx->statCap = (int)std::min<u64>(compBound, 2u << 20);
-    CK(ctx->dParent.ensure(pix * 4));
-    CK(ctx->dRootId.ensure(pix * 4));
+    CK(ctx->dBits.ensure((bitWords + 64) * 4));
+    CK(ctx->dWordRun.ensure((bitWords + 64) * 4));
+    CK(ctx->dRunComp.ensure((runTotal + 64) * 4));
+    CK(ctx->dRunScratch.ensure((runTotal * 3 + 64) * 4));
     CK(ctx->dConn.ensure(pix * 2));
-    CK(ctx->dRowCount.ensure(size_t(rows) * 4));
     CK(ctx->dNcomp.ensure(size_t(n) * 4));
     CK(ctx->dCompBase.ensure(size_t(n) * 4));
     CK(ctx->dTotal.ensure(4));
     CK(ctx->dStats.ensure(size_t(ctx->statCap) * sizeof(CompStat)));
-    CK(cudaMemsetAsync(ctx->dRowCount.p, 0, size_t(rows) * 4, s));
-    launch_cc(ctx->L, ctx->ptype, ctx->dIn, ctx->dSlices, n, dTiles, (int)tiles.size(), (uint32_t *)ctx->dParent.p,
-              (uint32_t *)ctx->dRootId.p, (uint16_t *)ctx->dConn.p, (int *)ctx->dRowCount.p, (int *)ctx->dNcomp.p,
-              (int *)ctx->dCompBase.p, (int *)ctx->dTotal.p, (CompStat *)ctx->dStats.p, ctx->statCap, fully, ctx->dErr);
+    CK(cudaMemsetAsync(ctx->dTotal.p, 0, 4, s));
+    launch_cc(ctx->L, ctx->ptype, ctx->dIn, ctx->dSlices, n, dTiles, (int)tiles.size(), (uint32_t *)ctx->dBits.p,
+              (uint32_t *)ctx->dWordRun.p, (uint32_t *)ctx->dRunComp.p, (uint32_t *)ctx->dRunScratch.p, (uint16_t *)ctx->dConn.p,
+              (int *)ctx->dNcomp.p, (int *)ctx->dCompBase.p, (int *)ctx->dTotal.p, (CompStat *)ctx->dStats.p, ctx->statCap, fully,
+              maxRows, ctx->dErr);
+    CK(cudaMemcpyAsync(ctx->compBase.data(), ctx->dCompBase.p, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(ctx->ncomp.data(), ctx->dNcomp.p, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
     int rc = check_device_error(ctx);
     if (rc)
       return rc;
     int acc = 0;
     for (int k = 0; k < n; ++k)
-    {
-      ctx->compBase[k] = acc;
-      acc += ctx->ncomp[k];
-    }
+      acc += ctx->ncomp[k]; // compBase[] was filled by the device (slots are handed out in completion order)
     ctx->totalComp = acc;
     if (n_components)
       std::memcpy(n_components, ctx->ncomp.data(), size_t(n) * 4);
@@ -626,17 +632,19 @@ extern "C"
     int rc = fetch_stats(ctx);
     if (rc)
       return rc;
-    for (int k = 0; k < ctx->totalComp; ++k)
-    {
-      const CompStat & s = ctx->hStats[k];
-      out[k].count = s.count;
-      out[k].sum_u = s.sumU;
-      out[k].sum_v = s.sumV;
-      out[k].min_u = s.minU;
-      out[k].min_v = s.minV;
-      out[k].max_u = s.maxU;
-      out[k].max_v = s.maxV;
-    }
+    int k = 0;
+    for (size_t sl = 0; sl < ctx->ncomp.size(); ++sl)
+      for (int q = 0; q < ctx->ncomp[sl]; ++q, ++k)
+      {
+        const CompStat & s = ctx->hStats[ctx->compBase[sl] + q];
+        out[k].count = s.count;
+        out[k].sum_u = s.sumU;
+        out[k].sum_v = s.sumV;
+        out[k].min_u = s.minU;
+        out[k].min_v = s.minV;
+        out[k].max_u = s.maxU;
+        out[k].max_v = s.maxV;
+      }
     return MCI_OK;
   }
 

@@ -542,381 +542,6 @@ launch_combine_max(Launch & L, int ptype, void * dst, const void * src, long lon
 }
 
 // ================================================================================================
-// K1/K2/K4  batched 2-D connected components on the annotated slices
-//           (RegionedConnectedComponents, X:1224-1238; numbering of ITK ConnectedComponentImageFilter:
-//            ids 1..n by raster position of each component's first pixel; Centroid sums X:1101-1134)
-// Union-find on pixels with the smaller index as parent, so every root is its component's
-// raster-first pixel; consecutive ids = rank of the root in raster order.
-// ================================================================================================
-// representative of p with intermediate pointer jumping (path halving): every value written is an
-// ancestor of the cell it is written to, and parents only ever decrease, so racing writers are harmless
-__device__ __forceinline__ uint32_t
-uf_find(volatile uint32_t * parent, uint32_t p)
-{
-  uint32_t curr = parent[p];
-  if (curr != p)
-  {
-    uint32_t prev = p, next;
-    while (curr > (next = parent[curr]))
-    {
-      parent[prev] = next;
-      prev = curr;
-      curr = next;
-    }
-  }
-  return curr;
-}
-// read-only walk to the root (used once all unions are done: the flatten pass must leave every pixel
-// pointing at its ROOT, which racing path-halving writes could undo)
-__device__ __forceinline__ uint32_t
-uf_root(const volatile uint32_t * parent, uint32_t p)
-{
-  uint32_t q;
-  while ((q = parent[p]) != p)
-    p = q;
-  return p;
-}
-__device__ __forceinline__ void
-uf_union(uint32_t * parent, uint32_t a, uint32_t b)
-{
-  for (;;)
-  {
-    a = uf_find(parent, a);
-    b = uf_find(parent, b);
-    if (a == b)
-      return;
-    if (a < b)
-    {
-      uint32_t t = a;
-      a = b;
-      b = t;
-    }
-    uint32_t old = atomicMin(&parent[a], b);
-    if (old == a)
-      return;
-    a = old;
-  }
-}
-
-// Warps walk (row, 32-pixel chunk) cells of a tile.
-#define MCI_TILE_LOOP(tile, S, cw)                                                                                            \
-  const RowTile tile = tiles[blockIdx.x];                                                                                     \
-  const SliceDev S = slices[tile.item];                                                                                       \
-  const int cw = (S.w + 31) >> 5;                                                                                             \
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;                                       \
-  for (int cell = warp; cell < tile.nrows * cw; cell += nwarps)
-
-template <typename T>
-__global__ void __launch_bounds__(256)
-k_cc_init(const T * __restrict__ in, const SliceDev * __restrict__ slices, const RowTile * __restrict__ tiles, uint32_t * parentAll)
-{
-  MCI_TILE_LOOP(tile, S, cw)
-  {
-    const int y = tile.row0 + cell / cw;
-    const int x = (cell % cw) * 32 + lane;
-    bool fg = false;
-    if (x < S.w)
-      fg = in[S.base + (u64)((long long)x * S.su + (long long)y * S.sv)] == (T)S.label;
-    uint32_t bits = __ballot_sync(0xFFFFFFFFu, fg);
-    if (x < S.w)
-    {
-      uint32_t p = (uint32_t)y * (uint32_t)S.w + (uint32_t)x;
-      uint32_t v = MCI_NOLABEL;
-      if (fg)
-      {
-        uint32_t zeros = ~bits & ((1u << lane) - 1u);
-        int start = zeros ? 32 - __clz(zeros) : 0; // first pixel of this pixel's run inside the chunk
-        v = p - (uint32_t)(lane - start);
-      }
-      parentAll[S.pixOff + p] = v;
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256)
-k_cc_merge(const SliceDev * __restrict__ slices, const RowTile * __restrict__ tiles, uint32_t * parentAll, int fully)
-{
-  MCI_TILE_LOOP(tile, S, cw)
-  {
-    const int y = tile.row0 + cell / cw;
-    const int x = (cell % cw) * 32 + lane;
-    if (x >= S.w)
-      continue;
-    uint32_t * parent = parentAll + S.pixOff;
-    const uint32_t p = (uint32_t)y * (uint32_t)S.w + (uint32_t)x;
-    if (parent[p] == MCI_NOLABEL)
-      continue;
-    const bool left = x > 0 && parent[p - 1] != MCI_NOLABEL;
-    if (left && lane == 0)
-      uf_union(parent, p, p - 1);
-    if (y > 0)
-    {
-      const uint32_t u = p - (uint32_t)S.w;
-      const bool up = parent[u] != MCI_NOLABEL;
-      const bool upleft = x > 0 && parent[u - 1] != MCI_NOLABEL;
-      if (up)
-      {
-        if (!(left && upleft)) // otherwise the left neighbour already links the two rows
-          uf_union(parent, p, u);
-      }
-      else if (fully)
-      {
-        if (upleft)
-          uf_union(parent, p, u - 1);
-        if (x + 1 < S.w && parent[u + 1] != MCI_NOLABEL)
-          uf_union(parent, p, u + 1);
-      }
-    }
-  }
-}
-
-// path compression + number of roots per row
-__global__ void __launch_bounds__(256)
-k_cc_flatten(const SliceDev * __restrict__ slices, const RowTile * __restrict__ tiles, uint32_t * parentAll, int * rowCount)
-{
-  MCI_TILE_LOOP(tile, S, cw)
-  {
-    const int y = tile.row0 + cell / cw;
-    const int x = (cell % cw) * 32 + lane;
-    bool root = false;
-    if (x < S.w)
-    {
-      uint32_t * parent = parentAll + S.pixOff;
-      const uint32_t p = (uint32_t)y * (uint32_t)S.w + (uint32_t)x;
-      if (parent[p] != MCI_NOLABEL)
-      {
-        uint32_t r = uf_root(parent, p);
-        root = r == p;
-        if (!root)
-          parent[p] = r;
-      }
-    }
-    uint32_t bits = __ballot_sync(0xFFFFFFFFu, root);
-    if (lane == 0 && bits)
-      atomicAdd(&rowCount[S.rowOff + y], __popc(bits));
-  }
-}
-
-// one CTA per slice: exclusive scan of the per-row root counts; total = component count
-__global__ void __launch_bounds__(256) k_cc_rowscan(const SliceDev * __restrict__ slices, int * rowCount, int * ncomp)
-{
-  const SliceDev S = slices[blockIdx.x];
-  __shared__ int wsum[8];
-  __shared__ int carry;
-  if (threadIdx.x == 0)
-    carry = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int base = 0; base < S.h; base += 256)
-  {
-    int y = base + threadIdx.x;
-    int v = y < S.h ? rowCount[S.rowOff + y] : 0;
-    int s = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
-    {
-      int t = __shfl_up_sync(0xFFFFFFFFu, s, o);
-      if (lane >= o)
-        s += t;
-    }
-    if (lane == 31)
-      wsum[warp] = s;
-    __syncthreads();
-    int off = carry;
-    for (int k = 0; k < warp; ++k)
-      off += wsum[k];
-    if (y < S.h)
-      rowCount[S.rowOff + y] = off + s - v;
-    __syncthreads();
-    if (threadIdx.x == 255)
-      carry = off + s;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0)
-    ncomp[blockIdx.x] = carry;
-}
-
-// single CTA: exclusive scan over slices -> first CompStat slot of each slice; checks capacities
-__global__ void __launch_bounds__(256)
-k_cc_base(const int * __restrict__ ncomp, int nslices, int * compBase, int * total, int cap, int maxPerSlice, int * err)
-{
-  __shared__ int wsum[8];
-  __shared__ int carry;
-  if (threadIdx.x == 0)
-    carry = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int base = 0; base < nslices; base += 256)
-  {
-    int k = base + threadIdx.x;
-    int v = k < nslices ? ncomp[k] : 0;
-    if (v > maxPerSlice)
-      atomicMax(err, ERR_PIXELTYPE);
-    int s = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
-    {
-      int t = __shfl_up_sync(0xFFFFFFFFu, s, o);
-      if (lane >= o)
-        s += t;
-    }
-    if (lane == 31)
-      wsum[warp] = s;
-    __syncthreads();
-    int off = carry;
-    for (int q = 0; q < warp; ++q)
-      off += wsum[q];
-    if (k < nslices)
-      compBase[k] = off + s - v;
-    __syncthreads();
-    if (threadIdx.x == 255)
-      carry = off + s;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0)
-  {
-    *total = carry;
-    if (carry > cap)
-      atomicMax(err, ERR_COMPONENTS);
-  }
-}
-
-__global__ void
-k_stats_init(CompStat * stats, const int * total, int cap)
-{
-  int n = min(*total, cap);
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
-  {
-    CompStat s;
-    s.count = 0;
-    s.sumU = 0;
-    s.sumV = 0;
-    s.minU = 0x7FFFFFFF;
-    s.minV = 0x7FFFFFFF;
-    s.maxU = -0x7FFFFFFF;
-    s.maxV = -0x7FFFFFFF;
-    stats[k] = s;
-  }
-}
-
-// warp per row: roots receive consecutive ids in raster order
-__global__ void __launch_bounds__(256)
-k_cc_assign(const SliceDev * __restrict__ slices, const RowTile * __restrict__ tiles, const uint32_t * __restrict__ parentAll,
-            const int * __restrict__ rowCount, uint32_t * rootIdAll)
-{
-  const RowTile tile = tiles[blockIdx.x];
-  const SliceDev S = slices[tile.item];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const uint32_t * parent = parentAll + S.pixOff;
-  uint32_t * rootId = rootIdAll + S.pixOff;
-  for (int r = warp; r < tile.nrows; r += nwarps)
-  {
-    const int y = tile.row0 + r;
-    int cnt = rowCount[S.rowOff + y]; // exclusive prefix = roots before this row
-    for (int x0 = 0; x0 < S.w; x0 += 32)
-    {
-      const int x = x0 + lane;
-      bool root = false;
-      uint32_t p = (uint32_t)y * (uint32_t)S.w + (uint32_t)x;
-      if (x < S.w)
-        root = parent[p] == p;
-      uint32_t bits = __ballot_sync(0xFFFFFFFFu, root);
-      if (root)
-        rootId[p] = (uint32_t)(cnt + __popc(bits & ((1u << lane) - 1u)) + 1);
-      cnt += __popc(bits);
-    }
-  }
-}
-
-// component image + per-component statistics (one set of atomics per horizontal run chunk)
-__global__ void __launch_bounds__(256)
-k_cc_write(const SliceDev * __restrict__ slices, const RowTile * __restrict__ tiles, const uint32_t * __restrict__ parentAll,
-           const uint32_t * __restrict__ rootIdAll, const int * __restrict__ compBase, int statCap, uint16_t * connAll,
-           CompStat * stats)
-{
-  MCI_TILE_LOOP(tile, S, cw)
-  {
-    const int y = tile.row0 + cell / cw;
-    const int x = (cell % cw) * 32 + lane;
-    uint32_t id = 0;
-    if (x < S.w)
-    {
-      const uint32_t p = (uint32_t)y * (uint32_t)S.w + (uint32_t)x;
-      uint32_t r = parentAll[S.pixOff + p];
-      if (r != MCI_NOLABEL)
-        id = rootIdAll[S.pixOff + r];
-      connAll[S.pixOff + p] = (uint16_t)id;
-    }
-    uint32_t bits = __ballot_sync(0xFFFFFFFFu, id != 0);
-    if (id != 0 && !(lane > 0 && ((bits >> (lane - 1)) & 1u)))
-    {
-      uint32_t rest = ~(bits >> lane);
-      int len = rest ? __ffs(rest) - 1 : 32 - lane;
-      int slot = compBase[tile.item] + (int)id - 1;
-      if (slot < statCap)
-      {
-        CompStat * st = stats + slot;
-        long long u = S.u0 + x, v = S.v0 + y;
-        atomicAdd((unsigned long long *)&st->count, (unsigned long long)len);
-        atomicAdd((unsigned long long *)&st->sumU, (unsigned long long)(u * len + (long long)len * (len - 1) / 2));
-        atomicAdd((unsigned long long *)&st->sumV, (unsigned long long)(v * len));
-        atomicMin(&st->minU, (int)u);
-        atomicMax(&st->maxU, (int)u + len - 1);
-        atomicMin(&st->minV, (int)v);
-        atomicMax(&st->maxV, (int)v);
-      }
-    }
-  }
-}
-
-void
-launch_cc(Launch & L, int ptype, const void * in, const SliceDev * slices, int nslices, const RowTile * tiles, int ntiles,
-          uint32_t * parent, uint32_t * rootId, uint16_t * conn, int * rowCount, int * ncomp, int * compBase, int * total,
-          CompStat * stats, int statCap, int fully, int * err)
-{
-  if (nslices == 0 || ntiles == 0)
-    return;
-  switch (ptype)
-  {
-    case MCI_U8:
-      L.pre();
-      k_cc_init<uint8_t><<<ntiles, 256, 0, L.stream>>>((const uint8_t *)in, slices, tiles, parent);
-      break;
-    case MCI_U16:
-      L.pre();
-      k_cc_init<uint16_t><<<ntiles, 256, 0, L.stream>>>((const uint16_t *)in, slices, tiles, parent);
-      break;
-    default:
-      L.pre();
-      k_cc_init<int16_t><<<ntiles, 256, 0, L.stream>>>((const int16_t *)in, slices, tiles, parent);
-  }
-  L.post("k_cc_init");
-  L.pre();
-  k_cc_merge<<<ntiles, 256, 0, L.stream>>>(slices, tiles, parent, fully);
-  L.post("k_cc_merge");
-  L.pre();
-  k_cc_flatten<<<ntiles, 256, 0, L.stream>>>(slices, tiles, parent, rowCount);
-  L.post("k_cc_flatten");
-  L.pre();
-  k_cc_rowscan<<<nslices, 256, 0, L.stream>>>(slices, rowCount, ncomp);
-  L.post("k_cc_rowscan");
-  int maxPer = ptype == MCI_U8 ? 255 : (ptype == MCI_U16 ? 65535 : 32767);
-  L.pre();
-  k_cc_base<<<1, 256, 0, L.stream>>>(ncomp, nslices, compBase, total, statCap, maxPer, err);
-  L.post("k_cc_base");
-  L.pre();
-  k_stats_init<<<std::max(1, std::min(L.sms * 4, (statCap + 255) / 256)), 256, 0, L.stream>>>(stats, total, statCap);
-  L.post("k_stats_init");
-  L.pre();
-  k_cc_assign<<<ntiles, 256, 0, L.stream>>>(slices, tiles, parent, rowCount, rootId);
-  L.post("k_cc_assign");
-  L.pre();
-  k_cc_write<<<ntiles, 256, 0, L.stream>>>(slices, tiles, parent, rootId, compBase, statCap, conn, stats);
-  L.post("k_cc_write");
-
-}
-
-// ================================================================================================
 // K3  component matching: distinct (iId, jId) pairs of every segment  (X:1250-1272)
 // ================================================================================================
 __global__ void __launch_bounds__(256)

@@ -109,8 +109,8 @@ void launch_detect(Launch & L, int ptype, const void * in, void * out, const lon
 void launch_compact_labels(Launch & L, const int * bbox, int nl, const uint32_t * sliceBits, int wordsPerLabel, int wo1, int wo2,
                            int signedLabels, mci_label_info * labels, mci_labeled_slice * slices, int capSlices, int * counters);
 void launch_cc(Launch & L, int ptype, const void * in, const SliceDev * slices, int nslices, const RowTile * tiles, int ntiles,
-               uint32_t * parent, uint32_t * rootId, uint16_t * conn, int * rowCount, int * ncomp, int * compBase, int * total,
-               CompStat * stats, int statCap, int fully, int * err);
+               uint32_t * bits, uint32_t * wordRun, uint32_t * runComp, uint32_t * runScratch, uint16_t * conn, int * ncomp,
+               int * compBase, int * total, CompStat * stats, int statCap, int fully, int maxRows, int * err);
 void launch_pairs(Launch & L, const SliceDev * slices, const SegDev * segs, const RowTile * tiles, int ntiles, const uint16_t * conn,
                   u64 * table, uint32_t tableMask, mci_pair * pairs, int capPairs, int * nPairs, int * err);
 void launch_extract(Launch & L, const SliceDev * slices, const ExtractJob * jobs, int njobs, const uint16_t * conn, uint32_t * arena);

@@ -26,8 +26,10 @@ struct SliceDev
 {
   int axis, slice, label;
   int u0, v0, w, h;
-  int rowOff;    // offset into per-row arrays
-  u64 pixOff;    // offset into per-pixel arrays (parent, root id, component image)
+  int runCap;    // capacity of this slice's run table
+  u64 pixOff;    // offset into the component-image array
+  u64 bitOff;    // offset (words) into the bit-row / per-word run-number arrays
+  u64 runOff;    // offset into the run -> component table
   u64 base;      // voxel index of slice pixel (u0, v0)
   long long su, sv; // voxel strides of u and v
 };

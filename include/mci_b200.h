@@ -137,6 +137,9 @@ typedef struct
 } mci_pair;
 int mci_match_pairs(mci_ctx * ctx, int32_t n_segments, const mci_segment_desc * segments, int32_t * n_pairs);
 int mci_get_pairs(mci_ctx * ctx, mci_pair * pairs);
+/* mci_label_slices + mci_match_pairs launched back to back with a single host round trip (what the scheduler uses) */
+int mci_label_and_match(mci_ctx * ctx, int32_t n, const mci_slice_desc * slices, int fully_connected, int32_t n_segments,
+                        const mci_segment_desc * segments, int32_t * n_components /* [n] */, int32_t * n_pairs);
 
 /* ---- interpolation jobs ---------------------------------------------------------------------
  * One job = one Align (X:1136-1222) followed by

@@ -101,6 +101,7 @@ SYMBOLS = [
     ("mci_get_component_image", _I, [_P, ctypes.c_int32, _P]),
     ("mci_match_pairs", _I, [_P, ctypes.c_int32, _P, ctypes.POINTER(ctypes.c_int32)]),
     ("mci_get_pairs", _I, [_P, _P]),
+    ("mci_label_and_match", _I, [_P, ctypes.c_int32, _P, _I, ctypes.c_int32, _P, _P, ctypes.POINTER(ctypes.c_int32)]),
     ("mci_interpolate", _I, [_P, ctypes.c_int32, _P, _P, ctypes.c_int32, ctypes.POINTER(Params)]),
     ("mci_get_translations", _I, [_P, _P]),
     ("mci_get_align_stats", _I, [_P, _P]),

@@ -107,7 +107,8 @@ struct mci_ctx
   DBuf ownIn, ownOut;
   // detection
   DBuf dBBox, dSliceBits, dLabels, dLabeledSlices, dCounters, dChunkBits;
-  HBuf hStage;
+  HBuf hStage, hStage2, hRes; // hRes: pinned landing zone of the small device->host result tables
+  int resLabels = 0, resSlices = 0, resPairs = 0, resStats = 0; // how many entries of each table hRes holds
   int nLabels = 0, nLabeledSlices = 0;
   bool detected = false;
   // slices / components
@@ -120,6 +121,7 @@ struct mci_ctx
   DBuf dSliceBlob, dBits, dWordRun, dRunComp, dRunScratch, dConn, dNcomp, dCompBase, dTotal, dStats;
   SliceDev * dSlices = nullptr;
   int statCap = 0;
+  bool deferSync = false; // set by mci_label_and_match: the two phases launch back to back, one round trip at the end
   // pairs
   DBuf dSegBlob, dPairTable, dPairs;
   int nPairs = 0, capPairs = 0;
@@ -135,6 +137,15 @@ struct mci_ctx
   // error flag
   int * dErr = nullptr;
 };
+
+// layout of the pinned result cache (mci_ctx::hRes)
+static const int kSpecLabels = 1024, kSpecSlices = 16384, kSpecPairs = 16384, kSpecStats = 8192, kSpecNcomp = 65536;
+static const size_t kResLabelsOff = 64;
+static const size_t kResSlicesOff = kResLabelsOff + size_t(kSpecLabels) * sizeof(mci_label_info);
+static const size_t kResNcompOff = kResSlicesOff + size_t(kSpecSlices) * sizeof(mci_labeled_slice);
+static const size_t kResPairsOff = kResNcompOff + size_t(2 * kSpecNcomp) * sizeof(int);
+static const size_t kResStatsOff = kResPairsOff + size_t(kSpecPairs) * sizeof(mci_pair);
+static const size_t kResBytes = kResStatsOff + size_t(kSpecStats) * sizeof(mci::CompStat);
 
 #define CK(call)                                                                                                               \
   do                                                                                                                           \
@@ -249,6 +260,8 @@ extern "C"
     for (cudaEvent_t e : ctx->L.pool)
       cudaEventDestroy(e);
     ctx->hStage.release();
+    ctx->hRes.release();
+    ctx->hStage2.release();
     cudaFree(ctx->dErr);
     if (ctx->stream2)
       cudaStreamDestroy(ctx->stream2);
@@ -451,14 +464,24 @@ extern "C"
     launch_compact_labels(ctx->L, (int *)ctx->dBBox.p, nl, (uint32_t *)ctx->dSliceBits.p, wpl, wo1, wo2, ctx->ptype == MCI_I16,
                           (mci_label_info *)ctx->dLabels.p, (mci_labeled_slice *)ctx->dLabeledSlices.p, capSlices,
                           (int *)ctx->dCounters.p);
-    int h[2] = { 0, 0 };
-    CK(cudaMemcpyAsync(h, ctx->dCounters.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    // one round trip: the counters plus the first kSpecLabels / kSpecSlices table entries land in pinned memory
+    // together (label volumes rarely hold more); mci_get_detection fetches the rest if there is more
+    CK(ctx->hRes.ensure(kResBytes));
+    uint8_t * hr = (uint8_t *)ctx->hRes.p;
+    int * h = (int *)hr;
+    CK(cudaMemcpyAsync(h, ctx->dCounters.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(hr + kResLabelsOff, ctx->dLabels.p, size_t(std::min(nl, kSpecLabels)) * sizeof(mci_label_info),
+                       cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(hr + kResSlicesOff, ctx->dLabeledSlices.p, size_t(kSpecSlices) * sizeof(mci_labeled_slice),
+                       cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     if (h[1] > capSlices)
       return fail(ctx, MCI_ERR_CAPACITY, "too many labelled slices");
     ctx->nLabels = h[0];
     ctx->nLabeledSlices = h[1];
+    ctx->resLabels = std::min(h[0], std::min(nl, kSpecLabels));
+    ctx->resSlices = std::min(h[1], kSpecSlices);
     ctx->detected = true;
     if (n_labels)
       *n_labels = h[0];
@@ -472,13 +495,32 @@ extern "C"
     if (!ctx || !ctx->detected)
       return MCI_ERR_STATE;
     CK(cudaSetDevice(ctx->device));
+    const uint8_t * hr = (const uint8_t *)ctx->hRes.p;
+    bool pending = false;
     if (labels && ctx->nLabels)
-      CK(cudaMemcpyAsync(labels, ctx->dLabels.p, size_t(ctx->nLabels) * sizeof(mci_label_info), cudaMemcpyDeviceToHost,
-                         ctx->L.stream));
+    {
+      if (ctx->resLabels >= ctx->nLabels)
+        std::memcpy(labels, hr + kResLabelsOff, size_t(ctx->nLabels) * sizeof(mci_label_info));
+      else
+      {
+        CK(cudaMemcpyAsync(labels, ctx->dLabels.p, size_t(ctx->nLabels) * sizeof(mci_label_info), cudaMemcpyDeviceToHost,
+                           ctx->L.stream));
+        pending = true;
+      }
+    }
     if (slices && ctx->nLabeledSlices)
-      CK(cudaMemcpyAsync(slices, ctx->dLabeledSlices.p, size_t(ctx->nLabeledSlices) * sizeof(mci_labeled_slice),
-                         cudaMemcpyDeviceToHost, ctx->L.stream));
-    CK(cudaStreamSynchronize(ctx->L.stream));
+    {
+      if (ctx->resSlices >= ctx->nLabeledSlices)
+        std::memcpy(slices, hr + kResSlicesOff, size_t(ctx->nLabeledSlices) * sizeof(mci_labeled_slice));
+      else
+      {
+        CK(cudaMemcpyAsync(slices, ctx->dLabeledSlices.p, size_t(ctx->nLabeledSlices) * sizeof(mci_labeled_slice),
+                           cudaMemcpyDeviceToHost, ctx->L.stream));
+        pending = true;
+      }
+    }
+    if (pending)
+      CK(cudaStreamSynchronize(ctx->L.stream));
     return MCI_OK;
   }
 
@@ -595,6 +637,8 @@ extern "C"
               (uint32_t *)ctx->dWordRun.p, (uint32_t *)ctx->dRunComp.p, (uint32_t *)ctx->dRunScratch.p, (uint16_t *)ctx->dConn.p,
               (int *)ctx->dNcomp.p, (int *)ctx->dCompBase.p, (int *)ctx->dTotal.p, (CompStat *)ctx->dStats.p, ctx->statCap, fully,
               maxRows, ctx->dErr);
+    if (ctx->deferSync)
+      return MCI_OK;
     CK(cudaMemcpyAsync(ctx->compBase.data(), ctx->dCompBase.p, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(ctx->ncomp.data(), ctx->dNcomp.p, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
     int rc = check_device_error(ctx);
@@ -685,17 +729,19 @@ extern "C"
       sd[k].sj = b;
       ws[k] = A.w;
       hs[k] = A.h;
-      bound += std::min<u64>((u64)(ctx->ncomp[a] + 1) * (u64)(ctx->ncomp[b] + 1), (u64)A.w * A.h);
+      // distinct pairs of a segment: at most (ni+1)(nj+1); before the counts are known, a bound from the area
+      bound += ctx->deferSync ? std::min<u64>((u64)A.w * A.h / 16 + 64, 1u << 20)
+                              : std::min<u64>((u64)(ctx->ncomp[a] + 1) * (u64)(ctx->ncomp[b] + 1), (u64)A.w * A.h);
     }
     std::vector<RowTile> tiles;
     make_tiles(ws, hs, tiles);
     Blob blob;
     size_t oS = blob.add(sd), oT = blob.add(tiles);
     CK(ctx->dSegBlob.ensure(blob.bytes.size()));
-    CK(ctx->hStage.ensure(blob.bytes.size()));
-    std::memcpy(ctx->hStage.p, blob.bytes.data(), blob.bytes.size());
+    CK(ctx->hStage2.ensure(blob.bytes.size()));
+    std::memcpy(ctx->hStage2.p, blob.bytes.data(), blob.bytes.size());
     cudaStream_t s = ctx->L.stream;
-    CK(cudaMemcpyAsync(ctx->dSegBlob.p, ctx->hStage.p, blob.bytes.size(), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->dSegBlob.p, ctx->hStage2.p, blob.bytes.size(), cudaMemcpyHostToDevice, s));
     u64 tsize = 1 << 14;
     while (tsize < 4 * bound && tsize < (1ull << 27))
       tsize <<= 1;
@@ -708,6 +754,9 @@ extern "C"
     launch_pairs(ctx->L, ctx->dSlices, (SegDev *)((uint8_t *)ctx->dSegBlob.p + oS), (RowTile *)((uint8_t *)ctx->dSegBlob.p + oT),
                  (int)tiles.size(), (uint16_t *)ctx->dConn.p, (u64 *)ctx->dPairTable.p, (uint32_t)(tsize - 1),
                  (mci_pair *)ctx->dPairs.p, ctx->capPairs, (int *)ctx->dCounters.p, ctx->dErr);
+    ctx->resPairs = 0;
+    if (ctx->deferSync)
+      return MCI_OK;
     int h = 0;
     CK(cudaMemcpyAsync(&h, ctx->dCounters.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     int rc = check_device_error(ctx);
@@ -719,12 +768,82 @@ extern "C"
     return MCI_OK;
   }
 
+  // Connected components and component matching launched back to back, ONE host round trip: component counts,
+  // the pair list and the component statistics come back together (speculatively sized; anything beyond the
+  // speculation is fetched on demand by the getters).
+  int mci_label_and_match(mci_ctx * ctx, int32_t n, const mci_slice_desc * descs, int fully, int32_t nseg,
+                          const mci_segment_desc * segs, int32_t * n_components, int32_t * n_pairs)
+  {
+    if (!ctx)
+      return MCI_ERR_ARG;
+    if (n > kSpecNcomp)
+    {
+      int rc = mci_label_slices(ctx, n, descs, fully, n_components);
+      return rc ? rc : mci_match_pairs(ctx, nseg, segs, n_pairs);
+    }
+    ctx->deferSync = true;
+    int rc = mci_label_slices(ctx, n, descs, fully, nullptr);
+    if (!rc)
+      rc = mci_match_pairs(ctx, nseg, segs, nullptr);
+    ctx->deferSync = false;
+    if (rc)
+      return rc;
+    if (n_pairs)
+      *n_pairs = 0;
+    if (n == 0)
+      return MCI_OK;
+    cudaStream_t s = ctx->L.stream;
+    CK(ctx->hRes.ensure(kResBytes));
+    uint8_t * hr = (uint8_t *)ctx->hRes.p;
+    int * hn = (int *)(hr + kResNcompOff);
+    CK(cudaMemcpyAsync(hn, ctx->dNcomp.p, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(hn + kSpecNcomp, ctx->dCompBase.p, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
+    int * hc = (int *)hr + 4; // [4]: pair count
+    const int specPairs = nseg > 0 ? std::min(kSpecPairs, ctx->capPairs) : 0;
+    const int specStats = std::min(kSpecStats, ctx->statCap);
+    if (nseg > 0)
+    {
+      CK(cudaMemcpyAsync(hc, ctx->dCounters.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(hr + kResPairsOff, ctx->dPairs.p, size_t(specPairs) * sizeof(mci_pair), cudaMemcpyDeviceToHost, s));
+    }
+    else
+      *hc = 0;
+    CK(cudaMemcpyAsync(hr + kResStatsOff, ctx->dStats.p, size_t(specStats) * sizeof(CompStat), cudaMemcpyDeviceToHost, s));
+    rc = check_device_error(ctx);
+    if (rc)
+      return rc;
+    int acc = 0;
+    for (int k = 0; k < n; ++k)
+    {
+      ctx->ncomp[k] = hn[k];
+      ctx->compBase[k] = hn[kSpecNcomp + k];
+      acc += hn[k];
+    }
+    ctx->totalComp = acc;
+    ctx->nPairs = *hc;
+    ctx->resPairs = std::min(ctx->nPairs, specPairs);
+    if (acc <= specStats)
+    {
+      ctx->hStats.resize(acc);
+      if (acc)
+        std::memcpy(ctx->hStats.data(), hr + kResStatsOff, size_t(acc) * sizeof(CompStat));
+      ctx->statsOnHost = true;
+    }
+    if (n_components)
+      std::memcpy(n_components, ctx->ncomp.data(), size_t(n) * 4);
+    if (n_pairs)
+      *n_pairs = ctx->nPairs;
+    return MCI_OK;
+  }
+
   int mci_get_pairs(mci_ctx * ctx, mci_pair * pairs)
   {
     if (!ctx || (!pairs && ctx->nPairs))
       return MCI_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    if (ctx->nPairs)
+    if (ctx->nPairs && ctx->resPairs >= ctx->nPairs)
+      std::memcpy(pairs, (const uint8_t *)ctx->hRes.p + kResPairsOff, size_t(ctx->nPairs) * sizeof(mci_pair));
+    else if (ctx->nPairs)
     {
       CK(cudaMemcpyAsync(pairs, ctx->dPairs.p, size_t(ctx->nPairs) * sizeof(mci_pair), cudaMemcpyDeviceToHost, ctx->L.stream));
       CK(cudaStreamSynchronize(ctx->L.stream));

@@ -384,17 +384,9 @@ run_core(mci_ctx * ctx, const mci_filter_options * opt, const int64_t dims[3], c
   if (segments.empty())
     return MCI_OK;
 
-  // K1/K2: component images of every annotated slice that bounds a segment
+  // K1/K2/K3: component images of every annotated slice that bounds a segment, then the pair scan of every
+  // segment, launched back to back: one host round trip brings back counts, pairs and component statistics
   std::vector<int32_t> ncomp(sliceDescs.size());
-  rc = mci_label_slices(ctx, (int32_t)sliceDescs.size(), sliceDescs.data(), opt->use_ball_structuring_element, ncomp.data());
-  if (rc)
-    return rc;
-  for (int32_t c : ncomp)
-    stats->n_components += c;
-  double t2 = now_ms();
-  stats->ms_components = t2 - t1;
-
-  // K3: pair scan
   std::vector<mci_segment_desc> segDescs(segments.size());
   for (size_t k = 0; k < segments.size(); ++k)
   {
@@ -402,9 +394,14 @@ run_core(mci_ctx * ctx, const mci_filter_options * opt, const int64_t dims[3], c
     segDescs[k].slice_j = segments[k].sj;
   }
   int32_t nPairs = 0;
-  rc = mci_match_pairs(ctx, (int32_t)segDescs.size(), segDescs.data(), &nPairs);
+  rc = mci_label_and_match(ctx, (int32_t)sliceDescs.size(), sliceDescs.data(), opt->use_ball_structuring_element,
+                           (int32_t)segDescs.size(), segDescs.data(), ncomp.data(), &nPairs);
   if (rc)
     return rc;
+  for (int32_t c : ncomp)
+    stats->n_components += c;
+  double t2 = now_ms();
+  stats->ms_components = t2 - t1;
   std::vector<mci_pair> pairs(nPairs);
   rc = mci_get_pairs(ctx, pairs.data());
   if (rc)

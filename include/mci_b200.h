@@ -60,7 +60,7 @@ typedef struct
   int64_t launches;
   double total_ms;
 } mci_kernel_time;
-int mci_profile_enable(mci_ctx * ctx, int on);
+int mci_profile_enable(mci_ctx * ctx, int on); /* 0 off, 1 every launch, 2 only the HBM-streaming kernel k_copy_flag */
 int mci_profile_read(mci_ctx * ctx, mci_kernel_time * out, int32_t cap, int32_t * n);
 
 /* ---- volume ------------------------------------------------------------------------------- */

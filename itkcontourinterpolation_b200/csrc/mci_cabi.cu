@@ -318,6 +318,7 @@ extern "C"
     CK(cudaStreamSynchronize(ctx->L.stream));
     recycle_events(ctx);
     ctx->L.profile = on != 0;
+    ctx->L.only = on == 2 ? "k_copy_flag" : nullptr; // 2: time only the HBM-streaming kernel (negligible overhead)
     return MCI_OK;
   }
 

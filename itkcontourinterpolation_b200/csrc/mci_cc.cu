@@ -362,7 +362,7 @@ launch_cc(Launch & L, int ptype, const void * in, const SliceDev * slices, int n
 {
   if (nslices == 0 || ntiles == 0)
     return;
-  L.pre();
+  L.pre("k_slice_bits");
   switch (ptype)
   {
     case MCI_U8:
@@ -383,11 +383,11 @@ launch_cc(Launch & L, int ptype, const void * in, const SliceDev * slices, int n
   }
   const int smemBytes = ((maxRows + 1) + 3 * CC_SMEM_RUNS) * 4;
   const int maxPer = ptype == MCI_U8 ? 255 : (ptype == MCI_U16 ? 65535 : 32767);
-  L.pre();
+  L.pre("k_cc_runs");
   k_cc_runs<<<nslices, CC_THREADS, smemBytes, L.stream>>>(slices, bits, wordRun, runComp, runScratch, fully, ncomp, compBase, total,
                                                            stats, statCap, maxPer, err);
   L.post("k_cc_runs");
-  L.pre();
+  L.pre("k_cc_paint");
   k_cc_paint<<<ntiles, 256, 0, L.stream>>>(slices, tiles, bits, wordRun, runComp, conn);
   L.post("k_cc_paint");
 }

@@ -1033,11 +1033,11 @@ launch_dt_level(Launch & L, int ptype, const DtLevel & lv)
   const int nodeGrid = std::max(1, std::min(lv.maxNodes, L.sms * 8));
   const int itemGrid = std::max(1, std::min(lv.itemCap, L.sms * 8));
   const int histGrid = std::max(1, std::min((lv.hitemCap + 7) / 8, L.sms * 8));
-  L.pre();
+  L.pre("k_dt_prep");
   k_dt_prep<<<nodeGrid, 256, 0, L.stream>>>(lv.nodes, lv.count, lv.work, lv.arena, lv.scratch, lv.scratchTop, lv.scratchCap,
                                              lv.items, lv.itemCount, lv.itemCap, lv.hitems, lv.hitemCount, lv.hitemCap, lv.err);
   L.post("k_dt_prep");
-  L.pre();
+  L.pre("k_dt_hist");
   switch (ptype)
   {
     case MCI_U8:
@@ -1053,7 +1053,7 @@ launch_dt_level(Launch & L, int ptype, const DtLevel & lv)
                                                           lv.histSide, lv.bigHist, lv.bigCount, lv.nbig, lv.err);
   }
   L.post("k_dt_hist");
-  L.pre();
+  L.pre("k_dt_scan");
   switch (ptype)
   {
     case MCI_U8:
@@ -1066,15 +1066,15 @@ launch_dt_level(Launch & L, int ptype, const DtLevel & lv)
       k_dt_scan<int16_t><<<nodeGrid, 256, 0, L.stream>>>(lv.work, lv.count, lv.hist, lv.histStride, lv.histSide, lv.bigHist);
   }
   L.post("k_dt_scan");
-  L.pre();
+  L.pre("k_dt_median");
   k_dt_median<<<itemGrid, 256, 0, L.stream>>>(lv.work, lv.items, lv.itemCount, lv.scratch, (int)lv.dims[0], (int)lv.dims[1],
                                                (int)lv.dims[2], lv.err);
   L.post("k_dt_median");
-  L.pre();
+  L.pre("k_dt_alloc");
   k_dt_alloc<<<(lv.maxNodes + 127) / 128, 128, 0, L.stream>>>(lv.work, lv.count, lv.arenaTop, lv.arenaCap, lv.next, lv.nextCount,
                                                                 lv.nextCap, lv.witems, lv.witemCount, lv.itemCap, lv.err);
   L.post("k_dt_alloc");
-  L.pre();
+  L.pre("k_dt_emit");
   switch (ptype)
   {
     case MCI_U8:

@@ -448,7 +448,7 @@ launch_detect(Launch & L, int ptype, const void * in, void * out, const long lon
   const long long nWords = (nchunks + 31) / 32;
   int gridA = (int)std::max<long long>(1, std::min<long long>((nchunks + 4 * 256 - 1) / (4 * 256), (long long)L.sms * 8));
   int gridB = (int)std::max<long long>(1, std::min<long long>((nWords + 7) / 8, (long long)L.sms * 8));
-  L.pre();
+  L.pre("k_copy_flag");
   switch (ptype)
   {
     case MCI_U8:
@@ -461,7 +461,7 @@ launch_detect(Launch & L, int ptype, const void * in, void * out, const long lon
       k_copy_flag<int16_t><<<gridA, 256, 0, L.stream>>>((const int16_t *)in, (int16_t *)out, n, chunkBits);
   }
   L.post("k_copy_flag");
-  L.pre();
+  L.pre("k_detect_marked");
   switch (ptype)
   {
     case MCI_U8:
@@ -483,7 +483,7 @@ void
 launch_compact_labels(Launch & L, const int * bbox, int nl, const uint32_t * sliceBits, int wordsPerLabel, int wo1, int wo2,
                       int signedLabels, mci_label_info * labels, mci_labeled_slice * slices, int capSlices, int * counters)
 {
-  L.pre();
+  L.pre("k_compact_labels");
   k_compact_labels<<<(nl + 255) / 256, 256, 0, L.stream>>>(bbox, nl, sliceBits, wordsPerLabel, wo1, wo2, signedLabels, labels,
                                                           slices, capSlices, counters);
   L.post("k_compact_labels");
@@ -526,7 +526,7 @@ launch_combine_max(Launch & L, int ptype, void * dst, const void * src, long lon
     return;
   const int elt = ptype == MCI_U8 ? 1 : 2;
   int grid = (int)std::max<long long>(1, std::min<long long>((n / (16 / elt) + 255) / 256, (long long)L.sms * 16));
-  L.pre();
+  L.pre("k_combine_max");
   switch (ptype)
   {
     case MCI_U8:
@@ -609,7 +609,7 @@ launch_pairs(Launch & L, const SliceDev * slices, const SegDev * segs, const Row
 {
   if (ntiles == 0)
     return;
-  L.pre();
+  L.pre("k_pairs");
   k_pairs<<<ntiles, 256, 0, L.stream>>>(slices, segs, tiles, conn, table, tableMask, pairs, capPairs, nPairs, err);
   L.post("k_pairs");
 }
@@ -647,7 +647,7 @@ launch_extract(Launch & L, const SliceDev * slices, const ExtractJob * jobs, int
 {
   if (njobs == 0)
     return;
-  L.pre();
+  L.pre("k_extract");
   k_extract<<<njobs, 256, 0, L.stream>>>(slices, jobs, conn, arena);
   L.post("k_extract");
 }
@@ -1045,7 +1045,7 @@ launch_align(Launch & L, const AlignJob * jobs, int njobs, const MaskRef * refs,
     attr = true;
   }
   int grid = std::min(njobs, L.sms * 8);
-  L.pre();
+  L.pre("k_align");
   k_align<<<grid, ALIGN_THREADS, smemBytes + ALIGN_MASK_WORDS * 4, L.stream>>>(jobs, njobs, refs, arena, gscratch, heuristic,
                                                                               result, dbg, err);
   L.post("k_align");
@@ -1170,7 +1170,7 @@ launch_split(Launch & L, const SplitJob * jobs, int njobs, const MaskRef * refs,
     attr = true;
   }
   const int smemBytes = 160 * 1024;
-  L.pre();
+  L.pre("k_split");
   k_split<<<njobs, SPLIT_THREADS, smemBytes, L.stream>>>(jobs, refs, arena, gscratch, trans, ball, smemBytes / 4, err);
   L.post("k_split");
 }
@@ -1244,7 +1244,7 @@ launch_make_roots(Launch & L, const RootJob * roots, int nroots, MaskRef * refs,
 {
   if (nroots == 0)
     return;
-  L.pre();
+  L.pre("k_make_roots");
   k_make_roots<<<(nroots + 127) / 128, 128, 0, L.stream>>>(roots, nroots, refs, arena, trans, nodes);
   L.post("k_make_roots");
 }
@@ -1985,7 +1985,7 @@ launch_nodes_t(Launch & L, const Node * nodes, const int * count, int maxNodes, 
   }
   int g = std::max(1, std::min(grid, maxNodes));
   int smemWords = smemBytes / 4 - 2 * MCI_SMALL_HIST;
-  L.pre();
+  L.pre("k_nodes");
   k_nodes<T><<<g, MCI_NODE_THREADS, smemBytes, L.stream>>>(nodes, count, next, nextCount, nextCap, arena, arenaTop, arenaCap,
                                                           (const T *)in, (T *)out, dims[0], dims[1], dims[2], useDT, ball,
                                                           bigHist, slab, slabWords, smemWords, err);

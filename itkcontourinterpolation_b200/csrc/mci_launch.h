@@ -39,9 +39,21 @@ struct Launch
       cudaEventCreate(&e);
     return e;
   }
-  void pre()
+  const char * only = nullptr; // when set, only launches of this kernel are timed
+  bool pending = false;
+  static bool same(const char * a, const char * b)
   {
-    if (profile)
+    while (*a && *a == *b)
+    {
+      ++a;
+      ++b;
+    }
+    return *a == *b;
+  }
+  void pre(const char * name)
+  {
+    pending = profile && (!only || same(only, name));
+    if (pending)
     {
       pendingStart = take();
       cudaEventRecord(pendingStart, stream);
@@ -50,8 +62,9 @@ struct Launch
   void post(const char * name)
   {
     ++count;
-    if (profile)
+    if (pending)
     {
+      pending = false;
       Rec r;
       r.name = name;
       r.a = pendingStart;

@@ -213,3 +213,26 @@ def test_full_size_c5_on_one_gpu(flt):
     del dense
     out = run_gpu(flt, vol, axis=2)
     assert_same(out, O.interpolate(vol, axis=2, threads=os.cpu_count() or 1), "C5 full size")
+
+
+def _big_roi_volume(n=1200, dtype=np.uint16):
+    """Shapes far larger than any shared-memory budget, with ragged borders and holes (many runs per row):
+    exercises the global-scratch fall-backs of Align, the 1-to-N split, the node kernels and the run tables."""
+    rng = np.random.default_rng(11)
+    v = np.zeros((5, n, n), dtype)
+    yy, xx = np.mgrid[:n, :n]
+    big = (yy - n // 2) ** 2 + (xx - n // 2) ** 2 <= (n // 2 - 20) ** 2
+    noise = rng.random((n, n)) < 0.35
+    v[0][big & ~(noise & ((yy + xx) % 7 == 0))] = 3           # pepper holes: thousands of runs, one giant component
+    two = ((yy - n // 2) ** 2 + (xx - n // 3) ** 2 <= (n // 7) ** 2) | ((yy - n // 2) ** 2 + (xx - 2 * n // 3) ** 2 <= (n // 8) ** 2)
+    v[4][two] = 3                                             # 1-to-2 branching against the giant shape
+    v[0][:14, :14][noise[:14, :14]] = 3                       # salt: a few dozen tiny components to extrapolate
+    return v
+
+
+@pytest.mark.parametrize("algo", ["D", "C"])
+def test_big_regions_take_the_global_scratch_paths(flt, algo):
+    kw = cases.ALGOS[algo]
+    v = _big_roi_volume()
+    out = run_gpu(flt, v, **kw)
+    assert_same(out, O.interpolate(v, threads=os.cpu_count() or 1, **kw), "big ROI " + algo)

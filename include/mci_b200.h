@@ -182,6 +182,15 @@ int mci_get_align_stats(mci_ctx * ctx, int32_t * out /* [4*n_jobs] */);
  * partial outputs of sharded runs (device pointers; runs on the context's stream) */
 int mci_combine_max(mci_ctx * ctx, void * dev_dst, const void * dev_src, int64_t n_pixels, int pixel_type);
 
+/* Multi-GPU combine by shapes instead of by voxels: after a (sharded) run, the mid slices it produced are available
+ * as a list of 48-byte records {x0,y0,w,h,pitch,pad,word offset; axis,label,mid,pad} plus their bit-packed rows
+ * (device pointers into the context, valid until the next run).  mci_apply_masks replays such a list -- typically
+ * another GPU's, received over NCCL -- into this context's output volume with the write rule of X:754-763. */
+int mci_get_emitted(mci_ctx * ctx, void ** recs_dev, int64_t * n_recs, void ** words_dev, int64_t * n_words);
+/* packs the list into a caller-owned device buffer: records at dst, bit rows at dst + words_offset_bytes */
+int mci_copy_emitted(mci_ctx * ctx, void * dst_dev, int64_t words_offset_bytes);
+int mci_apply_masks(mci_ctx * ctx, const void * recs_dev, int64_t n_recs, const void * words_dev, int64_t n_words);
+
 /* ---- host scheduler (layer 2): the filter itself --------------------------------------------
  * Mirrors the setters of H:85-165 and GenerateData (X:1559-1637). */
 typedef struct

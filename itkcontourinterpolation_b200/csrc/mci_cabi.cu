@@ -127,7 +127,10 @@ struct mci_ctx
   int nPairs = 0, capPairs = 0;
   // interpolation
   DBuf dJobBlob, dArena, dScratch, dBigHist, dSlab, dNodes, dLevelCounts, dArenaTop, dTrans;
-  DBuf dWork, dItems, dLevelScratch, dHist, dDtBig, dDtCounters;
+  DBuf dWork, dItems, dLevelScratch, dHist, dDtBig, dDtCounters, dEmit;
+  unsigned long long emitBase = 0; // arena word where the mid shapes of the last run start
+  int emitCap = 0;
+  bool haveEmit = false;
   bool histClean = false, dtBigClean = false;
   int bigHistGrid = 0;
   int nJobs = 0;
@@ -253,7 +256,7 @@ extern "C"
                       &ctx->dPairs,    &ctx->dJobBlob,  &ctx->dArena,   &ctx->dScratch,   &ctx->dBigHist, &ctx->dSlab,
                       &ctx->dNodes,    &ctx->dLevelCounts, &ctx->dArenaTop, &ctx->dTrans,
                       &ctx->dWork, &ctx->dItems, &ctx->dLevelScratch, &ctx->dHist, &ctx->dDtBig, &ctx->dDtCounters,
-                      &ctx->dChunkBits };
+                      &ctx->dChunkBits, &ctx->dEmit };
     for (DBuf * b : bufs)
       b->release();
     recycle_events(ctx);
@@ -873,6 +876,7 @@ extern "C"
       return MCI_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     ctx->nJobs = njobs;
+    ctx->haveEmit = false;
     if (njobs == 0)
       return MCI_OK;
     int rc = fetch_stats(ctx);
@@ -1113,6 +1117,13 @@ extern "C"
       nodeTotal += c;
     CK(ctx->dNodes.ensure(size_t(nodeTotal + 1) * sizeof(Node)));
     CK(ctx->dLevelCounts.ensure(size_t(maxDepth + 2) * sizeof(int)));
+    CK(ctx->dEmit.ensure(16 + size_t(nodeTotal + 1) * sizeof(EmitRec)));
+    CK(cudaMemsetAsync(ctx->dEmit.p, 0, 16, s));
+    ctx->emitCap = (int)nodeTotal;
+    ctx->emitBase = arenaWords;
+    ctx->haveEmit = true;
+    EmitRec * dEmitRecs = (EmitRec *)((uint8_t *)ctx->dEmit.p + 16);
+    int * dEmitCount = (int *)ctx->dEmit.p;
     CK(ctx->dArenaTop.ensure(8));
     // bitmaps of the global-scratch Align jobs must start cleared (the kernel clears them itself as well)
     std::vector<int> lc(maxDepth + 2, 0);
@@ -1217,6 +1228,10 @@ extern "C"
         lv.next = dNodes + off + levelCap[d];
         lv.nextCount = dCounts + d + 1;
         lv.nextCap = d + 1 < maxDepth ? (int)levelCap[d + 1] : 0;
+        lv.emit = dEmitRecs;
+        lv.emitCount = dEmitCount;
+        lv.emitCap = ctx->emitCap;
+        lv.emitBase = ctx->emitBase;
         lv.in = ctx->dIn;
         lv.out = ctx->dOut;
         for (int a = 0; a < 3; ++a)
@@ -1251,7 +1266,7 @@ extern "C"
         launch_nodes(ctx->L, ctx->ptype, cur, dCounts + d, (int)levelCap[d], nxt, dCounts + d + 1, nextCap,
                      (uint32_t *)ctx->dArena.p, (unsigned long long *)ctx->dArenaTop.p, arenaCap, ctx->dIn, ctx->dOut, ctx->dims,
                      0, prm->use_ball, (unsigned *)ctx->dBigHist.p, (uint32_t *)ctx->dSlab.p, slabWords, nodeGrid, nodeSmem,
-                     ctx->dErr);
+                     dEmitRecs, dEmitCount, ctx->emitCap, ctx->emitBase, ctx->dErr);
         off += levelCap[d];
       }
     }
@@ -1271,6 +1286,62 @@ extern "C"
                          size_t(ctx->nJobs) * 16, cudaMemcpyDeviceToHost, ctx->L.stream));
       CK(cudaStreamSynchronize(ctx->L.stream));
     }
+    return MCI_OK;
+  }
+
+  // ---- multi-GPU combine by mid-slice shapes ---------------------------------------------------------
+  int mci_get_emitted(mci_ctx * ctx, void ** recs_dev, int64_t * n_recs, void ** words_dev, int64_t * n_words)
+  {
+    if (!ctx || !recs_dev || !n_recs || !words_dev || !n_words)
+      return MCI_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    *recs_dev = nullptr;
+    *words_dev = nullptr;
+    *n_recs = 0;
+    *n_words = 0;
+    if (!ctx->haveEmit)
+      return MCI_OK; // the last run had no interpolation job
+    int cnt = 0;
+    unsigned long long top = 0;
+    CK(cudaMemcpyAsync(&cnt, ctx->dEmit.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->L.stream));
+    CK(cudaMemcpyAsync(&top, ctx->dArenaTop.p, 8, cudaMemcpyDeviceToHost, ctx->L.stream));
+    int rc = check_device_error(ctx);
+    if (rc)
+      return rc;
+    *recs_dev = (uint8_t *)ctx->dEmit.p + 16;
+    *n_recs = std::min(cnt, ctx->emitCap);
+    *words_dev = (uint32_t *)ctx->dArena.p + ctx->emitBase;
+    *n_words = (int64_t)(top - ctx->emitBase);
+    return MCI_OK;
+  }
+
+  int mci_copy_emitted(mci_ctx * ctx, void * dst_dev, int64_t words_offset_bytes)
+  {
+    if (!ctx || !dst_dev || words_offset_bytes < 0)
+      return MCI_ERR_ARG;
+    void *recs = nullptr, *words = nullptr;
+    int64_t nr = 0, nw = 0;
+    int rc = mci_get_emitted(ctx, &recs, &nr, &words, &nw);
+    if (rc)
+      return rc;
+    if ((int64_t)(nr * sizeof(EmitRec)) > words_offset_bytes)
+      return fail(ctx, MCI_ERR_ARG, "record area too small");
+    if (nr)
+      CK(cudaMemcpyAsync(dst_dev, recs, size_t(nr) * sizeof(EmitRec), cudaMemcpyDeviceToDevice, ctx->L.stream));
+    if (nw)
+      CK(cudaMemcpyAsync((uint8_t *)dst_dev + words_offset_bytes, words, size_t(nw) * 4, cudaMemcpyDeviceToDevice, ctx->L.stream));
+    CK(cudaStreamSynchronize(ctx->L.stream));
+    return MCI_OK;
+  }
+
+  int mci_apply_masks(mci_ctx * ctx, const void * recs_dev, int64_t n_recs, const void * words_dev, int64_t n_words)
+  {
+    if (!ctx || n_recs < 0 || (n_recs > 0 && (!recs_dev || !words_dev)) || !ctx->dIn || !ctx->dOut)
+      return MCI_ERR_ARG;
+    (void)n_words;
+    CK(cudaSetDevice(ctx->device));
+    launch_apply_masks(ctx->L, ctx->ptype, (const EmitRec *)recs_dev, (int)n_recs, (const uint32_t *)words_dev, ctx->dIn, ctx->dOut,
+                       ctx->dims);
     return MCI_OK;
   }
 

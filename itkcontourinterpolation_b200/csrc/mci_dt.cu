@@ -785,7 +785,8 @@ k_dt_median(NodeWork * work, const DtItem * __restrict__ items, const int * __re
 // ---------------------------------------------------------------------------------------------------
 __global__ void
 k_dt_alloc(NodeWork * work, const int * __restrict__ count, unsigned long long * arenaTop, unsigned long long arenaCap, Node * next,
-           int * nextCount, int nextCap, DtItem * witems, int * witemCount, int witemCap, int * err)
+           int * nextCount, int nextCap, DtItem * witems, int * witemCount, int witemCap, EmitRec * emit, int * emitCount,
+           int emitCap, unsigned long long emitBase, int * err)
 {
   const int nidx = blockIdx.x * blockDim.x + threadIdx.x;
   if (nidx >= *count)
@@ -814,6 +815,23 @@ k_dt_alloc(NodeWork * work, const int * __restrict__ count, unsigned long long *
     return;
   }
   W->M = M;
+  if (emit)
+  {
+    const int e = atomicAdd(emitCount, 1);
+    if (e < emitCap)
+    {
+      EmitRec r;
+      r.M = M;
+      r.M.off = M.off - emitBase;
+      r.axis = W->nd.axis;
+      r.label = W->nd.label;
+      r.mid = W->mid;
+      r.pad = 0;
+      emit[e] = r;
+    }
+    else
+      atomicMax(err, ERR_NODE_LIST);
+  }
   const int nItems = (mwords + DT_CHUNK - 1) / DT_CHUNK;
   const int base = atomicAdd(witemCount, nItems);
   if (base + nItems > witemCap)
@@ -1025,6 +1043,121 @@ k_dt_emit(const NodeWork * __restrict__ work, const DtItem * __restrict__ witems
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Replays the volume writes of mid slices produced elsewhere (another GPU's shard): same write rule as k_dt_emit.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_apply_masks(const EmitRec * __restrict__ recs, int nrecs, const uint32_t * __restrict__ words, const T * __restrict__ in, T * out,
+              long long VX, long long VY, long long VZ)
+{
+  constexpr int VPQ = 8 / sizeof(T);
+  constexpr int GPW = 32 / VPQ + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const unsigned long long nvox = (unsigned long long)VX * VY * VZ;
+  for (int ri = blockIdx.x; ri < nrecs; ri += gridDim.x)
+  {
+    const EmitRec R = recs[ri];
+    const MaskRef M = R.M;
+    const T label = (T)R.label;
+    long long su, sv;
+    unsigned long long vbase;
+    if (R.axis == 2)
+    {
+      su = 1;
+      sv = VX;
+      vbase = (unsigned long long)R.mid * VX * VY;
+    }
+    else if (R.axis == 1)
+    {
+      su = 1;
+      sv = VX * VY;
+      vbase = (unsigned long long)R.mid * VX;
+    }
+    else
+    {
+      su = VX;
+      sv = VX * VY;
+      vbase = (unsigned long long)R.mid;
+    }
+    const int mwords = M.h * M.pitch;
+    for (int cb = warp * 32; cb < mwords; cb += nwarps * 32)
+    {
+      const int cEnd = min(mwords, cb + 32);
+      const uint32_t myM = cb + lane < cEnd ? __ldg(words + M.off + cb + lane) : 0u;
+      if (su == 1)
+      {
+        const int nTasks = (cEnd - cb) * GPW;
+        for (int tb = 0; tb < nTasks; tb += 32)
+        {
+          const int task = tb + lane;
+          const int c = min(task / GPW, cEnd - cb - 1), q = task % GPW;
+          const uint32_t m = __shfl_sync(0xFFFFFFFFu, myM, c);
+          if (task < nTasks && m)
+          {
+            const int cell = cb + c;
+            const int r = cell / M.pitch, wi = cell - r * M.pitch;
+            const unsigned long long a0 = vbase + (unsigned long long)((long long)(M.x0 + 32 * wi) + (long long)(M.y0 + r) * sv);
+            const unsigned long long g = (a0 & ~(unsigned long long)(VPQ - 1)) + (unsigned long long)q * VPQ;
+            const long long sh = (long long)g - (long long)a0;
+            unsigned bits;
+            if (sh >= 32)
+              bits = 0u;
+            else if (sh >= 0)
+              bits = (m >> sh) & ((1u << VPQ) - 1u);
+            else
+              bits = (m << (-sh)) & ((1u << VPQ) - 1u);
+            if (bits && g + VPQ <= nvox)
+              write_group<T>(in, out, g, bits, label);
+            else if (bits)
+              for (int k = 0; k < VPQ; ++k)
+                if (((bits >> k) & 1u) && g + k < nvox && in[g + k] == 0)
+                  atomic_max_pixel(out + g + k, label);
+          }
+        }
+      }
+      else
+      {
+        for (int c = 0; c < cEnd - cb; ++c)
+        {
+          const uint32_t m = __shfl_sync(0xFFFFFFFFu, myM, c);
+          if ((m >> lane) & 1u)
+          {
+            const int cell = cb + c;
+            const int r = cell / M.pitch, wi = cell - r * M.pitch;
+            const unsigned long long a =
+              vbase + (unsigned long long)((long long)(M.x0 + 32 * wi + lane) * su + (long long)(M.y0 + r) * sv);
+            if (in[a] == 0)
+              atomic_max_pixel(out + a, label);
+          }
+        }
+      }
+    }
+  }
+}
+
+void
+launch_apply_masks(Launch & L, int ptype, const EmitRec * recs, int nrecs, const uint32_t * words, const void * in, void * out,
+                   const long long dims[3])
+{
+  if (nrecs <= 0)
+    return;
+  const int grid = std::max(1, std::min(nrecs, L.sms * 8));
+  L.pre("k_apply_masks");
+  switch (ptype)
+  {
+    case MCI_U8:
+      k_apply_masks<uint8_t><<<grid, 256, 0, L.stream>>>(recs, nrecs, words, (const uint8_t *)in, (uint8_t *)out, dims[0], dims[1], dims[2]);
+      break;
+    case MCI_U16:
+      k_apply_masks<uint16_t><<<grid, 256, 0, L.stream>>>(recs, nrecs, words, (const uint16_t *)in, (uint16_t *)out, dims[0], dims[1],
+                                                           dims[2]);
+      break;
+    default:
+      k_apply_masks<int16_t><<<grid, 256, 0, L.stream>>>(recs, nrecs, words, (const int16_t *)in, (int16_t *)out, dims[0], dims[1], dims[2]);
+  }
+  L.post("k_apply_masks");
+}
+
+// ---------------------------------------------------------------------------------------------------
 void
 launch_dt_level(Launch & L, int ptype, const DtLevel & lv)
 {
@@ -1072,7 +1205,8 @@ launch_dt_level(Launch & L, int ptype, const DtLevel & lv)
   L.post("k_dt_median");
   L.pre("k_dt_alloc");
   k_dt_alloc<<<(lv.maxNodes + 127) / 128, 128, 0, L.stream>>>(lv.work, lv.count, lv.arenaTop, lv.arenaCap, lv.next, lv.nextCount,
-                                                                lv.nextCap, lv.witems, lv.witemCount, lv.itemCap, lv.err);
+                                                                lv.nextCap, lv.witems, lv.witemCount, lv.itemCap, lv.emit, lv.emitCount,
+                                                                lv.emitCap, lv.emitBase, lv.err);
   L.post("k_dt_alloc");
   L.pre("k_dt_emit");
   switch (ptype)

@@ -1721,7 +1721,8 @@ __global__ void __launch_bounds__(MCI_NODE_THREADS, 2)
 k_nodes(const Node * __restrict__ nodes, const int * __restrict__ count, Node * next, int * nextCount, int nextCap,
         uint32_t * arena, unsigned long long * arenaTop, unsigned long long arenaCap, const T * __restrict__ in, T * out,
         long long VX, long long VY, long long VZ, int useDT, int ball, unsigned * bigHistAll, uint32_t * slabAll,
-        unsigned long long slabWords, int smemWords, int * err)
+        unsigned long long slabWords, int smemWords, EmitRec * emit, int * emitCount, int emitCap, unsigned long long emitBase,
+        int * err)
 {
   extern __shared__ uint32_t smem[];
   __shared__ NodeShared sh;
@@ -1878,6 +1879,23 @@ k_nodes(const Node * __restrict__ nodes, const int * __restrict__ count, Node * 
         atomicMax(err, ERR_ARENA);
       continue;
     }
+    if (emit && tid == 0)
+    {
+      const int e = atomicAdd(emitCount, 1);
+      if (e < emitCap)
+      {
+        EmitRec r;
+        r.M = M;
+        r.M.off = M.off - emitBase;
+        r.axis = nd.axis;
+        r.label = nd.label;
+        r.mid = mid;
+        r.pad = 0;
+        emit[e] = r;
+      }
+      else
+        atomicMax(err, ERR_NODE_LIST);
+    }
     // ---- store the mid shape and write it into the volume with the max rule (X:714-764)
     {
       const int lane = tid & 31, warp = tid >> 5;
@@ -1975,7 +1993,7 @@ static void
 launch_nodes_t(Launch & L, const Node * nodes, const int * count, int maxNodes, Node * next, int * nextCount, int nextCap,
                uint32_t * arena, unsigned long long * arenaTop, unsigned long long arenaCap, const void * in, void * out,
                const long long dims[3], int useDT, int ball, unsigned * bigHist, uint32_t * slab, unsigned long long slabWords,
-               int grid, int smemBytes, int * err)
+               int grid, int smemBytes, EmitRec * emit, int * emitCount, int emitCap, unsigned long long emitBase, int * err)
 {
   static bool attr = false;
   if (!attr)
@@ -1988,7 +2006,7 @@ launch_nodes_t(Launch & L, const Node * nodes, const int * count, int maxNodes, 
   L.pre("k_nodes");
   k_nodes<T><<<g, MCI_NODE_THREADS, smemBytes, L.stream>>>(nodes, count, next, nextCount, nextCap, arena, arenaTop, arenaCap,
                                                           (const T *)in, (T *)out, dims[0], dims[1], dims[2], useDT, ball,
-                                                          bigHist, slab, slabWords, smemWords, err);
+                                                          bigHist, slab, slabWords, smemWords, emit, emitCount, emitCap, emitBase, err);
   L.post("k_nodes");
 }
 
@@ -1996,7 +2014,8 @@ void
 launch_nodes(Launch & L, int ptype, const Node * nodes, const int * count, int maxNodes, Node * next, int * nextCount,
              int nextCap, uint32_t * arena, unsigned long long * arenaTop, unsigned long long arenaCap, const void * in,
              void * out, const long long dims[3], int useDT, int ball, unsigned * bigHist, uint32_t * slab,
-             unsigned long long slabWords, int grid, int smemBytes, int * err)
+             unsigned long long slabWords, int grid, int smemBytes, EmitRec * emit, int * emitCount, int emitCap,
+             unsigned long long emitBase, int * err)
 {
   if (maxNodes <= 0)
     return;
@@ -2004,15 +2023,15 @@ launch_nodes(Launch & L, int ptype, const Node * nodes, const int * count, int m
   {
     case MCI_U8:
       launch_nodes_t<uint8_t>(L, nodes, count, maxNodes, next, nextCount, nextCap, arena, arenaTop, arenaCap, in, out, dims,
-                              useDT, ball, bigHist, slab, slabWords, grid, smemBytes, err);
+                              useDT, ball, bigHist, slab, slabWords, grid, smemBytes, emit, emitCount, emitCap, emitBase, err);
       break;
     case MCI_U16:
       launch_nodes_t<uint16_t>(L, nodes, count, maxNodes, next, nextCount, nextCap, arena, arenaTop, arenaCap, in, out, dims,
-                               useDT, ball, bigHist, slab, slabWords, grid, smemBytes, err);
+                               useDT, ball, bigHist, slab, slabWords, grid, smemBytes, emit, emitCount, emitCap, emitBase, err);
       break;
     default:
       launch_nodes_t<int16_t>(L, nodes, count, maxNodes, next, nextCount, nextCap, arena, arenaTop, arenaCap, in, out, dims,
-                              useDT, ball, bigHist, slab, slabWords, grid, smemBytes, err);
+                              useDT, ball, bigHist, slab, slabWords, grid, smemBytes, emit, emitCount, emitCap, emitBase, err);
   }
 }
 

@@ -120,6 +120,13 @@ struct NodeWork
   MaskRef M;                        // the mid shape
 };
 
+// One mid slice produced by a run: enough to replay its volume write elsewhere (multi-GPU combine).
+struct EmitRec
+{
+  MaskRef M; // off is relative to the first mid-shape word of the arena
+  int axis, label, mid, pad;
+};
+
 struct DtItem
 {
   int node;

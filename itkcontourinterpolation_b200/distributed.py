@@ -1,5 +1,13 @@
 """One label volume sharded across the GPUs of one box by (label, axis, slice-pair) segment.
 
+Two ways to combine the partial results (ShardedInterpolator.run(mode=...)):
+
+  "masks" (default): every rank all-gathers the mid slices the others produced AS BIT-PACKED SHAPES (48-byte record
+      + A/8 bytes per slice: a few hundred MB for the 8.6 GB C5 volume) and replays their volume writes locally with
+      mci_apply_masks.  Every rank ends with the full output; no voxel ever crosses NVLink.
+  "slabs": z-slabs of the partial output volumes are exchanged and max-combined (described below); simple, but it
+      moves the whole volume.
+
 Every rank holds the input volume, runs slice detection, and interpolates only the segments
 k with k % world == rank (mci_filter_options.shard_index / shard_count); its partial output is the input
 copy plus its own mid slices.  One exchange step follows (the only inter-GPU traffic of the path):
@@ -99,10 +107,42 @@ class ShardedInterpolator:
         if rc:
             raise self.L.MciError(rc, self.lib.mci_last_error(self.ctx).decode())
 
+    def _combine_by_masks(self, partial, world):
+        """all-gather (records, bit rows) of every rank's mid slices, replay the others' into `partial`."""
+        torch, dist, ct = self.torch, self.dist, self.ct
+        recs, words = ct.c_void_p(), ct.c_void_p()
+        nrec, nword = ct.c_int64(0), ct.c_int64(0)
+        self._check(self.lib.mci_get_emitted(self.ctx, ct.byref(recs), ct.byref(nrec), ct.byref(words), ct.byref(nword)))
+        REC = 48
+        sizes = torch.tensor([nrec.value, nword.value], dtype=torch.int64, device=self.device)
+        allsizes = torch.empty((world, 2), dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(allsizes.view(-1), sizes, group=self.group)
+        allsizes = allsizes.cpu()
+        max_rec, max_word = int(allsizes[:, 0].max()), int(allsizes[:, 1].max())
+        if max_rec == 0:
+            return partial
+        slot = max_rec * REC + max_word * 4
+        slot = (slot + 15) // 16 * 16
+        send = torch.empty(slot, dtype=torch.uint8, device=self.device)
+        if nrec.value:
+            self._check(self.lib.mci_copy_emitted(self.ctx, send.data_ptr(), max_rec * REC))
+        gathered = torch.empty((world, slot), dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(gathered.view(-1), send, group=self.group)
+        torch.cuda.current_stream(self.device).synchronize()
+        rank = dist.get_rank(self.group)
+        for q in range(world):
+            n_r, n_w = int(allsizes[q, 0]), int(allsizes[q, 1])
+            if q == rank or n_r == 0:
+                continue
+            base = gathered[q].data_ptr()
+            self._check(self.lib.mci_apply_masks(self.ctx, base, n_r, base + max_rec * REC, n_w))
+        self._check(self.lib.mci_synchronize(self.ctx))
+        return partial
+
     def _combine(self, dst, src):
         self._check(self.lib.mci_combine_max(self.ctx, dst.data_ptr(), src.data_ptr(), dst.numel(), self._ptype[dst.dtype]))
 
-    def run(self, vol, gather=True, **options):
+    def run(self, vol, gather=True, mode="masks", **options):
         """vol: CUDA tensor [Z, Y, X] present on every rank.  Returns the interpolated volume."""
         torch, dist, ct = self.torch, self.dist, self.ct
         for k, v in options.items():
@@ -119,6 +159,8 @@ class ShardedInterpolator:
         self.last_stats = st.as_dict()
         if world == 1:
             return partial
+        if mode == "masks":
+            return self._combine_by_masks(partial, world)
 
         def combine(dst, src):
             # slices of a slot are not 16-byte aligned in general: stage through aligned temporaries when needed

@@ -54,3 +54,47 @@ def test_three_shards_combine_to_the_full_result(name, kw_gpu, kw_cpu):
         assert np.array_equal(acc.cpu().numpy().view(np.uint16), full)
     finally:
         lib.mci_destroy(ctx)
+
+
+@pytest.mark.parametrize("name,kw_gpu,kw_cpu", [
+    ("C4", dict(use_distance_transform=0, use_ball_structuring_element=1), dict(use_distance_transform=False, use_ball=True)),
+    ("C3", dict(axis=2), dict(axis=2)),
+])
+def test_combine_by_mid_slice_shapes(name, kw_gpu, kw_cpu):
+    """The NCCL-free core of the "masks" combine: shard 0's volume receives the mid slices of shards 1 and 2 as
+    (record, bit rows) lists through mci_get_emitted / mci_apply_masks and must end up equal to the full result."""
+    vol, _ = cases.synthetic_small()[name]
+    lib = L.lib()
+    dims = (ctypes.c_int64 * 3)(vol.shape[2], vol.shape[1], vol.shape[0])
+    d_in = torch.from_numpy(vol.view(np.int16)).cuda()
+    ctxs, outs, lists = [], [], []
+    try:
+        for r in range(3):
+            ctx = ctypes.c_void_p()
+            assert lib.mci_create(ctypes.byref(ctx), 0) == 0
+            ctxs.append(ctx)
+            opt = L.FilterOptions()
+            lib.mci_filter_default_options(ctypes.byref(opt))
+            for k, v in kw_gpu.items():
+                setattr(opt, k, v)
+            opt.shard_index, opt.shard_count = r, 3
+            out = torch.empty_like(d_in)
+            outs.append(out)
+            assert lib.mci_attach_device_volume(ctx, d_in.data_ptr(), out.data_ptr(), dims, L.U16) == 0
+            st = L.FilterStats()
+            assert lib.mci_filter_run_resident(ctx, ctypes.byref(opt), None, 0, ctypes.byref(st)) == 0, lib.mci_last_error(ctx)
+            recs, words = ctypes.c_void_p(), ctypes.c_void_p()
+            nr, nw = ctypes.c_int64(0), ctypes.c_int64(0)
+            assert lib.mci_get_emitted(ctx, ctypes.byref(recs), ctypes.byref(nr), ctypes.byref(words), ctypes.byref(nw)) == 0
+            lists.append((recs.value, nr.value, words.value, nw.value))
+        assert sum(l[1] for l in lists) > 0
+        for r in (1, 2):
+            recs, nr, words, nw = lists[r]
+            if nr:
+                assert lib.mci_apply_masks(ctxs[0], recs, nr, words, nw) == 0
+        assert lib.mci_synchronize(ctxs[0]) == 0
+        full = O.interpolate(vol, **kw_cpu)
+        assert np.array_equal(outs[0].cpu().numpy().view(np.uint16), full)
+    finally:
+        for ctx in ctxs:
+            lib.mci_destroy(ctx)

@@ -127,15 +127,15 @@ def main():
     n_gpus = max(args.gpus, world)
 
     vol, _, cfg = make_config(args.workload, args.scale)
-    if rank > 0:  # every rank owns a different label volume of the same shape
-        from itkcontourinterpolation_b200.synthetic import ellipsoid_volume, sparsify
-        vol = sparsify(ellipsoid_volume(cfg["dims"], cfg["n_labels"], cfg["seed"] + 1000 * rank, cfg["semi_axes"]), cfg["nth"])
+    # N > 1: every rank interpolates its own copy of the same workload volume (independent label volumes, fixed work
+    # per GPU); sharding ONE volume over the ranks is tools/run_sharded.py
     nvox = int(vol.size)
     cores = os.cpu_count() or 1
     config = {"workload": "%s: %s" % (args.workload, WORKLOAD_DESC[args.workload]), "dims": list(cfg["dims"]),
               "labels": cfg["n_labels"], "annotated_every": list(cfg["nth"]), "axis": cfg["axis"],
               "use_distance_transform": bool(cfg["use_dt"]), "ball": bool(cfg["ball"]), "seed": cfg["seed"],
-              "l2_policy": "inputs larger than L2 (volume in+out = %d MB per step)" % (2 * vol.nbytes // 2 ** 20)}
+              "l2_policy": "inputs larger than L2 (volume in+out = %d MB per step)" % (2 * vol.nbytes // 2 ** 20),
+              "parallelism": "one label volume per GPU, no data-path collective" if world > 1 else "single GPU"}
 
     if args.impl == "reference":
         # the reference's own CPU implementation cannot be built here (needs ITK 5.4); its restatement (oracle/)

@@ -1243,7 +1243,7 @@ extern "C"
     }
     else
     {
-      const int nodeSmem = 100 * 1024;
+      const int nodeSmem = 100 * 1024; // two CTAs per SM: shapes up to ~4 200 words (e.g. 360 x 360 pixels) stay on chip
       const int nodeGrid = ctx->L.sms * 2;
       if (ctx->bigHistGrid < nodeGrid)
       {
@@ -1251,11 +1251,12 @@ extern "C"
         CK(cudaMemsetAsync(ctx->dBigHist.p, 0, size_t(nodeGrid) * 2 * 65536 * 4, s));
         ctx->bigHistGrid = nodeGrid;
       }
-      const u64 smemWords = (u64)nodeSmem / 4 - 2 * 2048;
+      const u64 smemWords = (u64)nodeSmem / 4;
+      const u64 needWords = maxNodeWords * 6 + 6 * (maxNodeWords / 32 + 1);
       u64 slabWords = 0;
-      if (maxNodeWords * 6 > smemWords)
+      if (needWords > smemWords)
       {
-        slabWords = maxNodeWords * 6;
+        slabWords = needWords;
         CK(ctx->dSlab.ensure(size_t(nodeGrid) * slabWords * 4));
       }
       for (int d = 0; d < maxDepth; ++d)

@@ -1249,790 +1249,4 @@ launch_make_roots(Launch & L, const RootJob * roots, int nroots, MaskRef * refs,
   L.post("k_make_roots");
 }
 
-// ================================================================================================
-// K6/K7/K8/K10  one Interpolate1to1 call per CTA  (X:556-793)
-//   translate + binarise + AND (X:570-666), median by exact squared distances (FindMedianImageDistances,
-//   X:405-516) or by constrained dilations (FindMedianImageDilations, X:340-388), clip + write with the
-//   max rule (X:679-764), spawn the two children (X:766-792).
-// ================================================================================================
-
-// exact squared Euclidean distance from pixel (x, r) to the nearest set bit of Xb, or `cap` if not below cap
-__device__ __forceinline__ int
-edt_sq(const uint32_t * Xb, int pitch, int xr0, int xr1, int x, int r, int cap)
-{
-  int best = cap;
-  int k = max(0, max(xr0 - r, r - xr1));
-  for (;; ++k)
-  {
-    int kk = k * k;
-    if (kk >= best)
-      break;
-    int r1 = r - k, r2 = r + k;
-    if (r1 < xr0 && r2 > xr1)
-      break;
-    if (r1 >= xr0 && r1 <= xr1)
-      best = min(best, kk + row_nearest_sq(Xb + (size_t)r1 * pitch, pitch, x, best - kk));
-    if (k > 0 && r2 <= xr1 && r2 >= xr0)
-      best = min(best, kk + row_nearest_sq(Xb + (size_t)r2 * pitch, pitch, x, best - kk));
-  }
-  return best;
-}
-
-#define MCI_NODE_THREADS 512
-#define MCI_SMALL_HIST 2048
-
-struct NodeShared
-{
-  int xr0, xr1;           // first / last row holding intersection pixels
-  int anyXor;
-  int bigUsed;            // a distance beyond the small histogram was met
-  int maxIdx;             // largest histogram index used (small: d2; big: bin)
-  int bx0, by0, bx1, by1; // bounding box of the median
-  unsigned long long midOff;
-  long long redA[MCI_NODE_THREADS / 32], redB[MCI_NODE_THREADS / 32];
-  long long bestDiff[MCI_NODE_THREADS / 32];
-  int bestIdx[MCI_NODE_THREADS / 32];
-  int result;
-  int cnt, chg;
-  int K[2];
-};
-
-// block-wide exclusive scan of two per-thread values (returns exclusive prefixes, totals via tot*)
-__device__ __forceinline__ void
-block_scan2(NodeShared & sh, long long a, long long b, long long & pa, long long & pb, long long & totA, long long & totB)
-{
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  long long sa = a, sb = b;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1)
-  {
-    long long ta = __shfl_up_sync(0xFFFFFFFFu, sa, o), tb = __shfl_up_sync(0xFFFFFFFFu, sb, o);
-    if (lane >= o)
-    {
-      sa += ta;
-      sb += tb;
-    }
-  }
-  __syncthreads();
-  if (lane == 31)
-  {
-    sh.redA[warp] = sa;
-    sh.redB[warp] = sb;
-  }
-  __syncthreads();
-  long long oa = 0, ob = 0;
-  totA = 0;
-  totB = 0;
-  for (int k = 0; k < MCI_NODE_THREADS / 32; ++k)
-  {
-    if (k < warp)
-    {
-      oa += sh.redA[k];
-      ob += sh.redB[k];
-    }
-    totA += sh.redA[k];
-    totB += sh.redB[k];
-  }
-  pa = oa + sa - a;
-  pb = ob + sb - b;
-}
-
-// block-wide arg-min with ties to the lowest index
-__device__ __forceinline__ int
-block_argmin(NodeShared & sh, long long diff, int idx)
-{
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-  {
-    long long od = __shfl_xor_sync(0xFFFFFFFFu, diff, o);
-    int oi = __shfl_xor_sync(0xFFFFFFFFu, idx, o);
-    if (od < diff || (od == diff && oi < idx))
-    {
-      diff = od;
-      idx = oi;
-    }
-  }
-  __syncthreads();
-  if (lane == 0)
-  {
-    sh.bestDiff[warp] = diff;
-    sh.bestIdx[warp] = idx;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0)
-  {
-    long long d = sh.bestDiff[0];
-    int i = sh.bestIdx[0];
-    for (int k = 1; k < MCI_NODE_THREADS / 32; ++k)
-      if (sh.bestDiff[k] < d || (sh.bestDiff[k] == d && sh.bestIdx[k] < i))
-      {
-        d = sh.bestDiff[k];
-        i = sh.bestIdx[k];
-      }
-    sh.result = i;
-  }
-  __syncthreads();
-  return sh.result;
-}
-
-// FindMedianImageDistances (X:405-516).  Xb = intersection, Ib = i-shape, Sb = i xor j on entry; on exit
-// Sb holds the median.  Histograms are indexed by d2 while 10*d2 fits the pixel type without wrapping
-// (bins are then 10*d2, so scanning d2 ascending visits exactly the bins where the score can change);
-// otherwise by the wrapped bin `PixelType(10 * d2)` of X:431 in the per-CTA global table.
-template <typename T>
-__device__ void
-median_distances(NodeShared & sh, uint32_t * Xb, const uint32_t * Ib, uint32_t * Sb, int h, int pitch, unsigned * smallHist,
-                 unsigned * bigHist, int * err)
-{
-  const int words = h * pitch;
-  const int tid = threadIdx.x;
-  for (int k = tid; k < 2 * MCI_SMALL_HIST; k += MCI_NODE_THREADS)
-    smallHist[k] = 0u;
-  if (tid == 0)
-  {
-    sh.bigUsed = 0;
-    sh.maxIdx = -1;
-  }
-  __syncthreads();
-  const int xr0 = sh.xr0, xr1 = sh.xr1;
-  constexpr int kSmall = PixTraits<T>::kNoWrapD2 < MCI_SMALL_HIST - 1 ? PixTraits<T>::kNoWrapD2 : MCI_SMALL_HIST - 1;
-  int localMaxSmall = -1, localMaxBig = -1;
-  for (int idx = tid; idx < words; idx += MCI_NODE_THREADS)
-  {
-    uint32_t s = Sb[idx];
-    if (!s)
-      continue;
-    const int r = idx / pitch, wi = idx % pitch;
-    const uint32_t iw = Ib[idx];
-    while (s)
-    {
-      int b = __ffs(s) - 1;
-      s &= s - 1;
-      int d2 = edt_sq(Xb, pitch, xr0, xr1, wi * 32 + b, r, 0x7FFFFFFF);
-      int side = (iw >> b) & 1u ? 0 : 1;
-      if (d2 <= kSmall)
-      {
-        atomicAdd(&smallHist[side * MCI_SMALL_HIST + d2], 1u);
-        localMaxSmall = max(localMaxSmall, d2);
-      }
-      else
-      {
-        int q = __float2int_rz(__fmul_rn(10.0f, (float)d2));
-        int bin;
-        if (sizeof(T) == 1)
-          bin = q & 0xFF;
-        else if (std::is_signed<T>::value)
-        {
-          short v = (short)q;
-          if (v < 0)
-          {
-            atomicMax(err, ERR_PIXELTYPE); // reference: negative index into the histogram (X:431-437)
-            v = 0;
-          }
-          bin = v;
-        }
-        else
-          bin = q & 0xFFFF;
-        atomicAdd(&bigHist[side * 65536 + bin], 1u);
-        localMaxBig = max(localMaxBig, bin);
-      }
-    }
-  }
-  if (localMaxBig >= 0)
-  {
-    sh.bigUsed = 1;
-    atomicMax(&sh.maxIdx, localMaxBig);
-  }
-  __syncthreads();
-  const int big = sh.bigUsed;
-  __syncthreads();
-  if (!big && localMaxSmall >= 0)
-    atomicMax(&sh.maxIdx, localMaxSmall);
-  if (big)
-  {
-    // fold the small histogram into the bin table (bin = 10*d2 below the wrap)
-    for (int k = tid; k < 2 * MCI_SMALL_HIST; k += MCI_NODE_THREADS)
-    {
-      unsigned c = smallHist[k];
-      if (c)
-      {
-        int side = k / MCI_SMALL_HIST, d2 = k % MCI_SMALL_HIST;
-        int bin = (sizeof(T) == 1) ? ((10 * d2) & 0xFF) : 10 * d2;
-        atomicAdd(&bigHist[side * 65536 + bin], c);
-        atomicMax(&sh.maxIdx, bin);
-      }
-    }
-  }
-  __syncthreads();
-  const int n = sh.maxIdx + 1; // histogram length (maxSize, X:462)
-  if (n <= 0)
-  {
-    // no pixel outside the intersection: the median is the intersection (X:463-466)
-    for (int idx = tid; idx < words; idx += MCI_NODE_THREADS)
-      Sb[idx] = Xb[idx];
-    __syncthreads();
-    return;
-  }
-  const unsigned * hi = big ? bigHist : smallHist;
-  const unsigned * hj = big ? bigHist + 65536 : smallHist + MCI_SMALL_HIST;
-  const int chunk = (n + MCI_NODE_THREADS - 1) / MCI_NODE_THREADS;
-  const int lo = min(n, tid * chunk), hiEnd = min(n, lo + chunk);
-  long long ci = 0, cj = 0;
-  for (int k = lo; k < hiEnd; ++k)
-  {
-    ci += hi[k];
-    cj += hj[k];
-  }
-  long long pi, pj, iTot, jTot;
-  block_scan2(sh, ci, cj, pi, pj, iTot, jTot);
-  long long bestDiff = 0x7FFFFFFFFFFFFFFFll;
-  int bestIdx = 0x7FFFFFFF;
-  long long si = pi, sj = pj;
-  for (int k = lo; k < hiEnd; ++k)
-  {
-    si += hi[k];
-    sj += hj[k];
-    long long a = llabs(iTot - si + sj), b = llabs(jTot - sj + si);
-    long long d = llabs(a - b);
-    if (d < bestDiff)
-    {
-      bestDiff = d;
-      bestIdx = k;
-    }
-  }
-  int best = block_argmin(sh, bestDiff, bestIdx);
-  // threshold sdf <= float(bestBin)/10 on integer d2 (X:497-508)
-  int thr;
-  if (big)
-    thr = (int)floorf(__fdiv_rn((float)best, 10.0f));
-  else
-    thr = best;
-  if (big)
-  {
-    for (int k = tid; k < n; k += MCI_NODE_THREADS)
-    {
-      bigHist[k] = 0u;
-      bigHist[65536 + k] = 0u;
-    }
-  }
-  for (int idx = tid; idx < words; idx += MCI_NODE_THREADS)
-  {
-    uint32_t s = Sb[idx];
-    uint32_t m = Xb[idx];
-    if (s)
-    {
-      const int r = idx / pitch, wi = idx % pitch;
-      while (s)
-      {
-        int b = __ffs(s) - 1;
-        s &= s - 1;
-        if (edt_sq(Xb, pitch, xr0, xr1, wi * 32 + b, r, thr + 1) <= thr)
-          m |= 1u << b;
-      }
-    }
-    Sb[idx] = m;
-  }
-  __syncthreads();
-}
-
-// Constrained dilation sequence from Xb inside maskb (GenerateDilationSequence X:322-338, Dilate1 X:253-320).
-// Runs until the set stops growing or `stopAt` images have been produced (stopAt < 0: run to the end and
-// record in hist[s] how many pixels outside `otherb` joined at step s).  Returns the sequence length K.
-// D / Dn are ping-pong buffers; on return *cur points at the last image.
-__device__ int
-dilation_sequence(NodeShared & sh, const uint32_t * Xb, const uint32_t * maskb, const uint32_t * otherb, uint32_t * D,
-                  uint32_t * Dn, int h, int pitch, bool ball, int stopAt, unsigned * hist, uint32_t ** cur)
-{
-  const int words = h * pitch;
-  const int tid = threadIdx.x;
-  for (int idx = tid; idx < words; idx += MCI_NODE_THREADS)
-    D[idx] = Xb[idx];
-  __syncthreads();
-  int steps = 0; // number of growth steps so far
-  uint32_t * a = D;
-  uint32_t * b = Dn;
-  unsigned settled = 0; // bit j: my j-th word is full (equals the mask) in both buffers: nothing left to do there
-  while (stopAt < 0 || steps < stopAt)
-  {
-    if (tid == 0)
-      sh.cnt = 0;
-    __syncthreads();
-    int changed = 0, cnt = 0;
-    int j = 0;
-    for (int idx = tid; idx < words; idx += MCI_NODE_THREADS, ++j)
-    {
-      if (j < 32 && ((settled >> j) & 1u))
-        continue;
-      const int r = idx / pitch, wi = idx % pitch;
-      uint32_t old = a[idx];
-      uint32_t m = maskb[idx];
-      uint32_t v = old;
-      if (m & ~old)
-        v = old | (dilate_word(a, h, pitch, r, wi, ball) & m);
-      else if (j < 32)
-        settled |= 1u << j; // after this copy both buffers hold the final word
-      b[idx] = v;
-      uint32_t diff = v & ~old;
-      if (diff)
-      {
-        changed = 1;
-        cnt += __popc(diff & ~otherb[idx]);
-      }
-    }
-    if (cnt)
-      atomicAdd(&sh.cnt, cnt);
-    changed = __syncthreads_or(changed);
-    if (!changed)
-      break;
-    ++steps;
-    if (stopAt < 0 && tid == 0 && steps < 65536)
-      hist[steps] = (unsigned)sh.cnt;
-    uint32_t * t = a;
-    a = b;
-    b = t;
-    __syncthreads();
-  }
-  *cur = a;
-  return steps > 0 ? steps : 1; // [D1] alone when nothing grows (X:328-336)
-}
-
-// FindMedianImageDilations (X:340-388) without storing the sequences: only how many pixels of i\j (j\i)
-// join at each step matters for the scores, because intersection pixels are in every image.
-__device__ void
-median_dilations(NodeShared & sh, const uint32_t * Xb, const uint32_t * Ib, const uint32_t * Jb, uint32_t * Sb, uint32_t * D,
-                 uint32_t * Dn, int h, int pitch, bool ball, unsigned * bigHist, int * err)
-{
-  const int words = h * pitch;
-  const int tid = threadIdx.x;
-  unsigned * hI = bigHist;         // hI[s], s = 1..Ki : pixels of i\j joining at step s
-  unsigned * hJ = bigHist + 65536; // same for j\i
-  uint32_t * cur;
-  int Ki = dilation_sequence(sh, Xb, Ib, Jb, D, Dn, h, pitch, ball, -1, hI, &cur);
-  __syncthreads();
-  int Kj = dilation_sequence(sh, Xb, Jb, Ib, D, Dn, h, pitch, ball, -1, hJ, &cur);
-  __syncthreads();
-  if (Ki > 65535 || Kj > 65535)
-  {
-    if (tid == 0)
-      atomicMax(err, ERR_SCRATCH);
-    Ki = min(Ki, 65535);
-    Kj = min(Kj, 65535);
-  }
-  // totals of i\j and j\i (pixels a sequence never reaches still count in the symmetric differences)
-  long long ni = 0, nj = 0;
-  for (int idx = tid; idx < words; idx += MCI_NODE_THREADS)
-  {
-    ni += __popc(Ib[idx] & ~Jb[idx]);
-    nj += __popc(Jb[idx] & ~Ib[idx]);
-  }
-  long long d0, d1, Ni, Nj;
-  block_scan2(sh, ni, nj, d0, d1, Ni, Nj);
-  // inclusive prefix sums of the step histograms, in place (thread-chunked)
-  const int n = max(Ki, Kj) + 1;
-  {
-    const int chunk = (n + MCI_NODE_THREADS - 1) / MCI_NODE_THREADS;
-    const int lo = min(n, tid * chunk), hiEnd = min(n, lo + chunk);
-    long long ci = 0, cj = 0;
-    for (int k = lo; k < hiEnd; ++k)
-    {
-      ci += (k >= 1 && k <= Ki) ? hI[k] : 0u;
-      cj += (k >= 1 && k <= Kj) ? hJ[k] : 0u;
-    }
-    long long pi, pj, ti, tj;
-    block_scan2(sh, ci, cj, pi, pj, ti, tj);
-    long long si = pi, sj = pj;
-    for (int k = lo; k < hiEnd; ++k)
-    {
-      si += (k >= 1 && k <= Ki) ? hI[k] : 0u;
-      sj += (k >= 1 && k <= Kj) ? hJ[k] : 0u;
-      hI[k] = (unsigned)si;
-      hJ[k] = (unsigned)sj;
-    }
-  }
-  __syncthreads();
-  // seq[x] (X:349-371): the i-sequence is reversed BEFORE the swap that makes iSeq the longer one
-  const bool swapped = Ki < Kj;
-  const int L = swapped ? Kj : Ki;
-  const float ratio = __fdiv_rn((float)(swapped ? Ki : Kj), (float)L);
-  long long bestDiff = 0x7FFFFFFFFFFFFFFFll;
-  int bestIdx = 0x7FFFFFFF;
-  for (int x = tid; x < L; x += MCI_NODE_THREADS)
-  {
-    unsigned xj = __float2uint_rz(__fmul_rn(ratio, (float)x));
-    int si, sj; // sequence images D^i_si and D^j_sj forming seq[x]
-    if (!swapped)
-    {
-      si = Ki - x;
-      sj = (int)xj + 1;
-    }
-    else
-    {
-      sj = x + 1;
-      si = Ki - (int)xj;
-    }
-    long long ci = hI[min(si, Ki)], cj = hJ[min(sj, Kj)];
-    long long iS = cj + (Ni - ci);
-    long long jS = ci + (Nj - cj);
-    long long d = llabs(iS - jS);
-    if (d < bestDiff)
-    {
-      bestDiff = d;
-      bestIdx = x;
-    }
-  }
-  int bx = block_argmin(sh, bestDiff, bestIdx);
-  // (the reference starts from min = number of region pixels with a strict "<": any x beats it)
-  int si, sj;
-  {
-    unsigned xj = __float2uint_rz(__fmul_rn(ratio, (float)bx));
-    if (!swapped)
-    {
-      si = Ki - bx;
-      sj = (int)xj + 1;
-    }
-    else
-    {
-      sj = bx + 1;
-      si = Ki - (int)xj;
-    }
-  }
-  for (int k = tid; k < n; k += MCI_NODE_THREADS)
-  {
-    hI[k] = 0u;
-    hJ[k] = 0u;
-  }
-  __syncthreads();
-  // rebuild the chosen image: D^i_si | D^j_sj
-  dilation_sequence(sh, Xb, Ib, Jb, D, Dn, h, pitch, ball, si, nullptr, &cur);
-  __syncthreads();
-  for (int idx = tid; idx < words; idx += MCI_NODE_THREADS)
-    Sb[idx] = cur[idx];
-  __syncthreads();
-  dilation_sequence(sh, Xb, Jb, Ib, D, Dn, h, pitch, ball, sj, nullptr, &cur);
-  __syncthreads();
-  for (int idx = tid; idx < words; idx += MCI_NODE_THREADS)
-    Sb[idx] |= cur[idx];
-  __syncthreads();
-}
-
-template <typename T>
-__global__ void __launch_bounds__(MCI_NODE_THREADS, 2)
-k_nodes(const Node * __restrict__ nodes, const int * __restrict__ count, Node * next, int * nextCount, int nextCap,
-        uint32_t * arena, unsigned long long * arenaTop, unsigned long long arenaCap, const T * __restrict__ in, T * out,
-        long long VX, long long VY, long long VZ, int useDT, int ball, unsigned * bigHistAll, uint32_t * slabAll,
-        unsigned long long slabWords, int smemWords, EmitRec * emit, int * emitCount, int emitCap, unsigned long long emitBase,
-        int * err)
-{
-  extern __shared__ uint32_t smem[];
-  __shared__ NodeShared sh;
-  unsigned * smallHist = smem;
-  uint32_t * smemArr = smem + 2 * MCI_SMALL_HIST;
-  unsigned * bigHist = bigHistAll + (size_t)blockIdx.x * 2 * 65536;
-  const int tid = threadIdx.x;
-  const int nNodes = *count;
-  for (int nidx = blockIdx.x; nidx < nNodes; nidx += gridDim.x)
-  {
-    const Node nd = nodes[nidx];
-    // ---- translation halving with carry (X:570-608)
-    int t[2] = { nd.tx, nd.ty }, iT[2], jT[2];
-    bool carry = false;
-#pragma unroll
-    for (int d = 0; d < 2; ++d)
-    {
-      if (!carry)
-      {
-        iT[d] = t[d] / 2;
-        carry = (t[d] % 2) != 0;
-      }
-      else if (t[d] % 2 == 0)
-        iT[d] = t[d] / 2;
-      else
-      {
-        iT[d] = t[d] > 0 ? t[d] / 2 + 1 : t[d] / 2 - 1;
-        carry = false;
-      }
-      jT[d] = iT[d] - t[d];
-    }
-    const int mid = (nd.i + nd.j + (carry ? 1 : 0)) / 2;
-    // ---- working region: union of the two translated shapes' regions
-    const int ux0 = min(nd.A.x0 + iT[0], nd.B.x0 + jT[0]), uy0 = min(nd.A.y0 + iT[1], nd.B.y0 + jT[1]);
-    const int ux1 = max(nd.A.x0 + nd.A.w + iT[0], nd.B.x0 + nd.B.w + jT[0]);
-    const int uy1 = max(nd.A.y0 + nd.A.h + iT[1], nd.B.y0 + nd.B.h + jT[1]);
-    const int w = ux1 - ux0, h = uy1 - uy0;
-    const int pitch = (w + 31) >> 5;
-    const int words = h * pitch;
-    const int nArr = useDT ? 3 : 6;
-    uint32_t * base;
-    if ((long long)words * nArr <= smemWords)
-      base = smemArr;
-    else if ((unsigned long long)words * nArr <= slabWords)
-      base = slabAll + (size_t)blockIdx.x * slabWords;
-    else
-    {
-      if (tid == 0)
-        atomicMax(err, ERR_SCRATCH);
-      continue;
-    }
-    uint32_t * Xb = base;
-    uint32_t * Ib = base + words;
-    uint32_t * Sb = base + 2 * (size_t)words;
-    uint32_t * Jb = useDT ? nullptr : base + 3 * (size_t)words;
-    uint32_t * D = useDT ? nullptr : base + 4 * (size_t)words;
-    uint32_t * Dn = useDT ? nullptr : base + 5 * (size_t)words;
-    __syncthreads(); // previous node done with shared state
-    if (tid == 0)
-    {
-      sh.xr0 = 0x7FFFFFFF;
-      sh.xr1 = -1;
-      sh.anyXor = 0;
-      sh.bx0 = sh.by0 = 0x7FFFFFFF;
-      sh.bx1 = sh.by1 = -0x7FFFFFFF;
-    }
-    __syncthreads();
-    // ---- translate, binarise, intersect (X:610-666)
-    {
-      int r0 = 0x7FFFFFFF, r1 = -1;
-      for (int idx = tid; idx < words; idx += MCI_NODE_THREADS)
-      {
-        const int r = idx / pitch, wi = idx % pitch;
-        const int y = uy0 + r, x = ux0 + 32 * wi;
-        uint32_t a = mask_word(arena, nd.A, y - iT[1], x - iT[0]);
-        uint32_t b = mask_word(arena, nd.B, y - jT[1], x - jT[0]);
-        Xb[idx] = a & b;
-        Ib[idx] = a;
-        Sb[idx] = a ^ b;
-        if (Jb)
-          Jb[idx] = b;
-        if (a & b)
-        {
-          r0 = min(r0, r);
-          r1 = max(r1, r);
-        }
-      }
-      if (r1 >= 0)
-      {
-        atomicMin(&sh.xr0, r0);
-        atomicMax(&sh.xr1, r1);
-      }
-    }
-    __syncthreads();
-    if (sh.xr1 < 0)
-      continue; // empty intersection: both median finders return an empty image, nothing below can be written
-    // ---- median (X:668-676)
-    if (useDT)
-      median_distances<T>(sh, Xb, Ib, Sb, h, pitch, smallHist, bigHist, err);
-    else
-      median_dilations(sh, Xb, Ib, Jb, Sb, D, Dn, h, pitch, ball != 0, bigHist, err);
-    // ---- clip to the slice (X:679-712) and crop to the median's bounding box
-    const int d0 = nd.axis == 0 ? 1 : 0, d1 = nd.axis == 2 ? 1 : 2;
-    const long long dimsV[3] = { VX, VY, VZ };
-    const int SU = (int)dimsV[d0], SV = (int)dimsV[d1];
-    {
-      int bx0 = 0x7FFFFFFF, bx1 = -0x7FFFFFFF, by0 = 0x7FFFFFFF, by1 = -0x7FFFFFFF;
-      for (int idx = tid; idx < words; idx += MCI_NODE_THREADS)
-      {
-        const int r = idx / pitch, wi = idx % pitch;
-        const int y = uy0 + r;
-        uint32_t m = Sb[idx];
-        if (!m || y < 0 || y >= SV)
-          continue;
-        // clip columns
-        int xa = ux0 + 32 * wi;
-        if (xa < 0)
-          m = (xa <= -32) ? 0u : (m & (0xFFFFFFFFu << (-xa)));
-        if (xa + 32 > SU)
-          m = (xa >= SU) ? 0u : (m & (0xFFFFFFFFu >> (xa + 32 - SU)));
-        if (!m)
-          continue;
-        bx0 = min(bx0, xa + __ffs(m) - 1);
-        bx1 = max(bx1, xa + 31 - __clz(m));
-        by0 = min(by0, y);
-        by1 = max(by1, y);
-      }
-      if (by1 >= by0)
-      {
-        atomicMin(&sh.bx0, bx0);
-        atomicMax(&sh.bx1, bx1);
-        atomicMin(&sh.by0, by0);
-        atomicMax(&sh.by1, by1);
-      }
-    }
-    __syncthreads();
-    if (sh.by1 < sh.by0)
-      continue; // nothing inside the image
-    MaskRef M;
-    M.x0 = sh.bx0;
-    M.y0 = sh.by0;
-    M.w = sh.bx1 - sh.bx0 + 1;
-    M.h = sh.by1 - sh.by0 + 1;
-    M.pitch = (M.w + 31) >> 5;
-    M.pad = 0;
-    const int mwords = M.h * M.pitch;
-    if (tid == 0)
-      sh.midOff = atomicAdd(arenaTop, (unsigned long long)mwords);
-    __syncthreads();
-    M.off = sh.midOff;
-    if (M.off + (unsigned long long)mwords > arenaCap)
-    {
-      if (tid == 0)
-        atomicMax(err, ERR_ARENA);
-      continue;
-    }
-    if (emit && tid == 0)
-    {
-      const int e = atomicAdd(emitCount, 1);
-      if (e < emitCap)
-      {
-        EmitRec r;
-        r.M = M;
-        r.M.off = M.off - emitBase;
-        r.axis = nd.axis;
-        r.label = nd.label;
-        r.mid = mid;
-        r.pad = 0;
-        emit[e] = r;
-      }
-      else
-        atomicMax(err, ERR_NODE_LIST);
-    }
-    // ---- store the mid shape and write it into the volume with the max rule (X:714-764)
-    {
-      const int lane = tid & 31, warp = tid >> 5;
-      const T label = (T)nd.label;
-      long long su, sv;
-      unsigned long long vbase;
-      if (nd.axis == 2)
-      {
-        su = 1;
-        sv = VX;
-        vbase = (unsigned long long)mid * VX * VY;
-      }
-      else if (nd.axis == 1)
-      {
-        su = 1;
-        sv = VX * VY;
-        vbase = (unsigned long long)mid * VX;
-      }
-      else
-      {
-        su = VX;
-        sv = VX * VY;
-        vbase = (unsigned long long)mid;
-      }
-      for (int cell = warp; cell < mwords; cell += MCI_NODE_THREADS / 32)
-      {
-        const int r = cell / M.pitch, wi = cell % M.pitch;
-        const int y = M.y0 + r, x = M.x0 + 32 * wi;
-        // 32 bits of the median starting at slice column x
-        const uint32_t * row = Sb + (size_t)(y - uy0) * pitch;
-        int rx = x - ux0; // >= 0
-        int sw = rx >> 5, shf = rx & 31;
-        uint32_t lo = row[sw];
-        uint32_t hi = sw + 1 < pitch ? row[sw + 1] : 0u;
-        uint32_t m = __funnelshift_r(lo, hi, shf);
-        int valid = M.w - 32 * wi;
-        if (valid < 32)
-          m &= (1u << valid) - 1u;
-        if (lane == 0)
-          arena[M.off + cell] = m;
-        if ((m >> lane) & 1u)
-        {
-          unsigned long long a = vbase + (unsigned long long)((long long)(x + lane) * su + (long long)y * sv);
-          if (in[a] == 0)
-            atomic_max_pixel(out + a, label);
-        }
-      }
-    }
-    // ---- children (X:766-792)
-    if (tid == 0 && abs(nd.i - nd.j) > 2)
-    {
-      const bool first = abs(nd.i - mid) > 1, second = abs(nd.j - mid) > 1;
-      int nnew = (first ? 1 : 0) + (second ? 1 : 0);
-      if (nnew)
-      {
-        int pos = atomicAdd(nextCount, nnew);
-        if (pos + nnew > nextCap)
-          atomicMax(err, ERR_NODE_LIST);
-        else
-        {
-          if (first)
-          {
-            Node c;
-            c.A = nd.A;
-            c.B = M;
-            c.tx = iT[0];
-            c.ty = iT[1];
-            c.i = nd.i;
-            c.j = mid;
-            c.axis = nd.axis;
-            c.label = nd.label;
-            next[pos++] = c;
-          }
-          if (second)
-          {
-            Node c;
-            c.A = nd.B;
-            c.B = M;
-            c.tx = jT[0];
-            c.ty = jT[1];
-            c.i = nd.j;
-            c.j = mid;
-            c.axis = nd.axis;
-            c.label = nd.label;
-            next[pos++] = c;
-          }
-        }
-      }
-    }
-  }
-}
-
-template <typename T>
-static void
-launch_nodes_t(Launch & L, const Node * nodes, const int * count, int maxNodes, Node * next, int * nextCount, int nextCap,
-               uint32_t * arena, unsigned long long * arenaTop, unsigned long long arenaCap, const void * in, void * out,
-               const long long dims[3], int useDT, int ball, unsigned * bigHist, uint32_t * slab, unsigned long long slabWords,
-               int grid, int smemBytes, EmitRec * emit, int * emitCount, int emitCap, unsigned long long emitBase, int * err)
-{
-  static bool attr = false;
-  if (!attr)
-  {
-    cudaFuncSetAttribute(k_nodes<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.maxSmem - 1024);
-    attr = true;
-  }
-  int g = std::max(1, std::min(grid, maxNodes));
-  int smemWords = smemBytes / 4 - 2 * MCI_SMALL_HIST;
-  L.pre("k_nodes");
-  k_nodes<T><<<g, MCI_NODE_THREADS, smemBytes, L.stream>>>(nodes, count, next, nextCount, nextCap, arena, arenaTop, arenaCap,
-                                                          (const T *)in, (T *)out, dims[0], dims[1], dims[2], useDT, ball,
-                                                          bigHist, slab, slabWords, smemWords, emit, emitCount, emitCap, emitBase, err);
-  L.post("k_nodes");
-}
-
-void
-launch_nodes(Launch & L, int ptype, const Node * nodes, const int * count, int maxNodes, Node * next, int * nextCount,
-             int nextCap, uint32_t * arena, unsigned long long * arenaTop, unsigned long long arenaCap, const void * in,
-             void * out, const long long dims[3], int useDT, int ball, unsigned * bigHist, uint32_t * slab,
-             unsigned long long slabWords, int grid, int smemBytes, EmitRec * emit, int * emitCount, int emitCap,
-             unsigned long long emitBase, int * err)
-{
-  if (maxNodes <= 0)
-    return;
-  switch (ptype)
-  {
-    case MCI_U8:
-      launch_nodes_t<uint8_t>(L, nodes, count, maxNodes, next, nextCount, nextCap, arena, arenaTop, arenaCap, in, out, dims,
-                              useDT, ball, bigHist, slab, slabWords, grid, smemBytes, emit, emitCount, emitCap, emitBase, err);
-      break;
-    case MCI_U16:
-      launch_nodes_t<uint16_t>(L, nodes, count, maxNodes, next, nextCount, nextCap, arena, arenaTop, arenaCap, in, out, dims,
-                               useDT, ball, bigHist, slab, slabWords, grid, smemBytes, emit, emitCount, emitCap, emitBase, err);
-      break;
-    default:
-      launch_nodes_t<int16_t>(L, nodes, count, maxNodes, next, nextCount, nextCap, arena, arenaTop, arenaCap, in, out, dims,
-                              useDT, ball, bigHist, slab, slabWords, grid, smemBytes, emit, emitCount, emitCap, emitBase, err);
-  }
-}
-
 } // namespace mci

@@ -127,7 +127,7 @@ struct mci_ctx
   int nPairs = 0, capPairs = 0;
   // interpolation
   DBuf dJobBlob, dArena, dScratch, dBigHist, dSlab, dNodes, dLevelCounts, dArenaTop, dTrans;
-  DBuf dWork, dItems, dLevelScratch, dHist, dDtBig, dDtCounters, dEmit;
+  DBuf dWork, dItems, dLevelScratch, dHist, dDtBig, dDtCounters, dEmit, dArrival;
   unsigned long long emitBase = 0; // arena word where the mid shapes of the last run start
   int emitCap = 0;
   bool haveEmit = false;
@@ -256,7 +256,7 @@ extern "C"
                       &ctx->dPairs,    &ctx->dJobBlob,  &ctx->dArena,   &ctx->dScratch,   &ctx->dBigHist, &ctx->dSlab,
                       &ctx->dNodes,    &ctx->dLevelCounts, &ctx->dArenaTop, &ctx->dTrans,
                       &ctx->dWork, &ctx->dItems, &ctx->dLevelScratch, &ctx->dHist, &ctx->dDtBig, &ctx->dDtCounters,
-                      &ctx->dChunkBits, &ctx->dEmit };
+                      &ctx->dChunkBits, &ctx->dEmit, &ctx->dArrival };
     for (DBuf * b : bufs)
       b->release();
     recycle_events(ctx);
@@ -1259,6 +1259,9 @@ extern "C"
         slabWords = needWords;
         CK(ctx->dSlab.ensure(size_t(nodeGrid) * slabWords * 4));
       }
+      // arrival-step maps of the two dilation sequences, one pair per resident CTA (capped: larger shapes re-run)
+      const u64 arrPixels = std::min<u64>(maxNodeWords * 32, 4u << 20);
+      CK(ctx->dArrival.ensure(size_t(nodeGrid) * 2 * arrPixels * sizeof(unsigned short)));
       for (int d = 0; d < maxDepth; ++d)
       {
         Node * cur = dNodes + off;
@@ -1266,10 +1269,14 @@ extern "C"
         int nextCap = d + 1 < maxDepth ? (int)levelCap[d + 1] : 0;
         launch_nodes(ctx->L, ctx->ptype, cur, dCounts + d, (int)levelCap[d], nxt, dCounts + d + 1, nextCap,
                      (uint32_t *)ctx->dArena.p, (unsigned long long *)ctx->dArenaTop.p, arenaCap, ctx->dIn, ctx->dOut, ctx->dims,
-                     0, prm->use_ball, (unsigned *)ctx->dBigHist.p, (uint32_t *)ctx->dSlab.p, slabWords, nodeGrid, nodeSmem,
+                     0, prm->use_ball, (unsigned *)ctx->dBigHist.p, (uint32_t *)ctx->dSlab.p, slabWords,
+                     (unsigned short *)ctx->dArrival.p, arrPixels, nodeGrid, nodeSmem,
                      dEmitRecs, dEmitCount, ctx->emitCap, ctx->emitBase, ctx->dErr);
         off += levelCap[d];
       }
+      // the node kernel only stores the mid shapes; their volume writes (X:743-764) happen here in one grid-wide pass
+      launch_apply_masks(ctx->L, ctx->ptype, dEmitRecs, ctx->emitCap, dEmitCount, (uint32_t *)ctx->dArena.p + ctx->emitBase, ctx->dIn,
+                         ctx->dOut, ctx->dims);
     }
     CK(cudaGetLastError());
     return MCI_OK;
@@ -1341,8 +1348,8 @@ extern "C"
       return MCI_ERR_ARG;
     (void)n_words;
     CK(cudaSetDevice(ctx->device));
-    launch_apply_masks(ctx->L, ctx->ptype, (const EmitRec *)recs_dev, (int)n_recs, (const uint32_t *)words_dev, ctx->dIn, ctx->dOut,
-                       ctx->dims);
+    launch_apply_masks(ctx->L, ctx->ptype, (const EmitRec *)recs_dev, (int)n_recs, nullptr, (const uint32_t *)words_dev, ctx->dIn,
+                       ctx->dOut, ctx->dims);
     return MCI_OK;
   }
 

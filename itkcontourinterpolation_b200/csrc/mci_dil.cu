@@ -28,6 +28,7 @@ struct DilShared
   int bestI[DIL_THREADS / 32];
   int result;
   unsigned flag[3]; // rotating "something changed" words: bit 0 = i sequence, bit 1 = j sequence
+  unsigned cntI[3], cntJ[3]; // rotating per-step counts of pixels that joined outside the other shape
 };
 
 // wakes word idx and its two row neighbours (a superset of what can be reached is always safe)
@@ -48,7 +49,7 @@ dil_wake_row3(uint32_t * wake, int idx, int words)
 // One sequence's share of one step for word idx: returns true if the word changed.
 __device__ __forceinline__ bool
 dil_step_word(const uint32_t * cur, uint32_t * nxt, const uint32_t * mask, const uint32_t * other, uint32_t * wakeNxt, int idx, int h,
-              int pitch, int words, bool ball, unsigned * histSlot)
+              int pitch, int words, bool ball, unsigned * histSlot, unsigned short * arrival, unsigned short step)
 {
   const int r = idx / pitch, wi = idx - r * pitch;
   const uint32_t old = cur[idx];
@@ -61,10 +62,17 @@ dil_step_word(const uint32_t * cur, uint32_t * nxt, const uint32_t * mask, const
   if (!diff)
     return false;
   if (histSlot)
+    *histSlot += (unsigned)__popc(diff & ~other[idx]); // per-thread counter, reduced once per step
+  if (arrival)
   {
-    const int c = __popc(diff & ~other[idx]);
-    if (c)
-      atomicAdd(histSlot, (unsigned)c);
+    // the step at which each pixel joins: lets the chosen image be rebuilt by thresholding instead of re-running
+    uint32_t m2 = diff;
+    while (m2)
+    {
+      const int bpos = __ffs(m2) - 1;
+      m2 &= m2 - 1;
+      arrival[(size_t)idx * 32 + bpos] = step;
+    }
   }
   if (r > 0)
     dil_wake_row3(wakeNxt, idx - pitch, words);
@@ -80,8 +88,8 @@ dil_step_word(const uint32_t * cur, uint32_t * nxt, const uint32_t * mask, const
 // hold the last images; K = number of images of each sequence.
 __device__ void
 dil_run_pair(DilShared & sh, const uint32_t * Ib, const uint32_t * Jb, uint32_t * Di0, uint32_t * Di1, uint32_t * Dj0, uint32_t * Dj1,
-             uint32_t * wake /* 6 bitmaps */, int h, int pitch, bool ball, int stopI, int stopJ, unsigned * hI, unsigned * hJ, int & Ki,
-             int & Kj, int & ci, int & cj)
+             uint32_t * wake /* 6 bitmaps */, int h, int pitch, bool ball, int stopI, int stopJ, unsigned * hI, unsigned * hJ,
+             unsigned short * arrI, unsigned short * arrJ, int & Ki, int & Kj, int & ci, int & cj)
 {
   const int words = h * pitch, nbw = (words + 31) >> 5;
   const int tid = threadIdx.x;
@@ -104,7 +112,11 @@ dil_run_pair(DilShared & sh, const uint32_t * Ib, const uint32_t * Jb, uint32_t 
     wake[5 * nbw + k] = 0u;
   }
   if (tid == 0)
+  {
     sh.flag[0] = sh.flag[1] = sh.flag[2] = 0u;
+    sh.cntI[0] = sh.cntI[1] = sh.cntI[2] = 0u;
+    sh.cntJ[0] = sh.cntJ[1] = sh.cntJ[2] = 0u;
+  }
   __syncthreads();
   int stepsI = 0, stepsJ = 0;
   bool runI = stopI != 0, runJ = stopJ != 0;
@@ -118,8 +130,9 @@ dil_run_pair(DilShared & sh, const uint32_t * Ib, const uint32_t * Jb, uint32_t 
     uint32_t * nxtI = ci ? Di0 : Di1;
     uint32_t * curJ = cj ? Dj1 : Dj0;
     uint32_t * nxtJ = cj ? Dj0 : Dj1;
-    unsigned * slotHI = (hI && stepsI + 1 < DIL_STEPS) ? hI + stepsI + 1 : nullptr;
-    unsigned * slotHJ = (hJ && stepsJ + 1 < DIL_STEPS) ? hJ + stepsJ + 1 : nullptr;
+    unsigned myCntI = 0, myCntJ = 0;
+    unsigned * slotHI = hI ? &myCntI : nullptr;
+    unsigned * slotHJ = hJ ? &myCntJ : nullptr;
     // which of my words are awake: independent loads first (one bitmap word serves a whole warp), then only
     // the awake ones are visited -- dormant words cost no dependent shared-memory round trip
     unsigned awI = 0, awJ = 0;
@@ -137,23 +150,25 @@ dil_run_pair(DilShared & sh, const uint32_t * Ib, const uint32_t * Jb, uint32_t 
     {
       const int j = __ffs(awI) - 1;
       awI &= awI - 1;
-      if (dil_step_word(curI, nxtI, Ib, Jb, wake + slotN * nbw, tid + j * DIL_THREADS, h, pitch, words, ball, slotHI))
+      if (dil_step_word(curI, nxtI, Ib, Jb, wake + slotN * nbw, tid + j * DIL_THREADS, h, pitch, words, ball, slotHI, arrI,
+                        (unsigned short)(stepsI + 1)))
         mine |= 1u;
     }
     while (awJ)
     {
       const int j = __ffs(awJ) - 1;
       awJ &= awJ - 1;
-      if (dil_step_word(curJ, nxtJ, Jb, Ib, wake + (3 + slotN) * nbw, tid + j * DIL_THREADS, h, pitch, words, ball, slotHJ))
+      if (dil_step_word(curJ, nxtJ, Jb, Ib, wake + (3 + slotN) * nbw, tid + j * DIL_THREADS, h, pitch, words, ball, slotHJ, arrJ,
+                        (unsigned short)(stepsJ + 1)))
         mine |= 2u;
     }
     for (int idx = tid + 32 * DIL_THREADS; idx < words; idx += DIL_THREADS) // shapes beyond 32 words per thread
     {
       if (runI && ((wake[slot * nbw + (idx >> 5)] >> (idx & 31)) & 1u) &&
-          dil_step_word(curI, nxtI, Ib, Jb, wake + slotN * nbw, idx, h, pitch, words, ball, slotHI))
+          dil_step_word(curI, nxtI, Ib, Jb, wake + slotN * nbw, idx, h, pitch, words, ball, slotHI, arrI, (unsigned short)(stepsI + 1)))
         mine |= 1u;
       if (runJ && ((wake[(3 + slot) * nbw + (idx >> 5)] >> (idx & 31)) & 1u) &&
-          dil_step_word(curJ, nxtJ, Jb, Ib, wake + (3 + slotN) * nbw, idx, h, pitch, words, ball, slotHJ))
+          dil_step_word(curJ, nxtJ, Jb, Ib, wake + (3 + slotN) * nbw, idx, h, pitch, words, ball, slotHJ, arrJ, (unsigned short)(stepsJ + 1)))
         mine |= 2u;
     }
     for (int k = tid; k < nbw; k += DIL_THREADS)
@@ -163,10 +178,25 @@ dil_run_pair(DilShared & sh, const uint32_t * Ib, const uint32_t * Jb, uint32_t 
     }
     if (mine)
       atomicOr(&sh.flag[slot], mine);
+    if (myCntI)
+      atomicAdd(&sh.cntI[slot], myCntI);
+    if (myCntJ)
+      atomicAdd(&sh.cntJ[slot], myCntJ);
     if (tid == 0)
+    {
       sh.flag[slotN] = 0u;
+      sh.cntI[slotN] = 0u;
+      sh.cntJ[slotN] = 0u;
+    }
     __syncthreads();
     const unsigned f = sh.flag[slot];
+    if (tid == 0)
+    {
+      if (hI && runI && (f & 1u) && stepsI + 1 < DIL_STEPS)
+        hI[stepsI + 1] = sh.cntI[slot];
+      if (hJ && runJ && (f & 2u) && stepsJ + 1 < DIL_STEPS)
+        hJ[stepsJ + 1] = sh.cntJ[slot];
+    }
     if (runI)
     {
       if (f & 1u)
@@ -279,7 +309,7 @@ __global__ void __launch_bounds__(DIL_THREADS, 2)
 k_dil_nodes(const Node * __restrict__ nodes, const int * __restrict__ count, Node * next, int * nextCount, int nextCap, uint32_t * arena,
             unsigned long long * arenaTop, unsigned long long arenaCap, const T * __restrict__ in, T * out, long long VX,
             long long VY, long long VZ, int ball, unsigned * stepHistAll, uint32_t * slabAll, unsigned long long slabWords,
-            int smemWords, EmitRec * emit, int * emitCount, int emitCap, unsigned long long emitBase, int * err)
+            unsigned short * arrAll, unsigned long long arrPixels, int smemWords, EmitRec * emit, int * emitCount, int emitCap, unsigned long long emitBase, int * err)
 {
   extern __shared__ uint32_t smem[];
   __shared__ DilShared sh;
@@ -337,6 +367,10 @@ k_dil_nodes(const Node * __restrict__ nodes, const int * __restrict__ count, Nod
     uint32_t * Dj0 = base + 4 * (size_t)words;
     uint32_t * Dj1 = base + 5 * (size_t)words;
     uint32_t * wake = base + 6 * (size_t)words;
+    // arrival-step maps (global, one pair per CTA); shapes too large for them fall back to re-running the sequences
+    const bool haveArr = arrAll != nullptr && (unsigned long long)words * 32 <= arrPixels;
+    unsigned short * arrI = haveArr ? arrAll + (size_t)blockIdx.x * 2 * arrPixels : nullptr;
+    unsigned short * arrJ = haveArr ? arrI + arrPixels : nullptr;
     __syncthreads(); // previous node done with shared state
     if (tid == 0)
     {
@@ -366,7 +400,7 @@ k_dil_nodes(const Node * __restrict__ nodes, const int * __restrict__ count, Nod
       continue; // empty intersection: the median is empty, nothing below can be written
     // ---- FindMedianImageDilations (X:340-388)
     int Ki, Kj, ci, cj;
-    dil_run_pair(sh, Ib, Jb, Di0, Di1, Dj0, Dj1, wake, h, pitch, ball != 0, -1, -1, hI, hJ, Ki, Kj, ci, cj);
+    dil_run_pair(sh, Ib, Jb, Di0, Di1, Dj0, Dj1, wake, h, pitch, ball != 0, -1, -1, hI, hJ, arrI, arrJ, Ki, Kj, ci, cj);
     if (Ki >= DIL_STEPS || Kj >= DIL_STEPS)
     {
       if (tid == 0)
@@ -440,10 +474,41 @@ k_dil_nodes(const Node * __restrict__ nodes, const int * __restrict__ count, Nod
     __syncthreads();
     // ---- rebuild the chosen image: D^i_si | D^j_sj (images are numbered from 1; image s = s growth steps,
     // image 1 of a sequence that never grows is the intersection itself)
-    int k1, k2;
-    dil_run_pair(sh, Ib, Jb, Di0, Di1, Dj0, Dj1, wake, h, pitch, ball != 0, si, sj, nullptr, nullptr, k1, k2, ci, cj);
-    uint32_t * Sb = ci ? Di0 : Di1; // the i buffer that is NOT current receives the median
+    uint32_t * Sb;
+    if (haveArr)
     {
+      // threshold the arrival steps: pixel p of the final i image belongs to D^i_si iff it is an intersection pixel
+      // or joined at a step <= si (same for j)
+      const uint32_t * fi = ci ? Di1 : Di0;
+      const uint32_t * fj = cj ? Dj1 : Dj0;
+      Sb = ci ? Di0 : Di1;
+      for (int idx = tid; idx < words; idx += DIL_THREADS)
+      {
+        const uint32_t x = Ib[idx] & Jb[idx];
+        uint32_t m = x;
+        uint32_t ri = fi[idx] & ~x, rj = fj[idx] & ~x;
+        while (ri)
+        {
+          const int bpos = __ffs(ri) - 1;
+          ri &= ri - 1;
+          if ((int)arrI[(size_t)idx * 32 + bpos] <= si)
+            m |= 1u << bpos;
+        }
+        while (rj)
+        {
+          const int bpos = __ffs(rj) - 1;
+          rj &= rj - 1;
+          if ((int)arrJ[(size_t)idx * 32 + bpos] <= sj)
+            m |= 1u << bpos;
+        }
+        Sb[idx] = m;
+      }
+    }
+    else
+    {
+      int k1, k2;
+      dil_run_pair(sh, Ib, Jb, Di0, Di1, Dj0, Dj1, wake, h, pitch, ball != 0, si, sj, nullptr, nullptr, nullptr, nullptr, k1, k2, ci, cj);
+      Sb = ci ? Di0 : Di1; // the i buffer that is NOT current receives the median
       const uint32_t * fi = ci ? Di1 : Di0;
       const uint32_t * fj = cj ? Dj1 : Dj0;
       for (int idx = tid; idx < words; idx += DIL_THREADS)
@@ -521,52 +586,22 @@ k_dil_nodes(const Node * __restrict__ nodes, const int * __restrict__ count, Nod
       else
         atomicMax(err, ERR_NODE_LIST);
     }
-    // ---- store the mid shape and write it into the volume with the max rule (X:714-764)
+    // ---- store the mid shape (X:714-729); its volume write with the max rule (X:743-764) is done for all nodes
+    // at once by k_apply_masks after the last level
+    for (int cell = tid; cell < mwords; cell += DIL_THREADS)
     {
-      const int lane = tid & 31, warp = tid >> 5;
-      const T label = (T)nd.label;
-      long long su, sv;
-      unsigned long long vbase;
-      if (nd.axis == 2)
-      {
-        su = 1;
-        sv = VX;
-        vbase = (unsigned long long)mid * VX * VY;
-      }
-      else if (nd.axis == 1)
-      {
-        su = 1;
-        sv = VX * VY;
-        vbase = (unsigned long long)mid * VX;
-      }
-      else
-      {
-        su = VX;
-        sv = VX * VY;
-        vbase = (unsigned long long)mid;
-      }
-      for (int cell = warp; cell < mwords; cell += DIL_THREADS / 32)
-      {
-        const int r = cell / M.pitch, wi = cell - r * M.pitch;
-        const int y = M.y0 + r, x = M.x0 + 32 * wi;
-        const uint32_t * row = Sb + (size_t)(y - uy0) * pitch;
-        const int rx = x - ux0; // >= 0
-        const int sw = rx >> 5, shf = rx & 31;
-        const uint32_t lo = row[sw];
-        const uint32_t hi = sw + 1 < pitch ? row[sw + 1] : 0u;
-        uint32_t m = __funnelshift_r(lo, hi, shf);
-        const int valid = M.w - 32 * wi;
-        if (valid < 32)
-          m &= (1u << valid) - 1u;
-        if (lane == 0)
-          arena[M.off + cell] = m;
-        if ((m >> lane) & 1u)
-        {
-          const unsigned long long a = vbase + (unsigned long long)((long long)(x + lane) * su + (long long)y * sv);
-          if (in[a] == 0)
-            atomic_max_pixel(out + a, label);
-        }
-      }
+      const int r = cell / M.pitch, wi = cell - r * M.pitch;
+      const int y = M.y0 + r, x = M.x0 + 32 * wi;
+      const uint32_t * row = Sb + (size_t)(y - uy0) * pitch;
+      const int rx = x - ux0; // >= 0
+      const int sw = rx >> 5, shf = rx & 31;
+      const uint32_t lo = row[sw];
+      const uint32_t hi = sw + 1 < pitch ? row[sw + 1] : 0u;
+      uint32_t m = __funnelshift_r(lo, hi, shf);
+      const int valid = M.w - 32 * wi;
+      if (valid < 32)
+        m &= (1u << valid) - 1u;
+      arena[M.off + cell] = m;
     }
     // ---- children (X:766-792)
     if (tid == 0 && abs(nd.i - nd.j) > 2)
@@ -616,8 +651,8 @@ template <typename T>
 static void
 launch_dil_t(Launch & L, const Node * nodes, const int * count, int maxNodes, Node * next, int * nextCount, int nextCap,
              uint32_t * arena, unsigned long long * arenaTop, unsigned long long arenaCap, const void * in, void * out,
-             const long long dims[3], int ball, unsigned * stepHist, uint32_t * slab, unsigned long long slabWords, int grid,
-             int smemBytes, EmitRec * emit, int * emitCount, int emitCap, unsigned long long emitBase, int * err)
+             const long long dims[3], int ball, unsigned * stepHist, uint32_t * slab, unsigned long long slabWords,
+             unsigned short * arr, unsigned long long arrPixels, int grid, int smemBytes, EmitRec * emit, int * emitCount, int emitCap, unsigned long long emitBase, int * err)
 {
   static bool attr = false;
   if (!attr)
@@ -629,7 +664,7 @@ launch_dil_t(Launch & L, const Node * nodes, const int * count, int maxNodes, No
   L.pre("k_dil_nodes");
   k_dil_nodes<T><<<g, DIL_THREADS, smemBytes, L.stream>>>(nodes, count, next, nextCount, nextCap, arena, arenaTop, arenaCap,
                                                           (const T *)in, (T *)out, dims[0], dims[1], dims[2], ball, stepHist, slab,
-                                                          slabWords, smemBytes / 4, emit, emitCount, emitCap, emitBase, err);
+                                                          slabWords, arr, arrPixels, smemBytes / 4, emit, emitCount, emitCap, emitBase, err);
   L.post("k_dil_nodes");
 }
 
@@ -637,8 +672,8 @@ void
 launch_nodes(Launch & L, int ptype, const Node * nodes, const int * count, int maxNodes, Node * next, int * nextCount,
              int nextCap, uint32_t * arena, unsigned long long * arenaTop, unsigned long long arenaCap, const void * in,
              void * out, const long long dims[3], int useDT, int ball, unsigned * bigHist, uint32_t * slab,
-             unsigned long long slabWords, int grid, int smemBytes, EmitRec * emit, int * emitCount, int emitCap,
-             unsigned long long emitBase, int * err)
+             unsigned long long slabWords, unsigned short * arr, unsigned long long arrPixels, int grid, int smemBytes, EmitRec * emit,
+             int * emitCount, int emitCap, unsigned long long emitBase, int * err)
 {
   (void)useDT; // the distance-transform median has its own pipeline (mci_dt.cu)
   if (maxNodes <= 0)
@@ -647,15 +682,15 @@ launch_nodes(Launch & L, int ptype, const Node * nodes, const int * count, int m
   {
     case MCI_U8:
       launch_dil_t<uint8_t>(L, nodes, count, maxNodes, next, nextCount, nextCap, arena, arenaTop, arenaCap, in, out, dims, ball, bigHist,
-                            slab, slabWords, grid, smemBytes, emit, emitCount, emitCap, emitBase, err);
+                            slab, slabWords, arr, arrPixels, grid, smemBytes, emit, emitCount, emitCap, emitBase, err);
       break;
     case MCI_U16:
       launch_dil_t<uint16_t>(L, nodes, count, maxNodes, next, nextCount, nextCap, arena, arenaTop, arenaCap, in, out, dims, ball, bigHist,
-                             slab, slabWords, grid, smemBytes, emit, emitCount, emitCap, emitBase, err);
+                             slab, slabWords, arr, arrPixels, grid, smemBytes, emit, emitCount, emitCap, emitBase, err);
       break;
     default:
       launch_dil_t<int16_t>(L, nodes, count, maxNodes, next, nextCount, nextCap, arena, arenaTop, arenaCap, in, out, dims, ball, bigHist,
-                            slab, slabWords, grid, smemBytes, emit, emitCount, emitCap, emitBase, err);
+                            slab, slabWords, arr, arrPixels, grid, smemBytes, emit, emitCount, emitCap, emitBase, err);
   }
 }
 

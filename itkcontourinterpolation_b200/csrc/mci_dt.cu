@@ -925,6 +925,37 @@ write_group(const T * __restrict__ in, T * out, unsigned long long g /* first vo
   }
 }
 
+// same with the two groups already loaded (lets a caller keep several groups in flight)
+template <typename T>
+__device__ __forceinline__ void
+write_group_loaded(T * out, unsigned long long g, unsigned bits, T label, unsigned long long qinU, unsigned long long qoutU)
+{
+  constexpr int VPQ = 8 / sizeof(T);
+  union Q
+  {
+    unsigned long long u;
+    T v[VPQ];
+  };
+  Q qi, qo, qn;
+  qi.u = qinU;
+  qo.u = qoutU;
+  unsigned long long * po = reinterpret_cast<unsigned long long *>(out + g);
+  for (;;)
+  {
+    qn = qo;
+#pragma unroll
+    for (int k = 0; k < VPQ; ++k)
+      if (((bits >> k) & 1u) && qi.v[k] == 0 && qo.v[k] < label)
+        qn.v[k] = label;
+    if (qn.u == qo.u)
+      return;
+    unsigned long long prev = atomicCAS(po, qo.u, qn.u);
+    if (prev == qo.u)
+      return;
+    qo.u = prev;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_dt_emit(const NodeWork * __restrict__ work, const DtItem * __restrict__ witems, const int * __restrict__ witemCount,
@@ -1046,9 +1077,10 @@ k_dt_emit(const NodeWork * __restrict__ work, const DtItem * __restrict__ witems
 // Replays the volume writes of mid slices produced elsewhere (another GPU's shard): same write rule as k_dt_emit.
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_apply_masks(const EmitRec * __restrict__ recs, int nrecs, const uint32_t * __restrict__ words, const T * __restrict__ in, T * out,
-              long long VX, long long VY, long long VZ)
+k_apply_masks(const EmitRec * __restrict__ recs, int nrecsHost, const int * __restrict__ nrecsDev, const uint32_t * __restrict__ words,
+              const T * __restrict__ in, T * out, long long VX, long long VY, long long VZ)
 {
+  const int nrecs = nrecsDev ? min(*nrecsDev, nrecsHost) : nrecsHost; // device-side count capped by the list capacity
   constexpr int VPQ = 8 / sizeof(T);
   constexpr int GPW = 32 / VPQ + 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -1085,33 +1117,56 @@ k_apply_masks(const EmitRec * __restrict__ recs, int nrecs, const uint32_t * __r
       const uint32_t myM = cb + lane < cEnd ? __ldg(words + M.off + cb + lane) : 0u;
       if (su == 1)
       {
+        // x runs along the bits: aligned 8-byte groups, one per lane and task; four tasks are in flight per lane
+        // (loads of the input and output groups first, then the compare-and-swaps) to hide the memory latency
         const int nTasks = (cEnd - cb) * GPW;
-        for (int tb = 0; tb < nTasks; tb += 32)
+        constexpr int BATCH = 4;
+        for (int tb = 0; tb < nTasks; tb += 32 * BATCH)
         {
-          const int task = tb + lane;
-          const int c = min(task / GPW, cEnd - cb - 1), q = task % GPW;
-          const uint32_t m = __shfl_sync(0xFFFFFFFFu, myM, c);
-          if (task < nTasks && m)
+          unsigned long long g[BATCH];
+          unsigned bits[BATCH];
+          unsigned long long qin[BATCH], qout[BATCH];
+#pragma unroll
+          for (int u = 0; u < BATCH; ++u)
           {
-            const int cell = cb + c;
-            const int r = cell / M.pitch, wi = cell - r * M.pitch;
-            const unsigned long long a0 = vbase + (unsigned long long)((long long)(M.x0 + 32 * wi) + (long long)(M.y0 + r) * sv);
-            const unsigned long long g = (a0 & ~(unsigned long long)(VPQ - 1)) + (unsigned long long)q * VPQ;
-            const long long sh = (long long)g - (long long)a0;
-            unsigned bits;
-            if (sh >= 32)
-              bits = 0u;
-            else if (sh >= 0)
-              bits = (m >> sh) & ((1u << VPQ) - 1u);
-            else
-              bits = (m << (-sh)) & ((1u << VPQ) - 1u);
-            if (bits && g + VPQ <= nvox)
-              write_group<T>(in, out, g, bits, label);
-            else if (bits)
-              for (int k = 0; k < VPQ; ++k)
-                if (((bits >> k) & 1u) && g + k < nvox && in[g + k] == 0)
-                  atomic_max_pixel(out + g + k, label);
+            const int task = tb + u * 32 + lane;
+            const int c = min(task / GPW, cEnd - cb - 1), q = task % GPW;
+            const uint32_t m = __shfl_sync(0xFFFFFFFFu, myM, c);
+            bits[u] = 0u;
+            g[u] = 0ull;
+            if (task < nTasks && m)
+            {
+              const int cell = cb + c;
+              const int r = cell / M.pitch, wi = cell - r * M.pitch;
+              const unsigned long long a0 = vbase + (unsigned long long)((long long)(M.x0 + 32 * wi) + (long long)(M.y0 + r) * sv);
+              g[u] = (a0 & ~(unsigned long long)(VPQ - 1)) + (unsigned long long)q * VPQ;
+              const long long sh = (long long)g[u] - (long long)a0;
+              if (sh >= 32)
+                bits[u] = 0u;
+              else if (sh >= 0)
+                bits[u] = (m >> sh) & ((1u << VPQ) - 1u);
+              else
+                bits[u] = (m << (-sh)) & ((1u << VPQ) - 1u);
+              if (bits[u] && g[u] + VPQ > nvox)
+              {
+                for (int k = 0; k < VPQ; ++k) // last, partial group of the volume
+                  if (((bits[u] >> k) & 1u) && g[u] + k < nvox && in[g[u] + k] == 0)
+                    atomic_max_pixel(out + g[u] + k, label);
+                bits[u] = 0u;
+              }
+            }
           }
+#pragma unroll
+          for (int u = 0; u < BATCH; ++u)
+            if (bits[u])
+            {
+              qin[u] = __ldg(reinterpret_cast<const unsigned long long *>(in + g[u]));
+              qout[u] = *reinterpret_cast<const unsigned long long *>(out + g[u]);
+            }
+#pragma unroll
+          for (int u = 0; u < BATCH; ++u)
+            if (bits[u])
+              write_group_loaded<T>(out, g[u], bits[u], label, qin[u], qout[u]);
         }
       }
       else
@@ -1135,8 +1190,8 @@ k_apply_masks(const EmitRec * __restrict__ recs, int nrecs, const uint32_t * __r
 }
 
 void
-launch_apply_masks(Launch & L, int ptype, const EmitRec * recs, int nrecs, const uint32_t * words, const void * in, void * out,
-                   const long long dims[3])
+launch_apply_masks(Launch & L, int ptype, const EmitRec * recs, int nrecs, const int * nrecsDev, const uint32_t * words, const void * in,
+                   void * out, const long long dims[3])
 {
   if (nrecs <= 0)
     return;
@@ -1145,14 +1200,16 @@ launch_apply_masks(Launch & L, int ptype, const EmitRec * recs, int nrecs, const
   switch (ptype)
   {
     case MCI_U8:
-      k_apply_masks<uint8_t><<<grid, 256, 0, L.stream>>>(recs, nrecs, words, (const uint8_t *)in, (uint8_t *)out, dims[0], dims[1], dims[2]);
+      k_apply_masks<uint8_t><<<grid, 256, 0, L.stream>>>(recs, nrecs, nrecsDev, words, (const uint8_t *)in, (uint8_t *)out, dims[0], dims[1],
+                                                         dims[2]);
       break;
     case MCI_U16:
-      k_apply_masks<uint16_t><<<grid, 256, 0, L.stream>>>(recs, nrecs, words, (const uint16_t *)in, (uint16_t *)out, dims[0], dims[1],
-                                                           dims[2]);
+      k_apply_masks<uint16_t><<<grid, 256, 0, L.stream>>>(recs, nrecs, nrecsDev, words, (const uint16_t *)in, (uint16_t *)out, dims[0],
+                                                           dims[1], dims[2]);
       break;
     default:
-      k_apply_masks<int16_t><<<grid, 256, 0, L.stream>>>(recs, nrecs, words, (const int16_t *)in, (int16_t *)out, dims[0], dims[1], dims[2]);
+      k_apply_masks<int16_t><<<grid, 256, 0, L.stream>>>(recs, nrecs, nrecsDev, words, (const int16_t *)in, (int16_t *)out, dims[0], dims[1],
+                                                          dims[2]);
   }
   L.post("k_apply_masks");
 }

@@ -140,9 +140,9 @@ void launch_make_roots(Launch & L, const RootJob * roots, int nroots, MaskRef * 
 void launch_nodes(Launch & L, int ptype, const Node * nodes, const int * count, int maxNodes, Node * next, int * nextCount,
                   int nextCap, uint32_t * arena, unsigned long long * arenaTop, unsigned long long arenaCap, const void * in,
                   void * out, const long long dims[3], int useDT, int ball, unsigned * bigHist, uint32_t * slab,
-                  unsigned long long slabWords, int grid, int smemBytes, EmitRec * emit, int * emitCount, int emitCap,
-                  unsigned long long emitBase, int * err);
-void launch_apply_masks(Launch & L, int ptype, const EmitRec * recs, int nrecs, const uint32_t * words, const void * in, void * out,
-                        const long long dims[3]);
+                  unsigned long long slabWords, unsigned short * arr, unsigned long long arrPixels, int grid, int smemBytes,
+                  EmitRec * emit, int * emitCount, int emitCap, unsigned long long emitBase, int * err);
+void launch_apply_masks(Launch & L, int ptype, const EmitRec * recs, int nrecs, const int * nrecsDev, const uint32_t * words,
+                        const void * in, void * out, const long long dims[3]);
 
 } // namespace mci

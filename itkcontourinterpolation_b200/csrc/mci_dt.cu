@@ -1110,67 +1110,51 @@ k_apply_masks(const EmitRec * __restrict__ recs, int nrecsHost, const int * __re
       sv = VX * VY;
       vbase = (unsigned long long)R.mid;
     }
-    const int mwords = M.h * M.pitch;
-    for (int cb = warp * 32; cb < mwords; cb += nwarps * 32)
+    if (su == 1)
     {
-      const int cEnd = min(mwords, cb + 32);
-      const uint32_t myM = cb + lane < cEnd ? __ldg(words + M.off + cb + lane) : 0u;
-      if (su == 1)
+      // x runs along the bits.  A warp takes one mask row at a time and three of its words per iteration: lane
+      // 9*s + q handles aligned 8-byte group q of word s (27 lanes busy), so no per-task index arithmetic is left.
+      const int sub = lane / GPW, q = lane - sub * GPW;
+      for (int r = warp; r < M.h; r += nwarps)
       {
-        // x runs along the bits: aligned 8-byte groups, one per lane and task; four tasks are in flight per lane
-        // (loads of the input and output groups first, then the compare-and-swaps) to hide the memory latency
-        const int nTasks = (cEnd - cb) * GPW;
-        constexpr int BATCH = 4;
-        for (int tb = 0; tb < nTasks; tb += 32 * BATCH)
+        const unsigned long long rowBase = vbase + (unsigned long long)((long long)M.x0 + (long long)(M.y0 + r) * sv);
+        const uint32_t * rowWords = words + M.off + (size_t)r * M.pitch;
+        for (int wi0 = 0; wi0 < M.pitch; wi0 += 3)
         {
-          unsigned long long g[BATCH];
-          unsigned bits[BATCH];
-          unsigned long long qin[BATCH], qout[BATCH];
-#pragma unroll
-          for (int u = 0; u < BATCH; ++u)
-          {
-            const int task = tb + u * 32 + lane;
-            const int c = min(task / GPW, cEnd - cb - 1), q = task % GPW;
-            const uint32_t m = __shfl_sync(0xFFFFFFFFu, myM, c);
-            bits[u] = 0u;
-            g[u] = 0ull;
-            if (task < nTasks && m)
-            {
-              const int cell = cb + c;
-              const int r = cell / M.pitch, wi = cell - r * M.pitch;
-              const unsigned long long a0 = vbase + (unsigned long long)((long long)(M.x0 + 32 * wi) + (long long)(M.y0 + r) * sv);
-              g[u] = (a0 & ~(unsigned long long)(VPQ - 1)) + (unsigned long long)q * VPQ;
-              const long long sh = (long long)g[u] - (long long)a0;
-              if (sh >= 32)
-                bits[u] = 0u;
-              else if (sh >= 0)
-                bits[u] = (m >> sh) & ((1u << VPQ) - 1u);
-              else
-                bits[u] = (m << (-sh)) & ((1u << VPQ) - 1u);
-              if (bits[u] && g[u] + VPQ > nvox)
-              {
-                for (int k = 0; k < VPQ; ++k) // last, partial group of the volume
-                  if (((bits[u] >> k) & 1u) && g[u] + k < nvox && in[g[u] + k] == 0)
-                    atomic_max_pixel(out + g[u] + k, label);
-                bits[u] = 0u;
-              }
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < BATCH; ++u)
-            if (bits[u])
-            {
-              qin[u] = __ldg(reinterpret_cast<const unsigned long long *>(in + g[u]));
-              qout[u] = *reinterpret_cast<const unsigned long long *>(out + g[u]);
-            }
-#pragma unroll
-          for (int u = 0; u < BATCH; ++u)
-            if (bits[u])
-              write_group_loaded<T>(out, g[u], bits[u], label, qin[u], qout[u]);
+          const int wi = wi0 + sub;
+          if (sub >= 3 || wi >= M.pitch)
+            continue;
+          const uint32_t m = __ldg(rowWords + wi);
+          if (!m)
+            continue;
+          const unsigned long long a0 = rowBase + 32ull * wi;
+          const unsigned long long g = (a0 & ~(unsigned long long)(VPQ - 1)) + (unsigned long long)q * VPQ;
+          const int sh = (int)((long long)g - (long long)a0); // in (-VPQ, 32]
+          unsigned bits;
+          if (sh >= 32)
+            bits = 0u;
+          else if (sh >= 0)
+            bits = (m >> sh) & ((1u << VPQ) - 1u);
+          else
+            bits = (m << (-sh)) & ((1u << VPQ) - 1u);
+          if (!bits)
+            continue;
+          if (g + VPQ <= nvox)
+            write_group<T>(in, out, g, bits, label);
+          else
+            for (int k = 0; k < VPQ; ++k)
+              if (((bits >> k) & 1u) && g + k < nvox && in[g + k] == 0)
+                atomic_max_pixel(out + g + k, label);
         }
       }
-      else
+    }
+    else
+    {
+      const int mwords = M.h * M.pitch;
+      for (int cb = warp * 32; cb < mwords; cb += nwarps * 32)
       {
+        const int cEnd = min(mwords, cb + 32);
+        const uint32_t myM = cb + lane < cEnd ? __ldg(words + M.off + cb + lane) : 0u;
         for (int c = 0; c < cEnd - cb; ++c)
         {
           const uint32_t m = __shfl_sync(0xFFFFFFFFu, myM, c);

@@ -543,6 +543,38 @@ extern "C"
     return MCI_OK;
   }
 
+  // The pair bookkeeping of InterpolateBetweenTwo (X:1274-1446) for ONE segment, exposed so that it can be checked
+  // without a GPU: `pairs` are the distinct (iId, jId) != (0,0) of the segment as mci_match_pairs emits them.  Jobs
+  // come back with slice_a/slice_b = 0 for the i slice and 1 for the j slice, pos_a/pos_b = 0 / 1 likewise.
+  int mci_filter_schedule_pairs(const mci_pair * pairs, int32_t n_pairs, int use_extrapolation, mci_job * jobs, int32_t cap_jobs,
+                                int32_t * n_jobs, int32_t * b_ids, int32_t cap_b_ids, int32_t * n_b_ids)
+  {
+    if ((n_pairs > 0 && !pairs) || !n_jobs || !n_b_ids)
+      return MCI_ERR_ARG;
+    Segment seg;
+    seg.axis = 0;
+    seg.label = 1;
+    seg.i = 0;
+    seg.j = 1;
+    seg.si = 0;
+    seg.sj = 1;
+    std::set<IdPair> unclean;
+    for (int32_t k = 0; k < n_pairs; ++k)
+      unclean.insert(IdPair(pairs[k].i_id, pairs[k].j_id));
+    std::vector<mci_job> js;
+    std::vector<int32_t> ids;
+    schedule_segment(seg, unclean, use_extrapolation != 0, js, ids);
+    *n_jobs = (int32_t)js.size();
+    *n_b_ids = (int32_t)ids.size();
+    if ((int32_t)js.size() > cap_jobs || (int32_t)ids.size() > cap_b_ids)
+      return MCI_ERR_CAPACITY;
+    for (size_t k = 0; k < js.size(); ++k)
+      jobs[k] = js[k];
+    for (size_t k = 0; k < ids.size(); ++k)
+      b_ids[k] = ids[k];
+    return MCI_OK;
+  }
+
   void mci_filter_forget(mci_ctx * ctx)
   {
     std::lock_guard<std::mutex> hold(g_mutex);

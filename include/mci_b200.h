@@ -220,6 +220,15 @@ int mci_filter_run(mci_ctx * ctx, const mci_filter_options * opt, const void * h
 /* same, input already on the device (mci_upload_volume / mci_attach_device_volume) and output left there */
 int mci_filter_run_resident(mci_ctx * ctx, const mci_filter_options * opt, const int64_t * custom_slices,
                             int64_t n_custom, mci_filter_stats * stats);
+/* Throughput mode for a series of independent label volumes (same dims and pixel type): volume k goes through
+ * ctxs[k % ...] -- n_ctx contexts, each with its own stream, driven by one host thread each -- so the H2D copy of
+ * one volume, the kernels of another and the D2H copy of a third overlap (PCIe is full duplex; a single mci_filter_run
+ * leaves each direction idle most of the time).  Results are those of n_volumes mci_filter_run calls.  host_in[k] /
+ * host_out[k] should be pinned (mci_host_alloc) for the copies to be asynchronous.  stats: [n_volumes] or NULL.
+ * Returns the first non-zero status of any volume (its message is in that context's mci_last_error). */
+int mci_filter_run_batch(mci_ctx * const * ctxs, int32_t n_ctx, const mci_filter_options * opt, const void * const * host_in,
+                         void * const * host_out, int32_t n_volumes, const int64_t dims[3], int pixel_type,
+                         mci_filter_stats * stats);
 /* slice sets found by the last run / by mci_filter_detect, as (axis,label,slice) triplets:
  * GetLabeledSliceIndices (H:209-224) */
 int mci_filter_detect(mci_ctx * ctx, const mci_filter_options * opt, int64_t * n_triplets);

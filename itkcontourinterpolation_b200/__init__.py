@@ -3,5 +3,6 @@
 Importing the package does not load the CUDA library; constructing a filter does, and fails loudly
 without a GPU (there is no CPU fallback).
 """
-from .filter import MorphologicalContourInterpolator, morphological_contour_interpolator  # noqa: F401
+from .filter import (MorphologicalContourInterpolator, VolumeSeriesInterpolator,  # noqa: F401
+                     morphological_contour_interpolator)
 from .nrrd import read_nrrd  # noqa: F401

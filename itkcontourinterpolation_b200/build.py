@@ -52,5 +52,30 @@ def build(force=False, verbose=False):
     return LIB
 
 
+DRIVER = os.path.join(OUT, "mci_filter_test")
+
+
+def build_cpp_driver(verbose=False):
+    """g++ build of tests/cpp/mci_filter_test.cpp: the C++ filter class of include/mci_b200_filter.hpp driven the
+    way the reference's test driver drives itk::MorphologicalContourInterpolator.  Lives next to the library (rpath
+    $ORIGIN) so that it travels to the GPU box."""
+    lib = build(verbose=verbose)
+    root = os.path.join(_HERE, "..")
+    src = os.path.join(root, "tests", "cpp", "mci_filter_test.cpp")
+    hdrs = [os.path.join(root, "include", "mci_b200_filter.hpp"), os.path.join(root, "include", "mci_b200.h"), lib]
+    if not os.path.exists(src):
+        if os.path.exists(DRIVER):
+            return DRIVER
+        raise RuntimeError("mci_filter_test.cpp missing and no prebuilt driver present")
+    if _newer(DRIVER, [src] + hdrs):
+        cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-Wall", "-Wextra", "-I", os.path.join(root, "include"), src,
+               "-o", DRIVER, "-L", OUT, "-lmci_b200", "-Wl,-rpath,$ORIGIN"]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+    return DRIVER
+
+
 if __name__ == "__main__":
     print(build(verbose=True))
+    print(build_cpp_driver(verbose=True))

@@ -10,6 +10,8 @@
 #include <map>
 #include <mutex>
 #include <set>
+#include <thread>
+#include <atomic>
 #include <utility>
 #include <vector>
 
@@ -506,6 +508,44 @@ extern "C"
     stats->ms_total = t1 - t0;
     stats->n_launches = mci_launch_count(ctx) - l0;
     return rc;
+  }
+
+  int mci_filter_run_batch(mci_ctx * const * ctxs, int32_t nCtx, const mci_filter_options * opt, const void * const * hostIn,
+                           void * const * hostOut, int32_t nVolumes, const int64_t dims[3], int pixelType, mci_filter_stats * stats)
+  {
+    if (!ctxs || nCtx < 1 || !opt || nVolumes < 0 || (nVolumes > 0 && (!hostIn || !hostOut)) || !dims)
+      return MCI_ERR_ARG;
+    for (int32_t c = 0; c < nCtx; ++c)
+      if (!ctxs[c])
+        return MCI_ERR_ARG;
+    // one worker per context; volumes are handed out in order, so with n_ctx in flight the copy engines of both
+    // directions and the SMs are busy at the same time
+    std::atomic<int32_t> next(0);
+    std::atomic<int> firstError(MCI_OK);
+    auto worker = [&](int32_t c) {
+      for (;;)
+      {
+        int32_t k = next.fetch_add(1);
+        if (k >= nVolumes || firstError.load() != MCI_OK)
+          return;
+        int rc = mci_filter_run(ctxs[c], opt, hostIn[k], hostOut[k], dims, pixelType, nullptr, 0, stats ? stats + k : nullptr);
+        if (rc)
+        {
+          int expected = MCI_OK;
+          firstError.compare_exchange_strong(expected, rc);
+          return;
+        }
+      }
+    };
+    const int32_t nWorkers = nCtx < nVolumes ? nCtx : nVolumes;
+    std::vector<std::thread> threads;
+    for (int32_t c = 1; c < nWorkers; ++c)
+      threads.emplace_back(worker, c);
+    if (nWorkers > 0)
+      worker(0);
+    for (std::thread & t : threads)
+      t.join();
+    return firstError.load();
   }
 
   int mci_filter_detect(mci_ctx * ctx, const mci_filter_options * opt, int64_t * nTriplets)

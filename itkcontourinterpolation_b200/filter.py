@@ -152,3 +152,79 @@ def morphological_contour_interpolator(vol, label=0, axis=-1, heuristic_alignmen
         return (out, f.last_stats) if return_stats else out
     finally:
         f.close()
+
+
+class VolumeSeriesInterpolator:
+    """Throughput mode for a series of independent label volumes of one shape and pixel type
+    (mci_filter_run_batch): `depth` contexts -- own stream, own host thread, own pinned in/out buffers each -- so that
+    the H2D copy of one volume, the kernels of another and the D2H copy of a third overlap.  Every volume gets exactly
+    the result MorphologicalContourInterpolator.Update() gives it."""
+
+    def __init__(self, shape, dtype=np.uint16, depth=3, device=0, **options):
+        self._lib = L.lib()
+        self._shape = tuple(int(v) for v in shape)
+        self._dtype = np.dtype(dtype)
+        if len(self._shape) != 3 or self._dtype not in _PTYPE:
+            raise TypeError("expected a 3-D uint8/uint16/int16 volume shape [z, y, x]")
+        self._depth = int(depth)
+        self._ctxs, self._in, self._out = [], [], []
+        self._opt = L.FilterOptions()
+        self._lib.mci_filter_default_options(ctypes.byref(self._opt))
+        for k, v in options.items():
+            if not hasattr(self._opt, k) or k.startswith("shard"):
+                raise TypeError("unknown filter option %r" % k)
+            setattr(self._opt, k, int(v))
+        self._nbytes = int(np.prod(self._shape)) * self._dtype.itemsize
+        for _ in range(self._depth):
+            c = ctypes.c_void_p()
+            rc = self._lib.mci_create(ctypes.byref(c), int(device))
+            if rc != L.OK:
+                self.close()
+                raise L.MciError(rc, "mci_create failed (no usable CUDA device; there is no CPU fallback)")
+            self._ctxs.append(c)
+            for lst in (self._in, self._out):
+                p = self._lib.mci_host_alloc(self._nbytes)
+                if not p:
+                    self.close()
+                    raise MemoryError("pinned host allocation failed")
+                lst.append(p)
+
+    def close(self):
+        for p in self._in + self._out:
+            self._lib.mci_host_free(p)
+        for c in self._ctxs:
+            self._lib.mci_destroy(c)
+        self._ctxs, self._in, self._out = [], [], []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, volumes):
+        """Interpolates every volume of the sequence; returns the list of outputs (numpy arrays)."""
+        volumes = [np.ascontiguousarray(v) for v in volumes]
+        for v in volumes:
+            if v.shape != self._shape or v.dtype != self._dtype:
+                raise TypeError("every volume must have shape %r and dtype %s" % (self._shape, self._dtype))
+        dims = (ctypes.c_int64 * 3)(self._shape[2], self._shape[1], self._shape[0])
+        outs = []
+        d = self._depth
+        ctx_arr = (ctypes.c_void_p * d)(*[c.value for c in self._ctxs])
+        for g0 in range(0, len(volumes), d):  # one group of `depth` volumes per call: the pinned slots are reused
+            group = volumes[g0:g0 + d]
+            for k, v in enumerate(group):
+                ctypes.memmove(self._in[k], v.ctypes.data, self._nbytes)
+            n = len(group)
+            in_arr = (ctypes.c_void_p * n)(*self._in[:n])
+            out_arr = (ctypes.c_void_p * n)(*self._out[:n])
+            rc = self._lib.mci_filter_run_batch(ctx_arr, d, ctypes.byref(self._opt), in_arr, out_arr, n, dims,
+                                                _PTYPE[self._dtype], None)
+            if rc != L.OK:
+                msgs = [self._lib.mci_last_error(c).decode() for c in self._ctxs]
+                raise L.MciError(rc, "; ".join(m for m in msgs if m))
+            for k in range(n):
+                buf = (ctypes.c_char * self._nbytes).from_address(self._out[k])
+                outs.append(np.frombuffer(buf, dtype=self._dtype).reshape(self._shape).copy())
+        return outs

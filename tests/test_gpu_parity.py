@@ -236,3 +236,31 @@ def test_big_regions_take_the_global_scratch_paths(flt, algo):
     v = _big_roi_volume()
     out = run_gpu(flt, v, **kw)
     assert_same(out, O.interpolate(v, threads=os.cpu_count() or 1, **kw), "big ROI " + algo)
+
+
+def test_volume_series_throughput_mode_matches_single_runs():
+    # mci_filter_run_batch: several volumes in flight on separate contexts / streams / host threads
+    from itkcontourinterpolation_b200.filter import VolumeSeriesInterpolator
+    h = cases.handcrafted()
+    vols = [v for v in h.values() if v.shape == (9, 40, 48)]
+    assert len(vols) >= 6
+    vols = vols * 3                                              # 3 rounds through every in-flight slot
+    for depth, kw_gpu, kw_cpu in ((3, dict(), dict()),
+                                  (2, dict(use_distance_transform=0, use_ball_structuring_element=1),
+                                   dict(use_distance_transform=False, use_ball=True))):
+        s = VolumeSeriesInterpolator((9, 40, 48), np.uint16, depth=depth, **kw_gpu)
+        try:
+            outs = s.run(vols)
+        finally:
+            s.close()
+        assert len(outs) == len(vols)
+        for k, (v, o) in enumerate(zip(vols, outs)):
+            assert_same(o, O.interpolate(v, **kw_cpu), "series volume %d depth %d" % (k, depth))
+    vol, _, cfg = make_config("C3", 0.5)
+    ref = O.interpolate(vol, axis=2, threads=os.cpu_count() or 1)
+    s = VolumeSeriesInterpolator(vol.shape, np.uint16, depth=3, axis=2)
+    try:
+        for o in s.run([vol] * 7):
+            assert_same(o, ref, "C3/2 series")
+    finally:
+        s.close()

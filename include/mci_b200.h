@@ -191,6 +191,16 @@ int mci_get_emitted(mci_ctx * ctx, void ** recs_dev, int64_t * n_recs, void ** w
 int mci_copy_emitted(mci_ctx * ctx, void * dst_dev, int64_t words_offset_bytes);
 int mci_apply_masks(mci_ctx * ctx, const void * recs_dev, int64_t n_recs, const void * words_dev, int64_t n_words);
 
+/* ---- label smoothing applied to the interpolator's output by the reference's example --------
+ * itk::MedianImageFilter<TImage,TImage> with SetRadius(radius) (reference examples/mciExample.cxx:29-39): box
+ * neighbourhood (2r+1)^3, ZeroFluxNeumann boundary, element n/2 of the sorted neighbourhood.  radius in [0, 3].
+ * _resident: the context's device output volume (e.g. what mci_filter_run_resident left there) is replaced by its
+ * smoothed version, asynchronously on the context's stream; follow with mci_download_volume.
+ * _run: host in -> host out (upload, filter, download; synchronises). */
+int mci_median_filter_resident(mci_ctx * ctx, int radius);
+int mci_median_filter_run(mci_ctx * ctx, const void * host_in, void * host_out, const int64_t dims[3], int pixel_type,
+                          int radius);
+
 /* ---- host scheduler (layer 2): the filter itself --------------------------------------------
  * Mirrors the setters of H:85-165 and GenerateData (X:1559-1637). */
 typedef struct

@@ -4,5 +4,5 @@ Importing the package does not load the CUDA library; constructing a filter does
 without a GPU (there is no CPU fallback).
 """
 from .filter import (MorphologicalContourInterpolator, VolumeSeriesInterpolator,  # noqa: F401
-                     morphological_contour_interpolator)
+                     morphological_contour_interpolator, median_image_filter, interpolate_and_smooth)
 from .nrrd import read_nrrd  # noqa: F401

@@ -109,6 +109,8 @@ SYMBOLS = [
     ("mci_get_emitted", _I, [_P, ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_int64)]),
     ("mci_copy_emitted", _I, [_P, _P, ctypes.c_int64]),
     ("mci_apply_masks", _I, [_P, _P, ctypes.c_int64, _P, ctypes.c_int64]),
+    ("mci_median_filter_resident", _I, [_P, _I]),
+    ("mci_median_filter_run", _I, [_P, _P, _P, ctypes.POINTER(ctypes.c_int64), _I, _I]),
     ("mci_filter_default_options", None, [ctypes.POINTER(FilterOptions)]),
     ("mci_filter_run", _I, [_P, ctypes.POINTER(FilterOptions), _P, _P, ctypes.POINTER(ctypes.c_int64), _I, _P,
                             ctypes.c_int64, ctypes.POINTER(FilterStats)]),

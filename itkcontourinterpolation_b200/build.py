@@ -13,7 +13,7 @@ LIB = os.path.join(OUT, "libmci_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "177"] + os.environ.get("MCI_NVCC_EXTRA", "").split()
-SOURCES = ["mci_kernels.cu", "mci_cc.cu", "mci_dt.cu", "mci_dil.cu", "mci_cabi.cu", "mci_filter.cpp"]
+SOURCES = ["mci_kernels.cu", "mci_cc.cu", "mci_dt.cu", "mci_dil.cu", "mci_median.cu", "mci_cabi.cu", "mci_filter.cpp"]
 HEADERS = ["mci_types.h", "mci_kernels.cuh", "mci_launch.h", os.path.join("..", "..", "include", "mci_b200.h")]
 
 

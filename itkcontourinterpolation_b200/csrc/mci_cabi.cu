@@ -56,7 +56,8 @@ struct HBuf
     p = nullptr;
     cap = 0;
     size_t want = bytes + bytes / 4 + 256;
-    cudaError_t e = cudaMallocHost(&p, want);
+    // mapped: kernels read / write these buffers directly (see table_copy below)
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocMapped | cudaHostAllocPortable);
     if (e == cudaSuccess)
       cap = want;
     return e;
@@ -104,9 +105,10 @@ struct mci_ctx
   size_t nvox = 0;
   void * dIn = nullptr;
   void * dOut = nullptr;
-  DBuf ownIn, ownOut;
+  DBuf ownIn, ownOut, ownTmp, dMedTiles;
   // detection
   DBuf dBBox, dSliceBits, dLabels, dLabeledSlices, dCounters, dChunkBits;
+  HBuf hErr;
   HBuf hStage, hStage2, hRes; // hRes: pinned landing zone of the small device->host result tables
   int resLabels = 0, resSlices = 0, resPairs = 0, resStats = 0; // how many entries of each table hRes holds
   int nLabels = 0, nLabeledSlices = 0;
@@ -161,6 +163,67 @@ static const size_t kResBytes = kResStatsOff + size_t(kSpecStats) * sizeof(mci::
     }                                                                                                                          \
   } while (0)
 
+// ---- small tables between host and device ------------------------------------------------------------------
+// Descriptor blobs (host -> device) and result tables (device -> host) cross PCIe through MAPPED pinned memory with
+// SM loads / stores, never through the copy engines: a copy engine serves its queue in submission order, so with
+// several volumes in flight (mci_filter_run_batch) a 100-byte table copy would wait behind another context's
+// 100+ MB volume copy, milliseconds each time.  Up to four segments per launch; a segment may be bounded by an element
+// count that lives on the device, so speculative fixed-size transfers are not needed.
+struct TableSeg
+{
+  uint32_t * dst;
+  const uint32_t * src;
+  unsigned nWords;          // fixed size, or the cap when count != nullptr
+  const int * count;        // device pointer to an element count (or nullptr)
+  unsigned wordsPerElem;
+};
+struct TableSegs
+{
+  TableSeg s[4];
+  int n;
+};
+__global__ void __launch_bounds__(256) k_table_copy(TableSegs t)
+{
+  for (int k = 0; k < t.n; ++k)
+  {
+    const TableSeg sg = t.s[k];
+    unsigned n = sg.nWords;
+    if (sg.count)
+    {
+      const long long want = (long long)max(*sg.count, 0) * sg.wordsPerElem;
+      n = (unsigned)min((long long)n, want);
+    }
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+      sg.dst[i] = sg.src[i];
+  }
+}
+struct TableCopy
+{
+  TableSegs t;
+  unsigned maxWords = 0;
+  TableCopy() { t.n = 0; }
+  // bytes must be a multiple of 4 (every table here is)
+  void add(void * dst, const void * src, size_t bytes, const int * count = nullptr, unsigned bytesPerElem = 4)
+  {
+    TableSeg & g = t.s[t.n++];
+    g.dst = (uint32_t *)dst;
+    g.src = (const uint32_t *)src;
+    g.nWords = (unsigned)((bytes + 3) / 4);
+    g.count = count;
+    g.wordsPerElem = bytesPerElem / 4;
+    maxWords = std::max(maxWords, g.nWords);
+  }
+  void launch(Launch & L)
+  {
+    if (!t.n)
+      return;
+    const int grid = (int)std::max(1u, std::min((maxWords + 1023) / 1024, 64u));
+    L.pre("k_table_copy");
+    k_table_copy<<<grid, 256, 0, L.stream>>>(t);
+    L.post("k_table_copy");
+  }
+};
+
 static int
 fail(mci_ctx * ctx, int code, const std::string & msg)
 {
@@ -171,9 +234,14 @@ fail(mci_ctx * ctx, int code, const std::string & msg)
 static int
 check_device_error(mci_ctx * ctx)
 {
-  int h = 0;
-  CK(cudaMemcpyAsync(&h, ctx->dErr, sizeof(int), cudaMemcpyDeviceToHost, ctx->L.stream));
+  CK(ctx->hErr.ensure(64));
+  {
+    TableCopy tc;
+    tc.add(ctx->hErr.p, ctx->dErr, sizeof(int));
+    tc.launch(ctx->L);
+  }
   CK(cudaStreamSynchronize(ctx->L.stream));
+  const int h = *(volatile int *)ctx->hErr.p;
   if (ctx->L.failedKernel)
   {
     ctx->err = std::string("launch of ") + ctx->L.failedKernel + " failed: " + cudaGetErrorString(ctx->L.failedCode);
@@ -250,7 +318,7 @@ extern "C"
     mci_filter_forget(ctx);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->L.stream);
-    DBuf * bufs[] = { &ctx->ownIn,     &ctx->ownOut,   &ctx->dBBox,     &ctx->dSliceBits, &ctx->dLabels,  &ctx->dLabeledSlices,
+    DBuf * bufs[] = { &ctx->ownTmp, &ctx->dMedTiles, &ctx->ownIn,     &ctx->ownOut,   &ctx->dBBox,     &ctx->dSliceBits, &ctx->dLabels,  &ctx->dLabeledSlices,
                       &ctx->dCounters, &ctx->dSliceBlob, &ctx->dBits, &ctx->dWordRun,    &ctx->dConn,    &ctx->dRunComp, &ctx->dRunScratch,
                       &ctx->dNcomp,    &ctx->dCompBase, &ctx->dTotal,   &ctx->dStats,     &ctx->dSegBlob, &ctx->dPairTable,
                       &ctx->dPairs,    &ctx->dJobBlob,  &ctx->dArena,   &ctx->dScratch,   &ctx->dBigHist, &ctx->dSlab,
@@ -263,6 +331,7 @@ extern "C"
     for (cudaEvent_t e : ctx->L.pool)
       cudaEventDestroy(e);
     ctx->hStage.release();
+    ctx->hErr.release();
     ctx->hRes.release();
     ctx->hStage2.release();
     cudaFree(ctx->dErr);
@@ -440,6 +509,57 @@ extern "C"
     return MCI_OK;
   }
 
+  // ---- label smoothing after the interpolation (examples/mciExample.cxx:29-39) ----------------
+  static int median_into(mci_ctx * ctx, const void * src, void * dst, int radius)
+  {
+    if (radius == 0)
+    {
+      CK(cudaMemcpyAsync(dst, src, ctx->nvox * (ctx->ptype == MCI_U8 ? 1 : 2), cudaMemcpyDeviceToDevice, ctx->L.stream));
+      return MCI_OK;
+    }
+    CK(ctx->dMedTiles.ensure(size_t(median_tile_count(ctx->dims)) * sizeof(unsigned)));
+    launch_median3d(ctx->L, ctx->ptype, src, dst, ctx->dims, radius, (unsigned *)ctx->dMedTiles.p);
+    return MCI_OK;
+  }
+
+  int mci_median_filter_resident(mci_ctx * ctx, int radius)
+  {
+    if (!ctx || !ctx->dOut)
+      return MCI_ERR_ARG;
+    if (radius < 0 || radius > 3)
+      return fail(ctx, MCI_ERR_ARG, "median filter radius must be in [0, 3]");
+    CK(cudaSetDevice(ctx->device));
+    const size_t bytes = ctx->nvox * (ctx->ptype == MCI_U8 ? 1 : 2);
+    CK(ctx->ownTmp.ensure(bytes + 16));
+    int rc = median_into(ctx, ctx->dOut, ctx->ownTmp.p, radius);
+    if (rc)
+      return rc;
+    if (ctx->dOut == ctx->ownOut.p)
+    {
+      std::swap(ctx->ownOut, ctx->ownTmp); // the smoothed volume becomes the output; no copy
+      ctx->dOut = ctx->ownOut.p;
+    }
+    else
+      CK(cudaMemcpyAsync(ctx->dOut, ctx->ownTmp.p, bytes, cudaMemcpyDeviceToDevice, ctx->L.stream)); // caller-owned output
+    ctx->haveEmit = false;
+    return MCI_OK;
+  }
+
+  int mci_median_filter_run(mci_ctx * ctx, const void * host_in, void * host_out, const int64_t dims[3], int ptype, int radius)
+  {
+    if (!ctx || !host_in || !host_out)
+      return MCI_ERR_ARG;
+    if (radius < 0 || radius > 3)
+      return fail(ctx, MCI_ERR_ARG, "median filter radius must be in [0, 3]");
+    int rc = mci_upload_volume(ctx, host_in, dims, ptype);
+    if (rc)
+      return rc;
+    rc = median_into(ctx, ctx->dIn, ctx->dOut, radius);
+    if (rc)
+      return rc;
+    return mci_download_volume(ctx, host_out);
+  }
+
   // ---- slice detection ------------------------------------------------------------------------
   int mci_detect_slices(mci_ctx * ctx, int axis, int32_t * n_labels, int32_t * n_labeled_slices)
   {
@@ -473,11 +593,15 @@ extern "C"
     CK(ctx->hRes.ensure(kResBytes));
     uint8_t * hr = (uint8_t *)ctx->hRes.p;
     int * h = (int *)hr;
-    CK(cudaMemcpyAsync(h, ctx->dCounters.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(hr + kResLabelsOff, ctx->dLabels.p, size_t(std::min(nl, kSpecLabels)) * sizeof(mci_label_info),
-                       cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(hr + kResSlicesOff, ctx->dLabeledSlices.p, size_t(kSpecSlices) * sizeof(mci_labeled_slice),
-                       cudaMemcpyDeviceToHost, s));
+    {
+      TableCopy tc;
+      tc.add(h, ctx->dCounters.p, 2 * sizeof(int));
+      tc.add(hr + kResLabelsOff, ctx->dLabels.p, size_t(std::min(nl, kSpecLabels)) * sizeof(mci_label_info), (int *)ctx->dCounters.p,
+             sizeof(mci_label_info));
+      tc.add(hr + kResSlicesOff, ctx->dLabeledSlices.p, size_t(kSpecSlices) * sizeof(mci_labeled_slice), (int *)ctx->dCounters.p + 1,
+             sizeof(mci_labeled_slice));
+      tc.launch(ctx->L);
+    }
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     if (h[1] > capSlices)
@@ -623,7 +747,11 @@ extern "C"
     CK(ctx->hStage.ensure(blob.bytes.size()));
     std::memcpy(ctx->hStage.p, blob.bytes.data(), blob.bytes.size());
     cudaStream_t s = ctx->L.stream;
-    CK(cudaMemcpyAsync(ctx->dSliceBlob.p, ctx->hStage.p, blob.bytes.size(), cudaMemcpyHostToDevice, s));
+    {
+      TableCopy tc;
+      tc.add(ctx->dSliceBlob.p, ctx->hStage.p, blob.bytes.size());
+      tc.launch(ctx->L);
+    }
     ctx->dSlices = (SliceDev *)((uint8_t *)ctx->dSliceBlob.p + oS);
     RowTile * dTiles = (RowTile *)((uint8_t *)ctx->dSliceBlob.p + oT);
     ctx->statCap = (int)std::min<u64>(compBound, 2u << 20);
@@ -745,7 +873,11 @@ extern "C"
     CK(ctx->hStage2.ensure(blob.bytes.size()));
     std::memcpy(ctx->hStage2.p, blob.bytes.data(), blob.bytes.size());
     cudaStream_t s = ctx->L.stream;
-    CK(cudaMemcpyAsync(ctx->dSegBlob.p, ctx->hStage2.p, blob.bytes.size(), cudaMemcpyHostToDevice, s));
+    {
+      TableCopy tc;
+      tc.add(ctx->dSegBlob.p, ctx->hStage2.p, blob.bytes.size());
+      tc.launch(ctx->L);
+    }
     u64 tsize = 1 << 14;
     while (tsize < 4 * bound && tsize < (1ull << 27))
       tsize <<= 1;
@@ -800,19 +932,25 @@ extern "C"
     CK(ctx->hRes.ensure(kResBytes));
     uint8_t * hr = (uint8_t *)ctx->hRes.p;
     int * hn = (int *)(hr + kResNcompOff);
-    CK(cudaMemcpyAsync(hn, ctx->dNcomp.p, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(hn + kSpecNcomp, ctx->dCompBase.p, size_t(n) * 4, cudaMemcpyDeviceToHost, s));
     int * hc = (int *)hr + 4; // [4]: pair count
     const int specPairs = nseg > 0 ? std::min(kSpecPairs, ctx->capPairs) : 0;
     const int specStats = std::min(kSpecStats, ctx->statCap);
+    {
+      TableCopy tc;
+      tc.add(hn, ctx->dNcomp.p, size_t(n) * 4);
+      tc.add(hn + kSpecNcomp, ctx->dCompBase.p, size_t(n) * 4);
+      tc.add(hr + kResStatsOff, ctx->dStats.p, size_t(specStats) * sizeof(CompStat), (int *)ctx->dTotal.p, sizeof(CompStat));
+      tc.launch(ctx->L);
+    }
     if (nseg > 0)
     {
-      CK(cudaMemcpyAsync(hc, ctx->dCounters.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-      CK(cudaMemcpyAsync(hr + kResPairsOff, ctx->dPairs.p, size_t(specPairs) * sizeof(mci_pair), cudaMemcpyDeviceToHost, s));
+      TableCopy tc;
+      tc.add(hc, ctx->dCounters.p, sizeof(int));
+      tc.add(hr + kResPairsOff, ctx->dPairs.p, size_t(specPairs) * sizeof(mci_pair), (int *)ctx->dCounters.p, sizeof(mci_pair));
+      tc.launch(ctx->L);
     }
     else
       *hc = 0;
-    CK(cudaMemcpyAsync(hr + kResStatsOff, ctx->dStats.p, size_t(specStats) * sizeof(CompStat), cudaMemcpyDeviceToHost, s));
     rc = check_device_error(ctx);
     if (rc)
       return rc;
@@ -1103,10 +1241,22 @@ extern "C"
     Blob blob;
     const size_t oRefs = blob.add(refs), oExtract = blob.add(extracts), oAlign = blob.add(aligns), oSplit = blob.add(splits),
                  oRoots = blob.add(roots);
+    std::vector<int> lc(maxDepth + 2, 0);
+    lc[0] = nRootNodes;
+    const std::vector<unsigned long long> top(1, arenaWords);
+    const size_t oLc = blob.add(lc), oTop = blob.add(top);
     CK(ctx->dJobBlob.ensure(blob.bytes.size()));
     CK(ctx->hStage.ensure(blob.bytes.size()));
+    CK(ctx->dLevelCounts.ensure(size_t(maxDepth + 2) * sizeof(int)));
+    CK(ctx->dArenaTop.ensure(8));
     std::memcpy(ctx->hStage.p, blob.bytes.data(), blob.bytes.size());
-    CK(cudaMemcpyAsync(ctx->dJobBlob.p, ctx->hStage.p, blob.bytes.size(), cudaMemcpyHostToDevice, s));
+    {
+      TableCopy tc;
+      tc.add(ctx->dJobBlob.p, ctx->hStage.p, blob.bytes.size());
+      tc.add(ctx->dLevelCounts.p, (uint8_t *)ctx->hStage.p + oLc, lc.size() * sizeof(int));
+      tc.add(ctx->dArenaTop.p, (uint8_t *)ctx->hStage.p + oTop, 8);
+      tc.launch(ctx->L);
+    }
     uint8_t * jb = (uint8_t *)ctx->dJobBlob.p;
     MaskRef * dRefs = (MaskRef *)(jb + oRefs);
     CK(ctx->dArena.ensure(arenaCap * 4));
@@ -1116,7 +1266,6 @@ extern "C"
     for (long long c : levelCap)
       nodeTotal += c;
     CK(ctx->dNodes.ensure(size_t(nodeTotal + 1) * sizeof(Node)));
-    CK(ctx->dLevelCounts.ensure(size_t(maxDepth + 2) * sizeof(int)));
     CK(ctx->dEmit.ensure(16 + size_t(nodeTotal + 1) * sizeof(EmitRec)));
     CK(cudaMemsetAsync(ctx->dEmit.p, 0, 16, s));
     ctx->emitCap = (int)nodeTotal;
@@ -1124,13 +1273,6 @@ extern "C"
     ctx->haveEmit = true;
     EmitRec * dEmitRecs = (EmitRec *)((uint8_t *)ctx->dEmit.p + 16);
     int * dEmitCount = (int *)ctx->dEmit.p;
-    CK(ctx->dArenaTop.ensure(8));
-    // bitmaps of the global-scratch Align jobs must start cleared (the kernel clears them itself as well)
-    std::vector<int> lc(maxDepth + 2, 0);
-    lc[0] = nRootNodes;
-    CK(cudaMemcpyAsync(ctx->dLevelCounts.p, lc.data(), lc.size() * sizeof(int), cudaMemcpyHostToDevice, s));
-    unsigned long long top = arenaWords;
-    CK(cudaMemcpyAsync(ctx->dArenaTop.p, &top, 8, cudaMemcpyHostToDevice, s));
 
     // ---- launches
     launch_extract(ctx->L, ctx->dSlices, (ExtractJob *)(jb + oExtract), (int)extracts.size(), (uint16_t *)ctx->dConn.p,

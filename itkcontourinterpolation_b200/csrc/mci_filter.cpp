@@ -519,7 +519,9 @@ extern "C"
       if (!ctxs[c])
         return MCI_ERR_ARG;
     // one worker per context; volumes are handed out in order, so with n_ctx in flight the copy engines of both
-    // directions and the SMs are busy at the same time
+    // directions and the SMs are busy at the same time.  (What makes this work: the small descriptor / result tables
+    // of a run never enter a copy-engine queue -- mci_cabi.cu, TableCopy -- so a context in its compute phase is not
+    // held up behind another context's 100+ MB volume copy.)
     std::atomic<int32_t> next(0);
     std::atomic<int> firstError(MCI_OK);
     auto worker = [&](int32_t c) {

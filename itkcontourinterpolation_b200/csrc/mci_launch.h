@@ -120,6 +120,8 @@ struct DtLevel
 };
 void launch_dt_level(Launch & L, int ptype, const DtLevel & lv);
 
+long long median_tile_count(const long long dims[3]);
+void launch_median3d(Launch & L, int ptype, const void * in, void * out, const long long dims[3], int radius, unsigned * summary);
 void launch_combine_max(Launch & L, int ptype, void * dst, const void * src, long long n);
 void launch_detect(Launch & L, int ptype, const void * in, void * out, const long long dims[3], int axisSel, int * bbox, int nl,
                    uint32_t * sliceBits, int wordsPerLabel, int wo1, int wo2, uint32_t * chunkBits);

@@ -228,3 +228,49 @@ class VolumeSeriesInterpolator:
                 buf = (ctypes.c_char * self._nbytes).from_address(self._out[k])
                 outs.append(np.frombuffer(buf, dtype=self._dtype).reshape(self._shape).copy())
         return outs
+
+
+def _dims(vol):
+    return (ctypes.c_int64 * 3)(vol.shape[2], vol.shape[1], vol.shape[0])
+
+
+def _checked_volume(vol):
+    vol = np.ascontiguousarray(vol)
+    if vol.ndim != 3 or vol.dtype not in _PTYPE:
+        raise TypeError("expected a 3-D uint8/uint16/int16 label volume indexed [z, y, x]")
+    return vol
+
+
+def median_image_filter(vol, radius=1, device=0):
+    """itk::MedianImageFilter with SetRadius(radius) -- the label smoothing the reference's example applies to the
+    interpolator's output (examples/mciExample.cxx:29-39): box neighbourhood (2r+1)^3, ZeroFluxNeumann boundary."""
+    vol = _checked_volume(vol)
+    f = MorphologicalContourInterpolator(device)
+    try:
+        out = np.empty_like(vol)
+        f._check(f._lib.mci_median_filter_run(f._ctx, vol.ctypes.data, out.ctypes.data, _dims(vol), _PTYPE[vol.dtype], int(radius)))
+        return out
+    finally:
+        f.close()
+
+
+def interpolate_and_smooth(vol, smoothing_radius=2, device=0, **options):
+    """The whole of examples/mciExample.cxx: interpolate with the filter's settings (keyword names of
+    mci_filter_options, e.g. axis=2, use_distance_transform=0), then median-smooth with `smoothing_radius` -- the
+    interpolated volume stays in HBM between the two steps."""
+    vol = _checked_volume(vol)
+    f = MorphologicalContourInterpolator(device)
+    try:
+        for k, v in options.items():
+            if not hasattr(f._opt, k) or k.startswith("shard"):
+                raise TypeError("unknown filter option %r" % k)
+            setattr(f._opt, k, int(v))
+        f._upload(vol)
+        st = L.FilterStats()
+        f._check(f._lib.mci_filter_run_resident(f._ctx, ctypes.byref(f._opt), None, 0, ctypes.byref(st)))
+        f._check(f._lib.mci_median_filter_resident(f._ctx, int(smoothing_radius)))
+        out = np.empty_like(vol)
+        f._check(f._lib.mci_download_volume(f._ctx, out.ctypes.data))
+        return out
+    finally:
+        f.close()

@@ -40,9 +40,9 @@ class Stats(ctypes.Structure):
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "mci_oracle.cpp")
-    have_src = os.path.exists(src)
-    if force or not os.path.exists(_SO) or (have_src and os.path.getmtime(_SO) < os.path.getmtime(src)):
+    srcs = [os.path.join(_HERE, n) for n in ("mci_oracle.cpp", "median_filter_oracle.cpp")]
+    have_src = all(os.path.exists(s) for s in srcs)
+    if force or not os.path.exists(_SO) or (have_src and os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs)):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
 
@@ -72,6 +72,9 @@ def lib():
         L.mci_oracle_median.restype = ctypes.c_int
         L.mci_oracle_median.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.mci_oracle_median_image_filter.restype = ctypes.c_int
+        L.mci_oracle_median_image_filter.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.c_int,
+                                                     ctypes.c_int, ctypes.c_int]
         _lib = L
     return _lib
 
@@ -145,3 +148,15 @@ def median(i_mask, j_mask, dtype=np.uint16, use_distance_transform=True, use_bal
     if rc != 0:
         raise OracleError(lib().mci_oracle_last_error().decode())
     return o
+
+
+def median_image_filter(vol, radius=1, threads=1):
+    """itk::MedianImageFilter with SetRadius(radius), as examples/mciExample.cxx:29-39 applies it (restated)."""
+    vol = np.ascontiguousarray(vol)
+    assert vol.ndim == 3 and vol.dtype in PTYPES
+    out = np.empty_like(vol)
+    dims = (ctypes.c_int64 * 3)(vol.shape[2], vol.shape[1], vol.shape[0])
+    rc = lib().mci_oracle_median_image_filter(vol.ctypes.data, out.ctypes.data, dims, PTYPES[vol.dtype], int(radius), int(threads))
+    if rc != 0:
+        raise OracleError("median_image_filter: bad arguments (%d)" % rc)
+    return out

@@ -97,3 +97,10 @@ ALGOS = {"T": dict(use_distance_transform=True, use_ball=True),   # test driver:
          "B": dict(use_distance_transform=False, use_ball=True),
          "C": dict(use_distance_transform=False, use_ball=False),
          "D": dict(use_distance_transform=True, use_ball=False)}   # filter defaults
+
+# argument sets of the reference's regression tests on 64816L_amygdala_int (test/CMakeLists.txt:143-160): (axis, label)
+AMYGDALA_ARGS = [(-1, 0), (0, 0), (1, 0), (2, 0)] + [(a, l) for a in (0, 1, 2) for l in (1, 2, 3, 4)]
+
+
+def amygdala():
+    return np.load(os.path.join(GOLDEN, "64816L_amygdala_int.npz"))["vol"]

@@ -4,6 +4,8 @@
 // available): the pytest side converts fixtures and compares the written output with the oracle.
 //
 //   mci_filter_test inputRaw outputRaw X Y Z uchar|ushort|short [algorithm B|C|T|D] [axis] [label]
+//   mci_filter_test --example inputRaw outputRaw X Y Z uchar|ushort|short [smoothingRadius=2]
+//                                the reference's example program (examples/mciExample.cxx): interpolate, median-smooth
 //   mci_filter_test --api        interface checks that need no GPU (defaults, Modified(), error behaviour)
 #include <cctype>
 #include <cstdio>
@@ -73,6 +75,32 @@ doTest(const std::string & inFilename, const std::string & outFilename, size_t x
     for (const auto & kv : indices[a])
       for (auto s : kv.second)
         std::cout << a << " " << long(kv.first) << " " << long(s) << "\n";
+}
+
+// examples/mciExample.cxx:17-45 on raw files
+template <typename ImageType>
+void
+doExample(const std::string & inFilename, const std::string & outFilename, size_t x, size_t y, size_t z, int smoothingRadius)
+{
+  typename ImageType::Pointer image = readRaw<ImageType>(inFilename, x, y, z);
+
+  using mciType = mci_b200::MorphologicalContourInterpolator<ImageType>;
+  typename mciType::Pointer mci = mciType::New();
+  mci->SetInput(image);
+  mci->Update();
+
+  using MedianType = mci_b200::MedianImageFilter<ImageType, ImageType>;
+  typename MedianType::Pointer medF = MedianType::New();
+  medF->SetInput(mci->GetOutput());
+  medF->SetRadius(smoothingRadius);
+  medF->Update();
+
+  typename ImageType::Pointer out = medF->GetOutput();
+  std::ofstream               f(outFilename, std::ios::binary);
+  f.write(reinterpret_cast<const char *>(out->GetBufferPointer()),
+          std::streamsize(out->GetNumberOfPixels() * sizeof(typename ImageType::PixelType)));
+  if (!f)
+    throw mci_b200::ExceptionObject(MCI_ERR_ARG, "cannot write " + outFilename);
 }
 
 #define EXPECT(cond)                                                                                                           \
@@ -166,6 +194,27 @@ main(int argc, char * argv[])
 {
   if (argc == 2 && std::string(argv[1]) == "--api")
     return apiChecks();
+  if (argc >= 8 && std::string(argv[1]) == "--example")
+  {
+    const std::string type = argv[7];
+    const size_t      x = std::strtoul(argv[4], nullptr, 10), y = std::strtoul(argv[5], nullptr, 10), z = std::strtoul(argv[6], nullptr, 10);
+    const int         smoothingRadius = argc >= 9 ? std::stoi(argv[8]) : 2;
+    try
+    {
+      if (type == "uchar")
+        doExample<mci_b200::Image<unsigned char, 3>>(argv[2], argv[3], x, y, z, smoothingRadius);
+      else if (type == "ushort")
+        doExample<mci_b200::Image<unsigned short, 3>>(argv[2], argv[3], x, y, z, smoothingRadius);
+      else
+        doExample<mci_b200::Image<short, 3>>(argv[2], argv[3], x, y, z, smoothingRadius);
+    }
+    catch (mci_b200::ExceptionObject & exc)
+    {
+      std::cerr << exc.what() << std::endl;
+      return EXIT_FAILURE;
+    }
+    return EXIT_SUCCESS;
+  }
   if (argc < 7)
   {
     std::cerr << "Usage: " << argv[0] << " inputRaw outputRaw X Y Z uchar|ushort|short [algorithm] [axis] [label]\n"

@@ -34,6 +34,10 @@ def main():
         from itkcontourinterpolation_b200.nrrd import read_nrrd
         for f in ("SevenLabels", "ManyToMany"):
             np.save(os.path.join(gold, f + ".npy"), read_nrrd(os.path.join(ref, f + ".nrrd")))
+    nii = "/root/reference/wasm/test/data/input/64816L_amygdala_int.nii.gz"
+    if os.path.exists(nii):
+        from itkcontourinterpolation_b200.nifti import read_nifti
+        np.savez_compressed(os.path.join(gold, "64816L_amygdala_int.npz"), vol=read_nifti(nii))  # int16, 170x400x210
     table = {}
     inputs = {"SevenLabels": np.load(os.path.join(gold, "SevenLabels.npy")),
               "ManyToMany": np.load(os.path.join(gold, "ManyToMany.npy"))}
@@ -46,6 +50,14 @@ def main():
     for name, (vol, cfg) in cases.synthetic_small().items():
         out = O.interpolate(vol, axis=cfg.get("axis", -1), use_distance_transform=cfg["use_dt"], use_ball=cfg["ball"])
         table["synthetic_%s" % name] = dict(input=sha(vol), output=sha(out), shape=list(vol.shape), dtype=str(vol.dtype))
+    # the reference's regression matrix for 64816L_amygdala_int (test/CMakeLists.txt:143-160): algorithms B, C, T x
+    # {all axes, axis a, axis a + label l}, read as Image<short,3> like its driver does (test/...Test.cxx:110-114)
+    amy = np.load(os.path.join(gold, "64816L_amygdala_int.npz"))["vol"]
+    for algo in "BCT":
+        for axis, label in cases.AMYGDALA_ARGS:
+            out = O.interpolate(amy, axis=axis, label=label, threads=os.cpu_count() or 1, **cases.ALGOS[algo])
+            table["64816L_amygdala_int_%s_%d_%d" % (algo, axis, label)] = dict(input=sha(amy), output=sha(out),
+                                                                                shape=list(amy.shape), dtype=str(amy.dtype))
     with open(os.path.join(gold, "golden.json"), "w") as f:
         json.dump(table, f, indent=1, sort_keys=True)
     print("wrote", len(table), "entries")

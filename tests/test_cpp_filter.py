@@ -79,3 +79,18 @@ def test_regression_matrix_through_the_cpp_class(driver, tmp_path, seven_labels,
     for label in (5, 9, 77):
         out, _ = run_driver(driver, tmp_path, vol, "C", -1, label)
         assert np.array_equal(out, O.interpolate(vol, label=label, **DRIVER_ALGOS["C"])), label
+
+
+@pytest.mark.gpu
+def test_example_program_interpolate_then_median_smooth(driver, tmp_path, seven_labels, many_to_many):
+    # examples/mciExample.cxx: Image<unsigned char, 3>, default settings, MedianImageFilter radius 2 (default) or given
+    from oracle import oracle_lib as O
+    for vol, radius in ((seven_labels.astype(np.uint8), None), (many_to_many.astype(np.uint8), 1), (many_to_many, 3)):
+        src, dst = tmp_path / "in.raw", tmp_path / "out.raw"
+        vol.tofile(src)
+        z, y, x = vol.shape
+        cmd = [driver, "--example", str(src), str(dst), str(x), str(y), str(z), TYPE[vol.dtype]] + ([str(radius)] if radius else [])
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        got = np.fromfile(dst, vol.dtype).reshape(vol.shape)
+        assert np.array_equal(got, O.median_image_filter(O.interpolate(vol), radius or 2))

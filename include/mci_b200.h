@@ -53,6 +53,10 @@ int64_t mci_launch_count(const mci_ctx * ctx);
 /* CUDA stream the context launches on (cudaStream_t as void*), for callers that time with events */
 void * mci_stream(const mci_ctx * ctx);
 int mci_synchronize(mci_ctx * ctx);
+/* How the host thread waits for the bulk volume copies (100+ MB, milliseconds): 0 (default) = spin, lowest latency
+ * for one volume at a time; 1 = sleep on a blocking event, for when several contexts / ranks share the host cores
+ * (mci_filter_run_batch sets it on its contexts).  Short waits (kernel phases) always spin. */
+int mci_set_wait_mode(mci_ctx * ctx, int sleep_on_bulk_copies);
 /* per-kernel device times, CUDA events recorded on the launching stream around every launch while enabled */
 typedef struct
 {

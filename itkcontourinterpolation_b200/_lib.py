@@ -87,6 +87,7 @@ SYMBOLS = [
     ("mci_launch_count", ctypes.c_int64, [_P]),
     ("mci_stream", _P, [_P]),
     ("mci_synchronize", _I, [_P]),
+    ("mci_set_wait_mode", _I, [_P, _I]),
     ("mci_profile_enable", _I, [_P, _I]),
     ("mci_profile_read", _I, [_P, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
     ("mci_upload_volume", _I, [_P, _P, ctypes.POINTER(ctypes.c_int64), _I]),

@@ -139,6 +139,11 @@ struct mci_ctx
   // second stream: 1-to-N splits run beside the alignment of the other jobs
   cudaStream_t stream2 = nullptr;
   cudaEvent_t evAlignedSplits = nullptr, evSplitDone = nullptr;
+  // bulk volume copies are waited for with a BLOCKING event (the host thread sleeps for the milliseconds they take
+  // instead of spinning: several contexts / ranks share the host cores); everything else spin-waits for latency
+  cudaEvent_t evBulk = nullptr;
+  bool bulkPending = false;
+  bool sleepOnBulk = false; // mci_set_wait_mode
   // error flag
   int * dErr = nullptr;
 };
@@ -167,7 +172,7 @@ static const size_t kResBytes = kResStatsOff + size_t(kSpecStats) * sizeof(mci::
 // Descriptor blobs (host -> device) and result tables (device -> host) cross PCIe through MAPPED pinned memory with
 // SM loads / stores, never through the copy engines: a copy engine serves its queue in submission order, so with
 // several volumes in flight (mci_filter_run_batch) a 100-byte table copy would wait behind another context's
-// 100+ MB volume copy, milliseconds each time.  Up to four segments per launch; a segment may be bounded by an element
+// 100+ MB volume copy, milliseconds each time.  Up to six segments per launch; a segment may be bounded by an element
 // count that lives on the device, so speculative fixed-size transfers are not needed.
 struct TableSeg
 {
@@ -179,7 +184,7 @@ struct TableSeg
 };
 struct TableSegs
 {
-  TableSeg s[4];
+  TableSeg s[6];
   int n;
 };
 __global__ void __launch_bounds__(256) k_table_copy(TableSegs t)
@@ -231,12 +236,14 @@ fail(mci_ctx * ctx, int code, const std::string & msg)
   return code;
 }
 
+// tc: result tables of the phase that ride along in the same launch as the error flag
 static int
-check_device_error(mci_ctx * ctx)
+check_device_error(mci_ctx * ctx, TableCopy * riders = nullptr)
 {
   CK(ctx->hErr.ensure(64));
   {
-    TableCopy tc;
+    TableCopy own;
+    TableCopy & tc = riders ? *riders : own;
     tc.add(ctx->hErr.p, ctx->dErr, sizeof(int));
     tc.launch(ctx->L);
   }
@@ -307,6 +314,7 @@ extern "C"
     cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&ctx->evAlignedSplits, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->evSplitDone, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->evBulk, cudaEventDisableTiming | cudaEventBlockingSync);
     *out = ctx;
     return MCI_OK;
   }
@@ -341,6 +349,8 @@ extern "C"
       cudaEventDestroy(ctx->evAlignedSplits);
     if (ctx->evSplitDone)
       cudaEventDestroy(ctx->evSplitDone);
+    if (ctx->evBulk)
+      cudaEventDestroy(ctx->evBulk);
     cudaStreamDestroy(ctx->L.stream);
     delete ctx;
   }
@@ -361,6 +371,14 @@ extern "C"
   }
   int64_t mci_launch_count(const mci_ctx * ctx) { return ctx ? ctx->L.count : 0; }
   void * mci_stream(const mci_ctx * ctx) { return ctx ? (void *)ctx->L.stream : nullptr; }
+  int mci_set_wait_mode(mci_ctx * ctx, int sleep_on_bulk_copies)
+  {
+    if (!ctx)
+      return MCI_ERR_ARG;
+    ctx->sleepOnBulk = sleep_on_bulk_copies != 0;
+    ctx->bulkPending = false;
+    return MCI_OK;
+  }
   int mci_synchronize(mci_ctx * ctx)
   {
     if (!ctx)
@@ -458,6 +476,11 @@ extern "C"
     ctx->dIn = ctx->ownIn.p;
     ctx->dOut = ctx->ownOut.p;
     CK(cudaMemcpyAsync(ctx->dIn, host, bytes, cudaMemcpyHostToDevice, ctx->L.stream));
+    if (ctx->sleepOnBulk && bytes >= (size_t(8) << 20))
+    {
+      CK(cudaEventRecord(ctx->evBulk, ctx->L.stream));
+      ctx->bulkPending = true;
+    }
     return MCI_OK;
   }
 
@@ -482,6 +505,12 @@ extern "C"
     CK(cudaSetDevice(ctx->device));
     size_t bytes = ctx->nvox * (ctx->ptype == MCI_U8 ? 1 : 2);
     CK(cudaMemcpyAsync(host, ctx->dOut, bytes, cudaMemcpyDeviceToHost, ctx->L.stream));
+    if (ctx->sleepOnBulk && bytes >= (size_t(8) << 20))
+    {
+      CK(cudaEventRecord(ctx->evBulk, ctx->L.stream));
+      CK(cudaEventSynchronize(ctx->evBulk)); // sleeps
+    }
+    ctx->bulkPending = false;
     return check_device_error(ctx);
   }
 
@@ -601,6 +630,11 @@ extern "C"
       tc.add(hr + kResSlicesOff, ctx->dLabeledSlices.p, size_t(kSpecSlices) * sizeof(mci_labeled_slice), (int *)ctx->dCounters.p + 1,
              sizeof(mci_labeled_slice));
       tc.launch(ctx->L);
+    }
+    if (ctx->bulkPending)
+    {
+      ctx->bulkPending = false;
+      CK(cudaEventSynchronize(ctx->evBulk)); // the upload queued ahead of the detection kernels: sleep through it
     }
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
@@ -935,23 +969,18 @@ extern "C"
     int * hc = (int *)hr + 4; // [4]: pair count
     const int specPairs = nseg > 0 ? std::min(kSpecPairs, ctx->capPairs) : 0;
     const int specStats = std::min(kSpecStats, ctx->statCap);
-    {
-      TableCopy tc;
-      tc.add(hn, ctx->dNcomp.p, size_t(n) * 4);
-      tc.add(hn + kSpecNcomp, ctx->dCompBase.p, size_t(n) * 4);
-      tc.add(hr + kResStatsOff, ctx->dStats.p, size_t(specStats) * sizeof(CompStat), (int *)ctx->dTotal.p, sizeof(CompStat));
-      tc.launch(ctx->L);
-    }
+    TableCopy tc;
+    tc.add(hn, ctx->dNcomp.p, size_t(n) * 4);
+    tc.add(hn + kSpecNcomp, ctx->dCompBase.p, size_t(n) * 4);
+    tc.add(hr + kResStatsOff, ctx->dStats.p, size_t(specStats) * sizeof(CompStat), (int *)ctx->dTotal.p, sizeof(CompStat));
     if (nseg > 0)
     {
-      TableCopy tc;
       tc.add(hc, ctx->dCounters.p, sizeof(int));
       tc.add(hr + kResPairsOff, ctx->dPairs.p, size_t(specPairs) * sizeof(mci_pair), (int *)ctx->dCounters.p, sizeof(mci_pair));
-      tc.launch(ctx->L);
     }
     else
       *hc = 0;
-    rc = check_device_error(ctx);
+    rc = check_device_error(ctx, &tc); // one launch: the five tables and the error flag
     if (rc)
       return rc;
     int acc = 0;
@@ -1030,6 +1059,7 @@ extern "C"
     std::vector<RootJob> roots(njobs);
     std::map<std::pair<int, int>, MaskRef> compMasks;
     u64 arenaWords = 0, scratchWords = 0;
+    int maxSplitWords = 0;
     const int alignSmemCap = 150 * 1024; // bitmap + queue; the kernel adds 48 KB for staging the shapes
     int alignSmem = 0;
     int nRootNodes = 0;
@@ -1160,6 +1190,7 @@ extern "C"
           sp.pad = 0;
           sp.scratchOff = scratchWords;
           scratchWords += (u64)jb.n_b * ma.h * ma.pitch;
+          maxSplitWords = (int)std::min<u64>(std::max<u64>((u64)maxSplitWords, (u64)ma.h * ma.pitch), 1u << 20);
           R.splitRef = sp.outRef;
           for (int q = 0; q < jb.n_b; ++q)
           {
@@ -1287,7 +1318,7 @@ extern "C"
       CK(cudaStreamWaitEvent(ctx->stream2, ctx->evAlignedSplits, 0));
       ctx->L.stream = ctx->stream2;
       launch_split(ctx->L, (SplitJob *)(jb + oSplit), (int)splits.size(), dRefs, (uint32_t *)ctx->dArena.p,
-                   (uint32_t *)ctx->dScratch.p, (int2 *)ctx->dTrans.p, prm->use_ball, ctx->dErr);
+                   (uint32_t *)ctx->dScratch.p, (int2 *)ctx->dTrans.p, prm->use_ball, maxSplitWords, ctx->dErr);
       ctx->L.stream = s;
       CK(cudaEventRecord(ctx->evSplitDone, ctx->stream2));
     }

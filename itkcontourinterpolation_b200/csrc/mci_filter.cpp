@@ -540,6 +540,8 @@ extern "C"
       }
     };
     const int32_t nWorkers = nCtx < nVolumes ? nCtx : nVolumes;
+    for (int32_t c = 0; c < nWorkers; ++c)
+      mci_set_wait_mode(ctxs[c], nWorkers > 1); // several host threads: sleep through the bulk copies instead of spinning
     std::vector<std::thread> threads;
     for (int32_t c = 1; c < nWorkers; ++c)
       threads.emplace_back(worker, c);
@@ -547,6 +549,8 @@ extern "C"
       worker(0);
     for (std::thread & t : threads)
       t.join();
+    for (int32_t c = 0; c < nWorkers; ++c)
+      mci_set_wait_mode(ctxs[c], 0);
     return firstError.load();
   }
 

@@ -1116,26 +1116,50 @@ k_split(const SplitJob * __restrict__ jobs, const MaskRef * __restrict__ refs, u
   bool curIsFirst = true;
   unsigned settled = 0; // bit j: my j-th word has no free pixel left and both buffers hold its final planes
   int pending = 1;
+  // the nB planes of either buffer are contiguous (stride `words`): shared memory, or the arena planes of the output
+  // refs (allocated back to back) and the job's scratch planes
+  uint32_t * const firstBuf = plane(true, true, 0);
+  uint32_t * const secondBuf = plane(false, true, 0);
+  // row / word / mask of my first word stay in registers: shapes up to blockDim.x words (the usual case, the launcher
+  // sizes the CTA for it) never divide inside the loop
+  const int idx0 = threadIdx.x;
+  const bool has0 = idx0 < words;
+  const int r0 = has0 ? idx0 / A.pitch : 0, wi0 = has0 ? idx0 - r0 * A.pitch : 0;
+  const uint32_t m0 = has0 ? mask[idx0] : 0u;
   for (int step = 0; step < maxSteps && pending; ++step)
   {
+    const uint32_t * C = curIsFirst ? firstBuf : secondBuf;
+    uint32_t * N = curIsFirst ? secondBuf : firstBuf;
     int flag = 0;
     int j = 0;
-    for (int idx = threadIdx.x; idx < words; idx += blockDim.x, ++j)
+    for (int idx = idx0; idx < words; idx += blockDim.x, ++j)
     {
       if (j < 32 && ((settled >> j) & 1u))
         continue;
-      int r = idx / A.pitch, wi = idx % A.pitch;
-      uint32_t m = mask[idx];
+      int r, wi;
+      uint32_t m;
+      if (j == 0)
+      {
+        r = r0;
+        wi = wi0;
+        m = m0;
+      }
+      else
+      {
+        r = idx / A.pitch;
+        wi = idx - r * A.pitch;
+        m = mask[idx];
+      }
       uint32_t owned = 0;
       for (int k = 0; k < nB; ++k)
-        owned |= plane(true, curIsFirst, k)[idx];
-      uint32_t freeBits = m & ~owned;
+        owned |= C[(size_t)k * words + idx];
+      const uint32_t freeBits = m & ~owned;
       uint32_t taken = 0;
       for (int k = 0; k < nB; ++k)
       {
-        const uint32_t * c = plane(true, curIsFirst, k);
-        uint32_t g = freeBits ? (dilate_word(c, A.h, A.pitch, r, wi, ball != 0) & freeBits & ~taken) : 0u;
-        plane(false, curIsFirst, k)[idx] = c[idx] | g;
+        const uint32_t * c = C + (size_t)k * words;
+        const uint32_t g = freeBits ? (dilate_word(c, A.h, A.pitch, r, wi, ball != 0) & freeBits & ~taken) : 0u;
+        N[(size_t)k * words + idx] = c[idx] | g;
         taken |= g;
       }
       if (freeBits & ~taken)
@@ -1159,7 +1183,7 @@ k_split(const SplitJob * __restrict__ jobs, const MaskRef * __restrict__ refs, u
 
 void
 launch_split(Launch & L, const SplitJob * jobs, int njobs, const MaskRef * refs, uint32_t * arena, uint32_t * gscratch,
-             const int2 * trans, int ball, int * err)
+             const int2 * trans, int ball, int maxWords, int * err)
 {
   if (njobs == 0)
     return;
@@ -1171,7 +1195,9 @@ launch_split(Launch & L, const SplitJob * jobs, int njobs, const MaskRef * refs,
   }
   const int smemBytes = 160 * 1024;
   L.pre("k_split");
-  k_split<<<njobs, SPLIT_THREADS, smemBytes, L.stream>>>(jobs, refs, arena, gscratch, trans, ball, smemBytes / 4, err);
+  // one word per thread where the shapes allow it; fewer warps make the per-step barrier cheaper
+  const int threads = std::max(128, std::min(SPLIT_THREADS, (maxWords + 31) / 32 * 32));
+  k_split<<<njobs, threads, smemBytes, L.stream>>>(jobs, refs, arena, gscratch, trans, ball, smemBytes / 4, err);
   L.post("k_split");
 }
 

@@ -136,7 +136,7 @@ void launch_extract(Launch & L, const SliceDev * slices, const ExtractJob * jobs
 void launch_align(Launch & L, const AlignJob * jobs, int njobs, const MaskRef * refs, const uint32_t * arena, uint32_t * gscratch,
                   int heuristic, int2 * result, int4 * dbg, int smemBytes, int * err);
 void launch_split(Launch & L, const SplitJob * jobs, int njobs, const MaskRef * refs, uint32_t * arena, uint32_t * gscratch,
-                  const int2 * trans, int ball, int * err);
+                  const int2 * trans, int ball, int maxWords, int * err);
 void launch_make_roots(Launch & L, const RootJob * roots, int nroots, MaskRef * refs, uint32_t * arena, const int2 * trans,
                        Node * nodes);
 void launch_nodes(Launch & L, int ptype, const Node * nodes, const int * count, int maxNodes, Node * next, int * nextCount,

@@ -16,6 +16,7 @@
 //      the cumulative count passes n/2.
 // Results are staged in shared memory and stored with 16-byte vectors.  Algorithmic traffic: s*N read + s*N written.
 #include <algorithm>
+#include <type_traits>
 
 #include "mci_launch.h"
 
@@ -113,33 +114,74 @@ __global__ void __launch_bounds__(MED_THREADS) k_median_tiles(const T * __restri
   }
 }
 
+constexpr int MED_DMAX = 4;  // tiles with up to this many distinct values take the bit-mask path
+constexpr int MED_PADL = 8;  // a staged row holds x in [x0 - 8, x0 + 40): 48 pixels, 16-byte aligned in global memory
+constexpr int MED_RW = 48;
+
 template <typename T, int R>
 __global__ void __launch_bounds__(MED_THREADS) k_median3d(const T * __restrict__ in, T * __restrict__ out, int X, int Y, int Z,
                                                           int tilesX, int tilesY, int tilesZ, const unsigned * __restrict__ summary)
 {
-  constexpr int HX = MED_TX + 2 * R, HY = MED_TY + 2 * R, HZ = MED_TZ + 2 * R;
-  constexpr int HXP = HX + 1;               // row pitch in 16-bit units; odd in 32-bit words for the row-per-thread pass below
+  constexpr int HY = MED_TY + 2 * R, HZ = MED_TZ + 2 * R;
   constexpr int NROWS = HY * HZ;            // halo rows
+  constexpr int C0 = MED_PADL - R;          // column of the window's first pixel for output ox = 0
   constexpr int NWIN = (2 * R + 1) * (2 * R + 1) * (2 * R + 1);
   constexpr int KTH = NWIN / 2;             // 0-based rank of the median (std::nth_element at begin + size / 2)
-  __shared__ uint16_t raw[HZ * HY * HXP];
-  __shared__ unsigned long long eX[NROWS], eY[NROWS], eZ[NROWS]; // bit hx: value change between hx and its +x / +y / +z neighbour
-  __shared__ unsigned long long aX[HZ * MED_TY], aY[HZ * MED_TY], aZ[HZ * MED_TY]; // OR over the window's y range
-  __shared__ unsigned long long bX[MED_TZ * MED_TY], bM[MED_TZ * MED_TY];          // ... and over its z range
+  constexpr unsigned long long WMASK = (1ull << (2 * R + 1)) - 1ull;
+  typedef unsigned long long u64;
+  __shared__ __align__(16) uint16_t raw[NROWS * MED_RW];
+  __shared__ u64 vm[(MED_DMAX - 1) * NROWS];      // vm[k][row] bit c: pixel (row, c) holds the k-th smallest value of the tile
+  __shared__ u64 eX[NROWS], eY[NROWS], eZ[NROWS]; // bit c: value change between column c and its +x / +y / +z neighbour
+  __shared__ u64 aX[HZ * MED_TY], aY[HZ * MED_TY], aZ[HZ * MED_TY]; // OR over the window's y range
+  __shared__ u64 bX[MED_TZ * MED_TY], bM[MED_TZ * MED_TY];          // ... and over its z range
   __shared__ uint16_t res[MED_TZ * MED_TY * MED_TX];
   __shared__ uint16_t list[MED_TZ * MED_TY * MED_TX];
   __shared__ int listCount;
+  __shared__ int sLo, sHi, sNext[MED_DMAX];
 
-  const int tid = threadIdx.x;
-  const long long tile = blockIdx.x;
-  const int tx = (int)(tile % tilesX), ty = (int)((tile / tilesX) % tilesY), tz = (int)(tile / ((long long)tilesX * tilesY));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned tile = blockIdx.x;
+  const int tx = (int)(tile % (unsigned)tilesX), ty = (int)((tile / (unsigned)tilesX) % (unsigned)tilesY),
+            tz = (int)(tile / ((unsigned)tilesX * (unsigned)tilesY));
   const int x0 = tx * MED_TX, y0 = ty * MED_TY, z0 = tz * MED_TZ;
   const long long XY = (long long)X * Y;
   if (tid == 0)
+  {
     listCount = 0;
-  const int ox = tid & 31, orow0 = tid >> 5; // output voxel (ox, row) with row = oy + MED_TY * oz, rows orow0, orow0 + 8, ...
+    sLo = 0x10000;
+    sHi = -1;
+    for (int k = 0; k < MED_DMAX; ++k)
+      sNext[k] = 0x10000;
+  }
+  const int ox = lane, orow0 = warp; // output voxel (ox, row) with row = oy + MED_TY * oz, rows orow0, orow0 + 8, ...
   constexpr int VEC = 16 / (int)sizeof(T);
   const bool vecOk = (X % VEC) == 0 && x0 + MED_TX <= X && (reinterpret_cast<size_t>(out) & 15) == 0;
+
+  // stores one value to the whole tile
+  auto storeConstant = [&](unsigned key) {
+    const T v = med_unkey<T>(key);
+    if (vecOk)
+    {
+      T tmp[VEC];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k)
+        tmp[k] = v;
+      constexpr int VPR = MED_TX / VEC;
+      for (int i = tid; i < MED_TY * MED_TZ * VPR; i += MED_THREADS)
+      {
+        const int c = i % VPR, row = i / VPR, gy = y0 + row % MED_TY, gz = z0 + row / MED_TY;
+        if (gy < Y && gz < Z)
+          __stcs(reinterpret_cast<uint4 *>(out + (long long)gz * XY + (long long)gy * X + x0 + c * VEC), *reinterpret_cast<const uint4 *>(tmp));
+      }
+    }
+    else
+      for (int row = orow0; row < MED_TY * MED_TZ; row += MED_THREADS / 32)
+      {
+        const int gy = y0 + (row % MED_TY), gz = z0 + (row / MED_TY), gx = x0 + ox;
+        if (gx < X && gy < Y && gz < Z)
+          out[(long long)gz * XY + (long long)gy * X + gx] = v;
+      }
+  };
 
   // ---- 0. the 27 tile summaries around this tile (halo <= 3 < tile extent): all one value -> constant store
   {
@@ -153,82 +195,188 @@ __global__ void __launch_bounds__(MED_THREADS) k_median3d(const T * __restrict__
     }
     if (__syncthreads_and(same) && mine != MED_MIXED)
     {
-      const T v = med_unkey<T>(mine);
-      if (vecOk)
-      {
-        T tmp[VEC];
-#pragma unroll
-        for (int k = 0; k < VEC; ++k)
-          tmp[k] = v;
-        constexpr int VPR = MED_TX / VEC;
-        for (int i = tid; i < MED_TY * MED_TZ * VPR; i += MED_THREADS)
-        {
-          const int c = i % VPR, row = i / VPR, gy = y0 + row % MED_TY, gz = z0 + row / MED_TY;
-          if (gy < Y && gz < Z)
-            __stcs(reinterpret_cast<uint4 *>(out + (long long)gz * XY + (long long)gy * X + x0 + c * VEC), *reinterpret_cast<const uint4 *>(tmp));
-        }
-      }
-      else
-        for (int row = orow0; row < MED_TY * MED_TZ; row += MED_THREADS / 32)
-        {
-          const int gy = y0 + (row % MED_TY), gz = z0 + (row / MED_TY), gx = x0 + ox;
-          if (gx < X && gy < Y && gz < Z)
-            out[(long long)gz * XY + (long long)gy * X + gx] = v;
-        }
+      storeConstant(mine);
       return;
     }
   }
 
-  // ---- 1. stage tile + halo (clamped coordinates = ZeroFluxNeumann)
-  if (x0 - R >= 0 && x0 + MED_TX + R <= X)
+  // ---- 1. stage 48-pixel rows of tile + halo as 16-bit keys (clamped coordinates = ZeroFluxNeumann)
+  if (sizeof(T) == 2 && (X % 8) == 0 && x0 >= MED_PADL && x0 - MED_PADL + MED_RW <= X && (reinterpret_cast<size_t>(in) & 15) == 0)
   {
-    // interior in x: no clamping along the row, one division per element less
-    for (int i = tid; i < HX * NROWS; i += MED_THREADS)
+    // interior in x, 16-bit pixels: six 16-byte loads per row
+    constexpr int CPR = MED_RW / 8;
+    for (int i = tid; i < NROWS * CPR; i += MED_THREADS)
     {
-      const int hx = i % HX, row = i / HX, hy = row % HY, hz = row / HY;
+      const int c = i % CPR, row = i / CPR, hy = row % HY, hz = row / HY;
       const int gy = min(max(y0 + hy - R, 0), Y - 1), gz = min(max(z0 + hz - R, 0), Z - 1);
-      raw[row * HXP + hx] = (uint16_t)med_key<T>(__ldg(in + (long long)gz * XY + (long long)gy * X + (x0 - R + hx)));
+      uint4 q = __ldg(reinterpret_cast<const uint4 *>(in + (long long)gz * XY + (long long)gy * X + (x0 - MED_PADL)) + c);
+      if (std::is_same<T, int16_t>::value)
+      {
+        q.x ^= 0x80008000u;
+        q.y ^= 0x80008000u;
+        q.z ^= 0x80008000u;
+        q.w ^= 0x80008000u;
+      }
+      reinterpret_cast<uint4 *>(raw)[i] = q;
     }
   }
   else
   {
-    for (int i = tid; i < HX * NROWS; i += MED_THREADS)
+    for (int i = tid; i < NROWS * MED_RW; i += MED_THREADS)
     {
-      const int hx = i % HX, row = i / HX, hy = row % HY, hz = row / HY;
-      const int gx = min(max(x0 + hx - R, 0), X - 1), gy = min(max(y0 + hy - R, 0), Y - 1), gz = min(max(z0 + hz - R, 0), Z - 1);
-      raw[row * HXP + hx] = (uint16_t)med_key<T>(__ldg(in + (long long)gz * XY + (long long)gy * X + gx));
+      const int c = i % MED_RW, row = i / MED_RW, hy = row % HY, hz = row / HY;
+      const int gx = min(max(x0 - MED_PADL + c, 0), X - 1), gy = min(max(y0 + hy - R, 0), Y - 1), gz = min(max(z0 + hz - R, 0), Z - 1);
+      raw[i] = (uint16_t)med_key<T>(__ldg(in + (long long)gz * XY + (long long)gy * X + gx));
     }
   }
   __syncthreads();
 
-  // ---- 2. value-change masks per halo row
-  for (int row = tid; row < NROWS; row += MED_THREADS)
+  // ---- 2. the distinct values of the staged block in ascending order, as long as there are at most MED_DMAX
+  unsigned vals[MED_DMAX], vHi;
+  int nvals;
   {
-    const int hy = row % HY, hz = row / HY;
-    const uint16_t * p = raw + row * HXP;
-    const uint16_t * py = hy + 1 < HY ? p + HXP : p;
-    const uint16_t * pz = hz + 1 < HZ ? p + HY * HXP : p;
-    unsigned long long mx = 0ull, my = 0ull, mz = 0ull;
-    unsigned v = p[0];
-#pragma unroll 4
-    for (int hx = 0; hx < HX; ++hx)
+    constexpr int NW = NROWS * MED_RW / 2; // 32-bit words, two pixels each
+    const unsigned * rw = reinterpret_cast<const unsigned *>(raw);
+    int lo = 0x10000, hi = -1;
+    for (int i = tid; i < NW; i += MED_THREADS)
     {
-      const unsigned nx = hx + 1 < HX ? p[hx + 1] : v;
-      mx |= (unsigned long long)(v != nx) << hx;
-      my |= (unsigned long long)(v != py[hx]) << hx;
-      mz |= (unsigned long long)(v != pz[hx]) << hx;
-      v = nx;
+      const unsigned w = rw[i];
+      const int a = (int)(w & 0xFFFFu), b = (int)(w >> 16);
+      lo = min(lo, min(a, b));
+      hi = max(hi, max(a, b));
     }
-    eX[row] = mx;
-    eY[row] = my;
-    eZ[row] = mz;
+    lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+    hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+    if (lane == 0)
+    {
+      atomicMin(&sLo, lo);
+      atomicMax(&sHi, hi);
+    }
+    __syncthreads();
+    lo = sLo;
+    hi = sHi;
+    if (lo == hi)
+    {
+      storeConstant((unsigned)lo); // the block inside the 27 tiles is uniform after all
+      return;
+    }
+    vals[0] = (unsigned)lo;
+    nvals = 1;
+    vHi = (unsigned)hi;
+    // values strictly between the last one found and the maximum, smallest first; round r fills vals[r]
+    bool done = false;
+#pragma unroll
+    for (int r = 1; r < MED_DMAX; ++r)
+      if (!done)
+      {
+        const int last = (int)vals[r - 1];
+        int nxt = 0x10000;
+        for (int i = tid; i < NW; i += MED_THREADS)
+        {
+          const unsigned w = rw[i];
+          const int a = (int)(w & 0xFFFFu), b = (int)(w >> 16);
+          if (a > last && a < hi)
+            nxt = min(nxt, a);
+          if (b > last && b < hi)
+            nxt = min(nxt, b);
+        }
+        nxt = __reduce_min_sync(0xFFFFFFFFu, nxt);
+        if (lane == 0 && nxt < 0x10000)
+          atomicMin(&sNext[r], nxt);
+        __syncthreads();
+        nxt = sNext[r];
+        if (nxt == 0x10000)
+          done = true;
+        else if (r == MED_DMAX - 1)
+        {
+          nvals = MED_DMAX + 1; // a fifth value: generic path
+          done = true;
+        }
+        else
+        {
+          vals[r] = (unsigned)nxt;
+          nvals = r + 1;
+        }
+      }
+    if (nvals <= MED_DMAX - 1)
+    {
+#pragma unroll
+      for (int k = 1; k < MED_DMAX; ++k)
+        if (k == nvals)
+          vals[k] = vHi;
+      ++nvals;
+    }
+  }
+
+  if (nvals <= MED_DMAX)
+  {
+    // ---- 3a. value masks by warp ballot (one warp per row; the largest value needs no mask) ...
+    for (int row = warp; row < NROWS; row += MED_THREADS / 32)
+    {
+      const unsigned v0 = raw[row * MED_RW + lane];
+      const unsigned v1 = lane < MED_RW - 32 ? raw[row * MED_RW + 32 + lane] : 0x10000u;
+#pragma unroll
+      for (int k = 0; k < MED_DMAX - 1; ++k)
+        if (k < nvals - 1)
+        {
+          const unsigned b0 = __ballot_sync(0xFFFFFFFFu, v0 == vals[k]), b1 = __ballot_sync(0xFFFFFFFFu, v1 == vals[k]);
+          if (lane == 0)
+            vm[k * NROWS + row] = (u64)b0 | ((u64)b1 << 32);
+        }
+    }
+    __syncthreads();
+    // ... and the value-change masks from them: pixels c and c' differ iff some value mask differs between them
+    for (int row = tid; row < NROWS; row += MED_THREADS)
+    {
+      const int hy = row % HY, hz = row / HY;
+      u64 mx = 0ull, my = 0ull, mz = 0ull;
+#pragma unroll
+      for (int k = 0; k < MED_DMAX - 1; ++k)
+        if (k < nvals - 1)
+        {
+          const u64 m = vm[k * NROWS + row];
+          mx |= m ^ (m >> 1);
+          if (hy + 1 < HY)
+            my |= m ^ vm[k * NROWS + row + 1];
+          if (hz + 1 < HZ)
+            mz |= m ^ vm[k * NROWS + row + HY];
+        }
+      eX[row] = mx; // bit 47 compares with a pixel that is not staged; windows never reach it
+      eY[row] = my;
+      eZ[row] = mz;
+    }
+  }
+  else
+  {
+    // ---- 3b. many distinct values (not a label volume): value-change masks pixel by pixel
+    for (int row = tid; row < NROWS; row += MED_THREADS)
+    {
+      const int hy = row % HY, hz = row / HY;
+      const uint16_t * p = raw + row * MED_RW;
+      const uint16_t * py = hy + 1 < HY ? p + MED_RW : p;
+      const uint16_t * pz = hz + 1 < HZ ? p + HY * MED_RW : p;
+      u64 mx = 0ull, my = 0ull, mz = 0ull;
+      unsigned v = p[0];
+#pragma unroll 4
+      for (int c = 0; c < MED_RW; ++c)
+      {
+        const unsigned nx = c + 1 < MED_RW ? p[c + 1] : v;
+        mx |= (u64)(v != nx) << c;
+        my |= (u64)(v != py[c]) << c;
+        mz |= (u64)(v != pz[c]) << c;
+        v = nx;
+      }
+      eX[row] = mx;
+      eY[row] = my;
+      eZ[row] = mz;
+    }
   }
   __syncthreads();
   // OR over the y range of the window: x- and z-changes over [oy, oy + 2R], y-changes over [oy, oy + 2R - 1]
   for (int i = tid; i < HZ * MED_TY; i += MED_THREADS)
   {
     const int oy = i % MED_TY, hz = i / MED_TY;
-    unsigned long long sx = 0ull, sy = 0ull, sz = 0ull;
+    u64 sx = 0ull, sy = 0ull, sz = 0ull;
 #pragma unroll
     for (int d = 0; d <= 2 * R; ++d)
     {
@@ -246,7 +394,7 @@ __global__ void __launch_bounds__(MED_THREADS) k_median3d(const T * __restrict__
   for (int i = tid; i < MED_TZ * MED_TY; i += MED_THREADS)
   {
     const int oy = i % MED_TY, oz = i / MED_TY;
-    unsigned long long sx = 0ull, sm = 0ull;
+    u64 sx = 0ull, sm = 0ull;
 #pragma unroll
     for (int d = 0; d <= 2 * R; ++d)
     {
@@ -260,89 +408,93 @@ __global__ void __launch_bounds__(MED_THREADS) k_median3d(const T * __restrict__
   }
   __syncthreads();
 
-  // ---- 3. uniform neighbourhoods take the centre value; the others go on the list
+  // ---- 4. uniform neighbourhoods take the centre value; the others go on the list
   for (int row = orow0; row < MED_TY * MED_TZ; row += MED_THREADS / 32)
   {
     const int oy = row % MED_TY, oz = row / MED_TY;
-    // x-changes between hx and hx + 1 for hx in [ox, ox + 2R - 1]; y/z-changes at hx in [ox, ox + 2R]
-    const unsigned long long hit = ((bX[row] >> ox) & ((1ull << (2 * R)) - 1ull)) | ((bM[row] >> ox) & ((1ull << (2 * R + 1)) - 1ull));
+    // x-changes between c and c + 1 for c in [ox + C0, ox + C0 + 2R - 1]; y/z-changes at c in [ox + C0, ox + C0 + 2R]
+    const u64 hit = ((bX[row] >> (ox + C0)) & (WMASK >> 1)) | ((bM[row] >> (ox + C0)) & WMASK);
     const int o = row * MED_TX + ox;
     if (hit == 0ull)
-      res[o] = raw[((oz + R) * HY + oy + R) * HXP + ox + R];
+      res[o] = raw[((oz + R) * HY + oy + R) * MED_RW + ox + MED_PADL];
     else if (x0 + ox < X && y0 + oy < Y && z0 + oz < Z)
       list[atomicAdd(&listCount, 1)] = (uint16_t)o;
   }
   __syncthreads();
 
-  // ---- 4. exact selection for the listed voxels: distinct values in ascending order until the count passes n/2
+  // ---- 5. exact selection for the listed voxels
   const int nList = listCount;
-  for (int e = tid; e < nList; e += MED_THREADS)
+  if (nvals <= MED_DMAX)
   {
-    const int o = list[e];
-    const int vx = o % MED_TX, vy = (o / MED_TX) % MED_TY, vz = o / (MED_TX * MED_TY);
-    const uint16_t * base = raw + (vz * HY + vy) * HXP + vx;
-    int cur = -1, total = 0, m;
+    // counts of the tile's values inside the window by popcount of the value masks, smallest value first, until the
+    // cumulative count passes n/2
+    for (int e = tid; e < nList; e += MED_THREADS)
     {
-      // first pass: smallest and largest value with their counts; a two-valued neighbourhood (nearly all of them in
-      // a label volume) is decided here
-      int mx = -1, cmx = 0, c = 0;
-      m = 0x10000;
-      for (int dz = 0; dz <= 2 * R; ++dz)
-        for (int dy = 0; dy <= 2 * R; ++dy)
-        {
-          const uint16_t * p = base + (dz * HY + dy) * HXP;
+      const int o = list[e];
+      const int vx = o % MED_TX, vy = (o / MED_TX) % MED_TY, vz = o / (MED_TX * MED_TY);
+      const int sh = vx + C0;
+      unsigned answer = vHi;
+      int total = 0;
 #pragma unroll
-          for (int dx = 0; dx <= 2 * R; ++dx)
+      for (int k = 0; k < MED_DMAX - 1; ++k)
+        if (k < nvals - 1)
+        {
+          const u64 * m = vm + k * NROWS + vz * HY + vy;
+          int c = 0;
+#pragma unroll
+          for (int dz = 0; dz <= 2 * R; ++dz)
+#pragma unroll
+            for (int dy = 0; dy <= 2 * R; ++dy)
+              c += __popc((unsigned)((m[dz * HY + dy] >> sh) & WMASK));
+          total += c;
+          if (total > KTH)
           {
-            const int v = p[dx];
-            c = v < m ? 1 : c + (v == m);
-            m = min(m, v);
-            cmx = v > mx ? 1 : cmx + (v == mx);
-            mx = max(mx, v);
+            answer = vals[k];
+            break;
           }
         }
-      if (c > KTH)
-      {
-        res[o] = (uint16_t)m;
-        continue;
-      }
-      if (c + cmx == NWIN)
-      {
-        res[o] = (uint16_t)mx;
-        continue;
-      }
-      total = c;
-      cur = m;
+      res[o] = (uint16_t)answer;
     }
-    for (;;)
+  }
+  else
+  {
+    // distinct values of the neighbourhood in ascending order until the cumulative count passes n/2
+    for (int e = tid; e < nList; e += MED_THREADS)
     {
-      m = 0x10000;
-      int c = 0;
-      for (int dz = 0; dz <= 2 * R; ++dz)
-        for (int dy = 0; dy <= 2 * R; ++dy)
-        {
-          const uint16_t * p = base + (dz * HY + dy) * HXP;
-#pragma unroll
-          for (int dx = 0; dx <= 2 * R; ++dx)
+      const int o = list[e];
+      const int vx = o % MED_TX, vy = (o / MED_TX) % MED_TY, vz = o / (MED_TX * MED_TY);
+      const uint16_t * base = raw + (vz * HY + vy) * MED_RW + vx + C0;
+      int cur = -1, total = 0, m;
+      for (;;)
+      {
+        m = 0x10000;
+        int c = 0;
+        for (int dz = 0; dz <= 2 * R; ++dz)
+          for (int dy = 0; dy <= 2 * R; ++dy)
           {
-            const int v = p[dx];
-            if (v > cur)
+            const uint16_t * p = base + (dz * HY + dy) * MED_RW;
+#pragma unroll
+            for (int dx = 0; dx <= 2 * R; ++dx)
             {
-              c = v < m ? 1 : c + (v == m);
-              m = min(m, v);
+              const int v = p[dx];
+              if (v > cur)
+              {
+                c = v < m ? 1 : c + (v == m);
+                m = min(m, v);
+              }
             }
           }
-        }
-      total += c;
-      if (total > KTH)
-        break;
-      cur = m;
+        total += c;
+        if (total > KTH)
+          break;
+        cur = m;
+      }
+      res[o] = (uint16_t)m;
     }
-    res[o] = (uint16_t)m;
   }
   __syncthreads();
 
-  // ---- 5. store the tile: 16-byte vectors when rows are aligned and the tile is inside the volume
+  // ---- 6. store the tile: 16-byte vectors when rows are aligned and the tile is inside the volume
   if (vecOk)
   {
     constexpr int VPR = MED_TX / VEC; // vectors per row

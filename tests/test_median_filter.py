@@ -40,10 +40,21 @@ def test_gpu_median_matches_oracle_on_small_volumes():
     shapes = ((7, 9, 11), (1, 5, 6), (16, 5, 16), (3, 3, 3), (2, 1, 40), (9, 17, 33), (8, 8, 32), (10, 24, 70), (1, 1, 1))
     for dt in (np.uint8, np.uint16, np.int16):
         for shape in shapes:
-            for n in (2, 9, 4000):            # two-valued, few labels, noise (every neighbourhood distinct values)
+            for n in (2, 3, 4, 5, 9, 4000):   # 2..4 values per tile: bit-mask path; more: generic path; noise
                 v = rand_labels(rng, shape, dt, min(n, 250) if dt == np.uint8 else n)
                 for r in (0, 1, 2, 3):
                     assert np.array_equal(median_image_filter(v, r), O.median_image_filter(v, r, threads=4)), (dt, shape, n, r)
+    # label-like blobs: tiles with one to four values, uniform neighbourhoods next to mixed ones, borders
+    blobs = np.zeros((37, 70, 150), np.uint16)
+    zz, yy, xx = np.mgrid[:37, :70, :150]
+    for k, (cz, cy, cx, rr) in enumerate(((10, 20, 30, 9), (14, 26, 41, 8), (25, 50, 100, 12), (30, 60, 140, 10), (5, 5, 5, 7), (18, 35, 75, 15))):
+        blobs[(zz - cz) ** 2 + (yy - cy) ** 2 + (xx - cx) ** 2 <= rr * rr] = 3 + 7 * k
+    for dt in (np.uint16, np.uint8, np.int16):
+        b = blobs.astype(dt)
+        if dt == np.int16:
+            b[b == 3] = -5
+        for r in (1, 2, 3):
+            assert np.array_equal(median_image_filter(b, r), O.median_image_filter(b, r, threads=4)), (dt, r)
     big = np.zeros((20, 40, 96), np.int16)
     big[5:15, 10:30, 20:70] = -7
     big[8:12, 15:25, 30:50] = 9

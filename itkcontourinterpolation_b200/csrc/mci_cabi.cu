@@ -1060,6 +1060,8 @@ extern "C"
     std::map<std::pair<int, int>, MaskRef> compMasks;
     u64 arenaWords = 0, scratchWords = 0;
     int maxSplitWords = 0;
+    int nSlots = 0; // axis-0 slot table entries
+    std::vector<Axis0Group> axis0Groups;
     const int alignSmemCap = 150 * 1024; // bitmap + queue; the kernel adds 48 KB for staging the shapes
     int alignSmem = 0;
     int nRootNodes = 0;
@@ -1120,6 +1122,7 @@ extern "C"
       R.axis = SA.axis;
       R.label = SA.label;
       R.rootOff = nRootNodes;
+      R.slot0 = -1;
       const CompStat & ca = statOf(jb.slice_a, jb.a_id);
       const long long acu = (long long)((unsigned long long)ca.sumU / (unsigned long long)ca.count);
       const long long acv = (long long)((unsigned long long)ca.sumV / (unsigned long long)ca.count);
@@ -1236,6 +1239,22 @@ extern "C"
         A.queueOff = scratchWords;
         scratchWords += 3ull * qcap;
       }
+      // trees perpendicular to x register their mid slices by position (k_apply_axis0)
+      if (SA.axis == 0)
+      {
+        R.slot0 = nSlots;
+        for (int q = 0; q < nRootsHere; ++q)
+        {
+          for (int c0 = 0; c0 < gap - 1; c0 += 32)
+          {
+            Axis0Group g;
+            g.slot0 = nSlots + c0;
+            g.n = std::min(32, gap - 1 - c0);
+            axis0Groups.push_back(g);
+          }
+          nSlots += gap - 1;
+        }
+      }
       // node bookkeeping
       nRootNodes += nRootsHere;
       int depth = depth_of_gap(gap);
@@ -1275,7 +1294,7 @@ extern "C"
     std::vector<int> lc(maxDepth + 2, 0);
     lc[0] = nRootNodes;
     const std::vector<unsigned long long> top(1, arenaWords);
-    const size_t oLc = blob.add(lc), oTop = blob.add(top);
+    const size_t oLc = blob.add(lc), oTop = blob.add(top), oGroups = blob.add(axis0Groups);
     CK(ctx->dJobBlob.ensure(blob.bytes.size()));
     CK(ctx->hStage.ensure(blob.bytes.size()));
     CK(ctx->dLevelCounts.ensure(size_t(maxDepth + 2) * sizeof(int)));
@@ -1297,13 +1316,16 @@ extern "C"
     for (long long c : levelCap)
       nodeTotal += c;
     CK(ctx->dNodes.ensure(size_t(nodeTotal + 1) * sizeof(Node)));
-    CK(ctx->dEmit.ensure(16 + size_t(nodeTotal + 1) * sizeof(EmitRec)));
+    CK(ctx->dEmit.ensure(16 + size_t(nodeTotal + 1) * sizeof(EmitRec) + size_t(nSlots + 1) * sizeof(int)));
     CK(cudaMemsetAsync(ctx->dEmit.p, 0, 16, s));
     ctx->emitCap = (int)nodeTotal;
     ctx->emitBase = arenaWords;
     ctx->haveEmit = true;
     EmitRec * dEmitRecs = (EmitRec *)((uint8_t *)ctx->dEmit.p + 16);
     int * dEmitCount = (int *)ctx->dEmit.p;
+    int * dSlots = emit_slot_table(dEmitRecs, ctx->emitCap);
+    if (nSlots)
+      CK(cudaMemsetAsync(dSlots, 0xFF, size_t(nSlots) * sizeof(int), s)); // -1: no mid slice at that position
 
     // ---- launches
     launch_extract(ctx->L, ctx->dSlices, (ExtractJob *)(jb + oExtract), (int)extracts.size(), (uint16_t *)ctx->dConn.p,
@@ -1413,6 +1435,9 @@ extern "C"
         launch_dt_level(ctx->L, ctx->ptype, lv);
         off += levelCap[d];
       }
+      // k_dt_emit wrote the slices of axes 1 and 2; the trees perpendicular to x go x-run by x-run
+      launch_apply_axis0(ctx->L, ctx->ptype, (Axis0Group *)(jb + oGroups), (int)axis0Groups.size(), dEmitRecs, dSlots,
+                         (uint32_t *)ctx->dArena.p + ctx->emitBase, ctx->dIn, ctx->dOut, ctx->dims);
     }
     else
     {
@@ -1449,7 +1474,9 @@ extern "C"
       }
       // the node kernel only stores the mid shapes; their volume writes (X:743-764) happen here in one grid-wide pass
       launch_apply_masks(ctx->L, ctx->ptype, dEmitRecs, ctx->emitCap, dEmitCount, (uint32_t *)ctx->dArena.p + ctx->emitBase, ctx->dIn,
-                         ctx->dOut, ctx->dims);
+                         ctx->dOut, ctx->dims, /*skipAxis0=*/1);
+      launch_apply_axis0(ctx->L, ctx->ptype, (Axis0Group *)(jb + oGroups), (int)axis0Groups.size(), dEmitRecs, dSlots,
+                         (uint32_t *)ctx->dArena.p + ctx->emitBase, ctx->dIn, ctx->dOut, ctx->dims);
     }
     CK(cudaGetLastError());
     return MCI_OK;
@@ -1522,7 +1549,7 @@ extern "C"
     (void)n_words;
     CK(cudaSetDevice(ctx->device));
     launch_apply_masks(ctx->L, ctx->ptype, (const EmitRec *)recs_dev, (int)n_recs, nullptr, (const uint32_t *)words_dev, ctx->dIn,
-                       ctx->dOut, ctx->dims);
+                       ctx->dOut, ctx->dims, /*skipAxis0=*/0); // another GPU's list: no slot table, slice by slice
     return MCI_OK;
   }
 

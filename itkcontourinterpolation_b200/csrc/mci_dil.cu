@@ -582,6 +582,8 @@ k_dil_nodes(const Node * __restrict__ nodes, const int * __restrict__ count, Nod
         r.mid = mid;
         r.pad = 0;
         emit[e] = r;
+        if (nd.slot0 >= 0)
+          emit_slot_table(emit, emitCap)[nd.slot0 + mid - nd.lo - 1] = e;
       }
       else
         atomicMax(err, ERR_NODE_LIST);
@@ -626,6 +628,8 @@ k_dil_nodes(const Node * __restrict__ nodes, const int * __restrict__ count, Nod
             c.j = mid;
             c.axis = nd.axis;
             c.label = nd.label;
+            c.slot0 = nd.slot0;
+            c.lo = nd.lo;
             next[pos++] = c;
           }
           if (second)
@@ -639,6 +643,8 @@ k_dil_nodes(const Node * __restrict__ nodes, const int * __restrict__ count, Nod
             c.j = mid;
             c.axis = nd.axis;
             c.label = nd.label;
+            c.slot0 = nd.slot0;
+            c.lo = nd.lo;
             next[pos++] = c;
           }
         }

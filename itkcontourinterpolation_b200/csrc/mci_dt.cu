@@ -828,6 +828,8 @@ k_dt_alloc(NodeWork * work, const int * __restrict__ count, unsigned long long *
       r.mid = W->mid;
       r.pad = 0;
       emit[e] = r;
+      if (W->nd.slot0 >= 0)
+        emit_slot_table(emit, emitCap)[W->nd.slot0 + W->mid - W->nd.lo - 1] = e;
     }
     else
       atomicMax(err, ERR_NODE_LIST);
@@ -873,6 +875,8 @@ k_dt_alloc(NodeWork * work, const int * __restrict__ count, unsigned long long *
         c.j = mid;
         c.axis = nd.axis;
         c.label = nd.label;
+        c.slot0 = nd.slot0;
+        c.lo = nd.lo;
         next[pos++] = c;
       }
       if (second)
@@ -886,6 +890,8 @@ k_dt_alloc(NodeWork * work, const int * __restrict__ count, unsigned long long *
         c.j = mid;
         c.axis = nd.axis;
         c.label = nd.label;
+        c.slot0 = nd.slot0;
+        c.lo = nd.lo;
         next[pos++] = c;
       }
     }
@@ -1054,7 +1060,7 @@ k_dt_emit(const NodeWork * __restrict__ work, const DtItem * __restrict__ witems
         }
       }
     }
-    else
+    else if (W->nd.slot0 < 0) // registered axis-0 trees are written x-run by x-run after the last level (k_apply_axis0)
     {
       for (int c = 0; c < wEnd - wBeg; ++c)
       {
@@ -1078,7 +1084,7 @@ k_dt_emit(const NodeWork * __restrict__ work, const DtItem * __restrict__ witems
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_apply_masks(const EmitRec * __restrict__ recs, int nrecsHost, const int * __restrict__ nrecsDev, const uint32_t * __restrict__ words,
-              const T * __restrict__ in, T * out, long long VX, long long VY, long long VZ)
+              const T * __restrict__ in, T * out, long long VX, long long VY, long long VZ, int skipAxis0)
 {
   const int nrecs = nrecsDev ? min(*nrecsDev, nrecsHost) : nrecsHost; // device-side count capped by the list capacity
   constexpr int VPQ = 8 / sizeof(T);
@@ -1088,6 +1094,8 @@ k_apply_masks(const EmitRec * __restrict__ recs, int nrecsHost, const int * __re
   for (int ri = blockIdx.x; ri < nrecs; ri += gridDim.x)
   {
     const EmitRec R = recs[ri];
+    if (skipAxis0 && R.axis == 0)
+      continue; // written by k_apply_axis0
     const MaskRef M = R.M;
     const T label = (T)R.label;
     long long su, sv;
@@ -1173,9 +1181,117 @@ k_apply_masks(const EmitRec * __restrict__ recs, int nrecsHost, const int * __re
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Volume writes of the trees whose slices are perpendicular to x (axis 0).  Written slice by slice, every pixel of
+// such a mid slice is a 2-byte read-modify-write X voxels away from the next: one 32-byte sector per voxel.  But the
+// mid slices of ONE tree sit at consecutive x, so for a fixed (y, z) their pixels form a contiguous x-run.  One CTA
+// takes up to 32 consecutive slice positions of a tree (Axis0Group; the slot table maps position -> record); a warp
+// takes a 32-pixel cell of the union region, lane k fetches that cell's word of slice k (funnel-shifted to the
+// cell), the 32 x n bit matrix is transposed with shuffles, and lane b writes the x-run of pixel b in aligned
+// 8-byte groups with the max rule (X:754-763).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_apply_axis0(const Axis0Group * __restrict__ groups, int ngroups, const EmitRec * __restrict__ recs, const int * __restrict__ slots,
+              const uint32_t * __restrict__ words, const T * __restrict__ in, T * out, long long VX, long long VY, long long VZ)
+{
+  constexpr int VPQ = 8 / sizeof(T);
+  __shared__ EmitRec s_rec[32];
+  __shared__ int s_box[4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const unsigned long long nvox = (unsigned long long)VX * VY * VZ;
+  for (int gi = blockIdx.x; gi < ngroups; gi += gridDim.x)
+  {
+    const Axis0Group G = groups[gi];
+    __syncthreads(); // previous group done with s_rec / s_box
+    if (threadIdx.x < 4)
+      s_box[threadIdx.x] = threadIdx.x < 2 ? 0x7FFFFFFF : -0x7FFFFFFF;
+    __syncthreads();
+    if (threadIdx.x < 32)
+    {
+      EmitRec R{};
+      const int e = threadIdx.x < G.n ? slots[G.slot0 + threadIdx.x] : -1;
+      if (e >= 0)
+        R = recs[e];
+      else
+        R.axis = -1;
+      s_rec[threadIdx.x] = R;
+      if (e >= 0 && R.M.w > 0 && R.M.h > 0)
+      {
+        atomicMin(&s_box[0], R.M.x0);
+        atomicMin(&s_box[1], R.M.y0);
+        atomicMax(&s_box[2], R.M.x0 + R.M.w);
+        atomicMax(&s_box[3], R.M.y0 + R.M.h);
+      }
+    }
+    __syncthreads();
+    const int U0 = s_box[0], V0 = s_box[1], U1 = s_box[2], V1 = s_box[3];
+    if (U1 <= U0 || V1 <= V0)
+      continue;
+    // my slice (lane k): geometry in registers
+    const EmitRec mine = s_rec[lane];
+    const bool valid = mine.axis == 0 && mine.M.w > 0;
+    // x of slot 0 and the label, from any valid record
+    const unsigned vmask = __ballot_sync(0xFFFFFFFFu, valid);
+    const int src = __ffs(vmask) - 1;
+    const int xSlot0 = __shfl_sync(0xFFFFFFFFu, mine.mid - lane, src);
+    const T label = (T)__shfl_sync(0xFFFFFFFFu, mine.label, src);
+    const uint32_t * myWords = words + mine.M.off;
+    const int ncw = (U1 - U0 + 31) >> 5, ncells = ncw * (V1 - V0);
+    for (int cell = warp; cell < ncells; cell += nwarps)
+    {
+      const int v = V0 + cell / ncw, Uc = U0 + 32 * (cell % ncw);
+      uint32_t W = 0u;
+      if (valid && v >= mine.M.y0 && v < mine.M.y0 + mine.M.h)
+      {
+        const uint32_t * row = myWords + (size_t)(v - mine.M.y0) * mine.M.pitch;
+        const int rx = Uc - mine.M.x0; // column of the mask that bit 0 of the cell maps to
+        if (rx >= 0)
+        {
+          const int sw = rx >> 5, sh = rx & 31;
+          const uint32_t lo = sw < mine.M.pitch ? __ldg(row + sw) : 0u;
+          const uint32_t hi = sw + 1 < mine.M.pitch ? __ldg(row + sw + 1) : 0u;
+          W = __funnelshift_r(lo, hi, sh);
+        }
+        else if (rx > -32)
+          W = __ldg(row) << (-rx);
+      }
+      unsigned any = __ballot_sync(0xFFFFFFFFu, W != 0u);
+      if (!any)
+        continue;
+      // transpose: bit k of `run` = pixel `lane` of slice k
+      unsigned run = 0u;
+      while (any)
+      {
+        const int k = __ffs(any) - 1;
+        any &= any - 1;
+        const uint32_t Wk = __shfl_sync(0xFFFFFFFFu, W, k);
+        run |= ((Wk >> lane) & 1u) << k;
+      }
+      if (!run)
+        continue;
+      // pixel (u = y, v = z): voxels x = xSlot0 + k for the set bits k
+      const unsigned long long a0 = ((unsigned long long)v * VY + (unsigned long long)(Uc + lane)) * VX + (unsigned long long)xSlot0;
+      const int kLast = 31 - __clz(run);
+      for (unsigned long long g = (a0 + (__ffs(run) - 1)) & ~(unsigned long long)(VPQ - 1); g <= a0 + kLast; g += VPQ)
+      {
+        const long long sh = (long long)g - (long long)a0; // in (-VPQ, 32)
+        const unsigned bits = (sh >= 0 ? (run >> sh) : (run << (-sh))) & ((1u << VPQ) - 1u);
+        if (!bits)
+          continue;
+        if (g + VPQ <= nvox)
+          write_group<T>(in, out, g, bits, label);
+        else
+          for (int k = 0; k < VPQ; ++k)
+            if (((bits >> k) & 1u) && g + k < nvox && in[g + k] == 0)
+              atomic_max_pixel(out + g + k, label);
+      }
+    }
+  }
+}
+
 void
 launch_apply_masks(Launch & L, int ptype, const EmitRec * recs, int nrecs, const int * nrecsDev, const uint32_t * words, const void * in,
-                   void * out, const long long dims[3])
+                   void * out, const long long dims[3], int skipAxis0)
 {
   if (nrecs <= 0)
     return;
@@ -1185,17 +1301,42 @@ launch_apply_masks(Launch & L, int ptype, const EmitRec * recs, int nrecs, const
   {
     case MCI_U8:
       k_apply_masks<uint8_t><<<grid, 256, 0, L.stream>>>(recs, nrecs, nrecsDev, words, (const uint8_t *)in, (uint8_t *)out, dims[0], dims[1],
-                                                         dims[2]);
+                                                         dims[2], skipAxis0);
       break;
     case MCI_U16:
       k_apply_masks<uint16_t><<<grid, 256, 0, L.stream>>>(recs, nrecs, nrecsDev, words, (const uint16_t *)in, (uint16_t *)out, dims[0],
-                                                           dims[1], dims[2]);
+                                                           dims[1], dims[2], skipAxis0);
       break;
     default:
       k_apply_masks<int16_t><<<grid, 256, 0, L.stream>>>(recs, nrecs, nrecsDev, words, (const int16_t *)in, (int16_t *)out, dims[0], dims[1],
-                                                          dims[2]);
+                                                          dims[2], skipAxis0);
   }
   L.post("k_apply_masks");
+}
+
+void
+launch_apply_axis0(Launch & L, int ptype, const Axis0Group * groups, int ngroups, const EmitRec * recs, const int * slots,
+                   const uint32_t * words, const void * in, void * out, const long long dims[3])
+{
+  if (ngroups <= 0)
+    return;
+  const int grid = std::max(1, std::min(ngroups, L.sms * 8));
+  L.pre("k_apply_axis0");
+  switch (ptype)
+  {
+    case MCI_U8:
+      k_apply_axis0<uint8_t><<<grid, 256, 0, L.stream>>>(groups, ngroups, recs, slots, words, (const uint8_t *)in, (uint8_t *)out, dims[0],
+                                                         dims[1], dims[2]);
+      break;
+    case MCI_U16:
+      k_apply_axis0<uint16_t><<<grid, 256, 0, L.stream>>>(groups, ngroups, recs, slots, words, (const uint16_t *)in, (uint16_t *)out, dims[0],
+                                                          dims[1], dims[2]);
+      break;
+    default:
+      k_apply_axis0<int16_t><<<grid, 256, 0, L.stream>>>(groups, ngroups, recs, slots, words, (const int16_t *)in, (int16_t *)out, dims[0],
+                                                         dims[1], dims[2]);
+  }
+  L.post("k_apply_axis0");
 }
 
 // ---------------------------------------------------------------------------------------------------

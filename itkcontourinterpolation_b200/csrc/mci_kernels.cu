@@ -1232,6 +1232,8 @@ k_make_roots(const RootJob * __restrict__ roots, int nroots, MaskRef * refs, uin
     n.j = R.posB;
     n.axis = R.axis;
     n.label = R.label;
+    n.slot0 = R.slot0;
+    n.lo = min(R.posA, R.posB);
     nodes[R.rootOff] = n;
   }
   else if (R.kind == JOB_ONE_TO_ONE)
@@ -1245,6 +1247,8 @@ k_make_roots(const RootJob * __restrict__ roots, int nroots, MaskRef * refs, uin
     n.j = R.posB;
     n.axis = R.axis;
     n.label = R.label;
+    n.slot0 = R.slot0;
+    n.lo = min(R.posA, R.posB);
     nodes[R.rootOff] = n;
   }
   else
@@ -1260,6 +1264,8 @@ k_make_roots(const RootJob * __restrict__ roots, int nroots, MaskRef * refs, uin
       n.j = R.posB;
       n.axis = R.axis;
       n.label = R.label;
+      n.slot0 = R.slot0 < 0 ? -1 : R.slot0 + q * (abs(R.posA - R.posB) - 1);
+      n.lo = min(R.posA, R.posB);
       nodes[R.rootOff + q] = n;
     }
   }

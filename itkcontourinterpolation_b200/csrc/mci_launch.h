@@ -145,6 +145,8 @@ void launch_nodes(Launch & L, int ptype, const Node * nodes, const int * count, 
                   unsigned long long slabWords, unsigned short * arr, unsigned long long arrPixels, int grid, int smemBytes,
                   EmitRec * emit, int * emitCount, int emitCap, unsigned long long emitBase, int * err);
 void launch_apply_masks(Launch & L, int ptype, const EmitRec * recs, int nrecs, const int * nrecsDev, const uint32_t * words,
-                        const void * in, void * out, const long long dims[3]);
+                        const void * in, void * out, const long long dims[3], int skipAxis0);
+void launch_apply_axis0(Launch & L, int ptype, const Axis0Group * groups, int ngroups, const EmitRec * recs, const int * slots,
+                        const uint32_t * words, const void * in, void * out, const long long dims[3]);
 
 } // namespace mci

@@ -103,6 +103,10 @@ struct Node
   int tx, ty;
   int i, j;
   int axis, label;
+  // trees whose slices are perpendicular to x (axis 0) register their mid slices in a slot table, one slot per slice
+  // position between the root's two slices, so that the volume writes of a whole tree can go x-run by x-run
+  // (k_apply_axis0): slot = slot0 + (mid - lo - 1); slot0 < 0: not registered
+  int slot0, lo;
 };
 
 // Per-node state of one level of the distance-transform pipeline (mci_dt.cu).
@@ -126,6 +130,12 @@ struct EmitRec
   MaskRef M; // off is relative to the first mid-shape word of the arena
   int axis, label, mid, pad;
 };
+// The axis-0 slot table (ints, record index or -1) lives behind the record list: emit + emitCap.
+__host__ __device__ inline int *
+emit_slot_table(EmitRec * emit, int emitCap)
+{
+  return reinterpret_cast<int *>(emit + emitCap);
+}
 
 struct DtItem
 {
@@ -144,6 +154,13 @@ struct RootJob
   int rootOff; // index of the first root node written
   int phRef;   // EXTRAPOLATE: MaskRef slot (1 word) for the phantom
   int phx, phy;
+  int slot0;   // first slot of the first root's tree in the axis-0 slot table (-1: none); further roots follow at gap-1 each
+};
+
+// up to 32 consecutive slots of one axis-0 tree (k_apply_axis0)
+struct Axis0Group
+{
+  int slot0, n;
 };
 
 struct VolDev

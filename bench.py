@@ -162,6 +162,8 @@ def main():
         print(json.dumps(line))
         return 0
 
+    # NCCL writes its version banner / debug lines to stdout; rank 0 must print ONE JSON line there
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug.%h.%p.log")
     import torch
     import torch.distributed as dist
     from itkcontourinterpolation_b200 import _lib as L

@@ -162,8 +162,11 @@ def main():
         print(json.dumps(line))
         return 0
 
-    # NCCL writes its version banner / debug lines to stdout; rank 0 must print ONE JSON line there
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug.%h.%p.log")
+    # libraries (NCCL's version banner) write to stdout; rank 0 must print ONE JSON line there: keep the real stdout
+    # aside and point fd 1 at stderr for everything else
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from itkcontourinterpolation_b200 import _lib as L
@@ -171,6 +174,13 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    try:
+        # host threads and the pinned buffers they first touch stay on the NUMA node of this rank's GPU
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+    except Exception:
+        pass
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -358,7 +368,8 @@ def main():
                 "kernels_note": "second pass of the same steps with CUDA events around every launch (%.3f ms/step)" % ms_res_profiled,
                 "job": {k: job_stats[k] for k in ("n_labels", "n_annotated_slices", "n_segments", "n_pairs", "n_jobs", "n_components")},
                 "bit_exact_vs_oracle": (not args.no_check)}
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     for a, b in zip(ins, outs):
         lib.mci_host_free(a)
         lib.mci_host_free(b)

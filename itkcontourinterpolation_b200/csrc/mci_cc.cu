@@ -375,12 +375,7 @@ launch_cc(Launch & L, int ptype, const void * in, const SliceDev * slices, int n
       k_slice_bits<int16_t><<<ntiles, 256, 0, L.stream>>>((const int16_t *)in, slices, tiles, bits);
   }
   L.post("k_slice_bits");
-  static bool attr = false;
-  if (!attr)
-  {
-    cudaFuncSetAttribute(k_cc_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, L.maxSmem - 2048);
-    attr = true;
-  }
+  L.ensure_max_smem(k_cc_runs, 0, L.maxSmem - 2048);
   const int smemBytes = ((maxRows + 1) + 3 * CC_SMEM_RUNS) * 4;
   const int maxPer = ptype == MCI_U8 ? 255 : (ptype == MCI_U16 ? 65535 : 32767);
   L.pre("k_cc_runs");

@@ -660,12 +660,7 @@ launch_dil_t(Launch & L, const Node * nodes, const int * count, int maxNodes, No
              const long long dims[3], int ball, unsigned * stepHist, uint32_t * slab, unsigned long long slabWords,
              unsigned short * arr, unsigned long long arrPixels, int grid, int smemBytes, EmitRec * emit, int * emitCount, int emitCap, unsigned long long emitBase, int * err)
 {
-  static bool attr = false;
-  if (!attr)
-  {
-    cudaFuncSetAttribute(k_dil_nodes<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.maxSmem - 2048);
-    attr = true;
-  }
+  L.ensure_max_smem(k_dil_nodes<T>, 3 + (int)sizeof(T) + (std::is_signed<T>::value ? 1 : 0), L.maxSmem - 2048);
   const int g = std::max(1, std::min(grid, maxNodes));
   L.pre("k_dil_nodes");
   k_dil_nodes<T><<<g, DIL_THREADS, smemBytes, L.stream>>>(nodes, count, next, nextCount, nextCap, arena, arenaTop, arenaCap,

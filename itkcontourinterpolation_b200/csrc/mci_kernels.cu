@@ -1038,12 +1038,7 @@ launch_align(Launch & L, const AlignJob * jobs, int njobs, const MaskRef * refs,
 {
   if (njobs == 0)
     return;
-  static bool attr = false;
-  if (!attr)
-  {
-    cudaFuncSetAttribute(k_align, cudaFuncAttributeMaxDynamicSharedMemorySize, L.maxSmem - 1024);
-    attr = true;
-  }
+  L.ensure_max_smem(k_align, 1, L.maxSmem - 1024);
   int grid = std::min(njobs, L.sms * 8);
   L.pre("k_align");
   k_align<<<grid, ALIGN_THREADS, smemBytes + ALIGN_MASK_WORDS * 4, L.stream>>>(jobs, njobs, refs, arena, gscratch, heuristic,
@@ -1187,12 +1182,7 @@ launch_split(Launch & L, const SplitJob * jobs, int njobs, const MaskRef * refs,
 {
   if (njobs == 0)
     return;
-  static bool attr = false;
-  if (!attr)
-  {
-    cudaFuncSetAttribute(k_split, cudaFuncAttributeMaxDynamicSharedMemorySize, L.maxSmem - 1024);
-    attr = true;
-  }
+  L.ensure_max_smem(k_split, 2, L.maxSmem - 1024);
   const int smemBytes = 160 * 1024;
   L.pre("k_split");
   // one word per thread where the shapes allow it; fewer warps make the per-step barrier cheaper

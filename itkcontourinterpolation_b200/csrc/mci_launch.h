@@ -39,6 +39,18 @@ struct Launch
       cudaEventCreate(&e);
     return e;
   }
+  // opt-in dynamic shared memory is a per-device function attribute: every context sets it once for itself (contexts
+  // may live on different devices and be driven by different host threads, so no process-wide flag)
+  unsigned attrDone = 0;
+  template <typename F>
+  void ensure_max_smem(F fn, int bit, int bytes)
+  {
+    if (!((attrDone >> bit) & 1u))
+    {
+      cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      attrDone |= 1u << bit;
+    }
+  }
   const char * only = nullptr; // when set, only launches of this kernel are timed
   bool pending = false;
   static bool same(const char * a, const char * b)

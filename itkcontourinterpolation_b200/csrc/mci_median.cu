@@ -140,9 +140,8 @@ __global__ void __launch_bounds__(MED_THREADS) k_median3d(const T * __restrict__
   __shared__ int sLo, sHi, sNext[MED_DMAX];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const unsigned tile = blockIdx.x;
-  const int tx = (int)(tile % (unsigned)tilesX), ty = (int)((tile / (unsigned)tilesX) % (unsigned)tilesY),
-            tz = (int)(tile / ((unsigned)tilesX * (unsigned)tilesY));
+  const int tx = blockIdx.x, ty = blockIdx.y, tz = blockIdx.z; // grid = tiles along x, y, z
+  const long long tile = ((long long)tz * tilesY + ty) * tilesX + tx;
   const int x0 = tx * MED_TX, y0 = ty * MED_TY, z0 = tz * MED_TZ;
   const long long XY = (long long)X * Y;
   if (tid == 0)
@@ -201,15 +200,28 @@ __global__ void __launch_bounds__(MED_THREADS) k_median3d(const T * __restrict__
   }
 
   // ---- 1. stage 48-pixel rows of tile + halo as 16-bit keys (clamped coordinates = ZeroFluxNeumann)
-  if (sizeof(T) == 2 && (X % 8) == 0 && x0 >= MED_PADL && x0 - MED_PADL + MED_RW <= X && (reinterpret_cast<size_t>(in) & 15) == 0)
+  if (sizeof(T) == 2 && (X % 8) == 0 && (reinterpret_cast<size_t>(in) & 15) == 0)
   {
-    // interior in x, 16-bit pixels: six 16-byte loads per row
+    // 16-bit pixels, rows 16-byte aligned: six 16-byte loads per row; a chunk beyond the volume's x range repeats
+    // the border pixel
     constexpr int CPR = MED_RW / 8;
     for (int i = tid; i < NROWS * CPR; i += MED_THREADS)
     {
       const int c = i % CPR, row = i / CPR, hy = row % HY, hz = row / HY;
       const int gy = min(max(y0 + hy - R, 0), Y - 1), gz = min(max(z0 + hz - R, 0), Z - 1);
-      uint4 q = __ldg(reinterpret_cast<const uint4 *>(in + (long long)gz * XY + (long long)gy * X + (x0 - MED_PADL)) + c);
+      const int xs = x0 - MED_PADL + 8 * c;
+      const T * rowp = in + (long long)gz * XY + (long long)gy * X;
+      uint4 q = __ldg(reinterpret_cast<const uint4 *>(rowp + min(max(xs, 0), X - 8)));
+      if (xs < 0)
+      {
+        const unsigned e = (q.x & 0xFFFFu) * 0x10001u;
+        q = make_uint4(e, e, e, e);
+      }
+      else if (xs >= X)
+      {
+        const unsigned e = (q.w >> 16) * 0x10001u;
+        q = make_uint4(e, e, e, e);
+      }
       if (std::is_same<T, int16_t>::value)
       {
         q.x ^= 0x80008000u;
@@ -532,17 +544,18 @@ launch_median_typed(Launch & L, const T * in, T * out, const long long dims[3], 
   L.pre("k_median_tiles");
   k_median_tiles<T><<<gridA, MED_THREADS, 0, L.stream>>>(in, summary, X, Y, Z, tilesX, tilesY, tiles);
   L.post("k_median_tiles");
+  const dim3 grid3((unsigned)tilesX, (unsigned)tilesY, (unsigned)tilesZ); // each volume dimension is at most 8192: <= 1024 tiles
   L.pre("k_median3d");
   switch (radius)
   {
     case 1:
-      k_median3d<T, 1><<<(unsigned)tiles, MED_THREADS, 0, L.stream>>>(in, out, X, Y, Z, tilesX, tilesY, tilesZ, summary);
+      k_median3d<T, 1><<<grid3, MED_THREADS, 0, L.stream>>>(in, out, X, Y, Z, tilesX, tilesY, tilesZ, summary);
       break;
     case 2:
-      k_median3d<T, 2><<<(unsigned)tiles, MED_THREADS, 0, L.stream>>>(in, out, X, Y, Z, tilesX, tilesY, tilesZ, summary);
+      k_median3d<T, 2><<<grid3, MED_THREADS, 0, L.stream>>>(in, out, X, Y, Z, tilesX, tilesY, tilesZ, summary);
       break;
     default:
-      k_median3d<T, 3><<<(unsigned)tiles, MED_THREADS, 0, L.stream>>>(in, out, X, Y, Z, tilesX, tilesY, tilesZ, summary);
+      k_median3d<T, 3><<<grid3, MED_THREADS, 0, L.stream>>>(in, out, X, Y, Z, tilesX, tilesY, tilesZ, summary);
   }
   L.post("k_median3d");
 }

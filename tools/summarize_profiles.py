@@ -25,10 +25,11 @@ def launches(path, out, title, lo=None, hi=None):
     recs = [(int(r[ci["ID"]]), short(r[ci["Kernel Name"]]), r[ci["Grid Size"]], r[ci["Block Size"]], float(r[ci["Metric Value"]]) / 1e3)
             for r in rows if r[ci["Metric Name"]] == "gpu__time_duration.sum"]
     if lo is None:
-        # one step = from the last k_copy_flag launch that is followed by a complete step
-        starts = [k for k, r in enumerate(recs) if r[1].startswith("k_copy_flag")]
-        a = starts[-2] if len(starts) >= 2 else starts[-1]
-        b = starts[-1] if len(starts) >= 2 else len(recs)
+        # one step = the launches from one k_copy_flag to the next; the second complete one (the first is the
+        # bit-exactness check through mci_filter_run, the later ones are warm-up / timed resident steps)
+        starts = [k for k, r in enumerate(recs) if r[1].startswith("k_copy_flag")] + [len(recs)]
+        segs = [(a, b) for a, b in zip(starts, starts[1:]) if any(r[1].startswith("k_dt_emit") or r[1].startswith("k_apply") for r in recs[a:b])]
+        a, b = segs[1] if len(segs) > 1 else segs[0]
         step = recs[a:b]
     else:
         step = [r for r in recs if lo <= r[0] <= hi]

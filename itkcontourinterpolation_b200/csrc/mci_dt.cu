@@ -125,6 +125,7 @@ k_dt_prep(const Node * __restrict__ nodes, const int * __restrict__ count, NodeW
           uint32_t * scratch, unsigned long long * scratchTop, unsigned long long scratchCap, DtItem * items, int * itemCount,
           int itemCap, DtItem * hitems, int * hitemCount, int hitemCap, int * err)
 {
+  pdl_wait();
   __shared__ int s_r0, s_r1;
   __shared__ unsigned long long s_off;
   __shared__ int s_item;
@@ -389,6 +390,7 @@ k_dt_hist(NodeWork * work, const DtItem * __restrict__ items, const int * __rest
           const uint32_t * __restrict__ scratch, unsigned * hist, int histStride, int histSide, unsigned * bigHist, int * bigCount,
           int nbig, int * err)
 {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   const int nItems = min(*itemCount, itemCap);
@@ -491,6 +493,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_dt_scan(NodeWork * work, const int * __restrict__ count, unsigned * hist, int histStride, int histSide, unsigned * bigHist)
 {
+  pdl_wait();
   __shared__ long long redA[8], redB[8], bestD[8];
   __shared__ int bestI[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -674,6 +677,7 @@ __global__ void __launch_bounds__(256)
 k_dt_median(NodeWork * work, const DtItem * __restrict__ items, const int * __restrict__ itemCount, uint32_t * scratch, int SU0,
             int SU1, int SU2, int * err)
 {
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nItems = *itemCount;
   for (int it = blockIdx.x; it < nItems; it += gridDim.x)
@@ -788,6 +792,7 @@ k_dt_alloc(NodeWork * work, const int * __restrict__ count, unsigned long long *
            int * nextCount, int nextCap, DtItem * witems, int * witemCount, int witemCap, EmitRec * emit, int * emitCount,
            int emitCap, unsigned long long emitBase, int * err)
 {
+  pdl_wait();
   const int nidx = blockIdx.x * blockDim.x + threadIdx.x;
   if (nidx >= *count)
     return;
@@ -968,6 +973,7 @@ k_dt_emit(const NodeWork * __restrict__ work, const DtItem * __restrict__ witems
           const uint32_t * __restrict__ scratch, uint32_t * arena, const T * __restrict__ in, T * out, long long VX, long long VY,
           long long VZ)
 {
+  pdl_wait();
   constexpr int VPQ = 8 / sizeof(T);       // voxels per aligned 8-byte group
   constexpr int GPW = 32 / VPQ + 1;        // groups a 32-pixel word can touch
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1191,16 +1197,19 @@ k_apply_masks(const EmitRec * __restrict__ recs, int nrecsHost, const int * __re
 // 8-byte groups with the max rule (X:754-763).
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_apply_axis0(const Axis0Group * __restrict__ groups, int ngroups, const EmitRec * __restrict__ recs, const int * __restrict__ slots,
-              const uint32_t * __restrict__ words, const T * __restrict__ in, T * out, long long VX, long long VY, long long VZ)
+k_apply_axis0(const Axis0Group * __restrict__ groups, int ngroups, int parts, const EmitRec * __restrict__ recs,
+              const int * __restrict__ slots, const uint32_t * __restrict__ words, const T * __restrict__ in, T * out, long long VX,
+              long long VY, long long VZ)
 {
   constexpr int VPQ = 8 / sizeof(T);
   __shared__ EmitRec s_rec[32];
   __shared__ int s_box[4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const unsigned long long nvox = (unsigned long long)VX * VY * VZ;
-  for (int gi = blockIdx.x; gi < ngroups; gi += gridDim.x)
+  // work unit = (group, part): the cells of a group are dealt to `parts` CTAs, there are far fewer trees than SMs x 8
+  for (int unit = blockIdx.x; unit < ngroups * parts; unit += gridDim.x)
   {
+    const int gi = unit / parts, part = unit - gi * parts;
     const Axis0Group G = groups[gi];
     __syncthreads(); // previous group done with s_rec / s_box
     if (threadIdx.x < 4)
@@ -1237,7 +1246,7 @@ k_apply_axis0(const Axis0Group * __restrict__ groups, int ngroups, const EmitRec
     const T label = (T)__shfl_sync(0xFFFFFFFFu, mine.label, src);
     const uint32_t * myWords = words + mine.M.off;
     const int ncw = (U1 - U0 + 31) >> 5, ncells = ncw * (V1 - V0);
-    for (int cell = warp; cell < ncells; cell += nwarps)
+    for (int cell = part * nwarps + warp; cell < ncells; cell += parts * nwarps)
     {
       const int v = V0 + cell / ncw, Uc = U0 + 32 * (cell % ncw);
       uint32_t W = 0u;
@@ -1320,20 +1329,21 @@ launch_apply_axis0(Launch & L, int ptype, const Axis0Group * groups, int ngroups
 {
   if (ngroups <= 0)
     return;
-  const int grid = std::max(1, std::min(ngroups, L.sms * 8));
+  const int parts = std::max(1, std::min(16, (L.sms * 8 + ngroups - 1) / ngroups));
+  const int grid = std::max(1, std::min(ngroups * parts, L.sms * 8));
   L.pre("k_apply_axis0");
   switch (ptype)
   {
     case MCI_U8:
-      k_apply_axis0<uint8_t><<<grid, 256, 0, L.stream>>>(groups, ngroups, recs, slots, words, (const uint8_t *)in, (uint8_t *)out, dims[0],
+      k_apply_axis0<uint8_t><<<grid, 256, 0, L.stream>>>(groups, ngroups, parts, recs, slots, words, (const uint8_t *)in, (uint8_t *)out, dims[0],
                                                          dims[1], dims[2]);
       break;
     case MCI_U16:
-      k_apply_axis0<uint16_t><<<grid, 256, 0, L.stream>>>(groups, ngroups, recs, slots, words, (const uint16_t *)in, (uint16_t *)out, dims[0],
+      k_apply_axis0<uint16_t><<<grid, 256, 0, L.stream>>>(groups, ngroups, parts, recs, slots, words, (const uint16_t *)in, (uint16_t *)out, dims[0],
                                                           dims[1], dims[2]);
       break;
     default:
-      k_apply_axis0<int16_t><<<grid, 256, 0, L.stream>>>(groups, ngroups, recs, slots, words, (const int16_t *)in, (int16_t *)out, dims[0],
+      k_apply_axis0<int16_t><<<grid, 256, 0, L.stream>>>(groups, ngroups, parts, recs, slots, words, (const int16_t *)in, (int16_t *)out, dims[0],
                                                          dims[1], dims[2]);
   }
   L.post("k_apply_axis0");
@@ -1349,22 +1359,22 @@ launch_dt_level(Launch & L, int ptype, const DtLevel & lv)
   const int itemGrid = std::max(1, std::min(lv.itemCap, L.sms * 8));
   const int histGrid = std::max(1, std::min((lv.hitemCap + 7) / 8, L.sms * 8));
   L.pre("k_dt_prep");
-  k_dt_prep<<<nodeGrid, 256, 0, L.stream>>>(lv.nodes, lv.count, lv.work, lv.arena, lv.scratch, lv.scratchTop, lv.scratchCap,
-                                             lv.items, lv.itemCount, lv.itemCap, lv.hitems, lv.hitemCount, lv.hitemCap, lv.err);
+  launch_pdl(k_dt_prep, nodeGrid, 256, 0, L.stream, lv.nodes, lv.count, lv.work, lv.arena, lv.scratch, lv.scratchTop, lv.scratchCap,
+             lv.items, lv.itemCount, lv.itemCap, lv.hitems, lv.hitemCount, lv.hitemCap, lv.err);
   L.post("k_dt_prep");
   L.pre("k_dt_hist");
   switch (ptype)
   {
     case MCI_U8:
-      k_dt_hist<uint8_t><<<histGrid, 256, 0, L.stream>>>(lv.work, lv.hitems, lv.hitemCount, lv.hitemCap, lv.scratch, lv.hist, lv.histStride,
+      launch_pdl(k_dt_hist<uint8_t>, histGrid, 256, 0, L.stream, lv.work, lv.hitems, lv.hitemCount, lv.hitemCap, lv.scratch, lv.hist, lv.histStride,
                                                           lv.histSide, lv.bigHist, lv.bigCount, lv.nbig, lv.err);
       break;
     case MCI_U16:
-      k_dt_hist<uint16_t><<<histGrid, 256, 0, L.stream>>>(lv.work, lv.hitems, lv.hitemCount, lv.hitemCap, lv.scratch, lv.hist, lv.histStride,
+      launch_pdl(k_dt_hist<uint16_t>, histGrid, 256, 0, L.stream, lv.work, lv.hitems, lv.hitemCount, lv.hitemCap, lv.scratch, lv.hist, lv.histStride,
                                                            lv.histSide, lv.bigHist, lv.bigCount, lv.nbig, lv.err);
       break;
     default:
-      k_dt_hist<int16_t><<<histGrid, 256, 0, L.stream>>>(lv.work, lv.hitems, lv.hitemCount, lv.hitemCap, lv.scratch, lv.hist, lv.histStride,
+      launch_pdl(k_dt_hist<int16_t>, histGrid, 256, 0, L.stream, lv.work, lv.hitems, lv.hitemCount, lv.hitemCap, lv.scratch, lv.hist, lv.histStride,
                                                           lv.histSide, lv.bigHist, lv.bigCount, lv.nbig, lv.err);
   }
   L.post("k_dt_hist");
@@ -1372,21 +1382,21 @@ launch_dt_level(Launch & L, int ptype, const DtLevel & lv)
   switch (ptype)
   {
     case MCI_U8:
-      k_dt_scan<uint8_t><<<nodeGrid, 256, 0, L.stream>>>(lv.work, lv.count, lv.hist, lv.histStride, lv.histSide, lv.bigHist);
+      launch_pdl(k_dt_scan<uint8_t>, nodeGrid, 256, 0, L.stream, lv.work, lv.count, lv.hist, lv.histStride, lv.histSide, lv.bigHist);
       break;
     case MCI_U16:
-      k_dt_scan<uint16_t><<<nodeGrid, 256, 0, L.stream>>>(lv.work, lv.count, lv.hist, lv.histStride, lv.histSide, lv.bigHist);
+      launch_pdl(k_dt_scan<uint16_t>, nodeGrid, 256, 0, L.stream, lv.work, lv.count, lv.hist, lv.histStride, lv.histSide, lv.bigHist);
       break;
     default:
-      k_dt_scan<int16_t><<<nodeGrid, 256, 0, L.stream>>>(lv.work, lv.count, lv.hist, lv.histStride, lv.histSide, lv.bigHist);
+      launch_pdl(k_dt_scan<int16_t>, nodeGrid, 256, 0, L.stream, lv.work, lv.count, lv.hist, lv.histStride, lv.histSide, lv.bigHist);
   }
   L.post("k_dt_scan");
   L.pre("k_dt_median");
-  k_dt_median<<<itemGrid, 256, 0, L.stream>>>(lv.work, lv.items, lv.itemCount, lv.scratch, (int)lv.dims[0], (int)lv.dims[1],
+  launch_pdl(k_dt_median, itemGrid, 256, 0, L.stream, lv.work, lv.items, lv.itemCount, lv.scratch, (int)lv.dims[0], (int)lv.dims[1],
                                                (int)lv.dims[2], lv.err);
   L.post("k_dt_median");
   L.pre("k_dt_alloc");
-  k_dt_alloc<<<(lv.maxNodes + 127) / 128, 128, 0, L.stream>>>(lv.work, lv.count, lv.arenaTop, lv.arenaCap, lv.next, lv.nextCount,
+  launch_pdl(k_dt_alloc, (lv.maxNodes + 127) / 128, 128, 0, L.stream, lv.work, lv.count, lv.arenaTop, lv.arenaCap, lv.next, lv.nextCount,
                                                                 lv.nextCap, lv.witems, lv.witemCount, lv.itemCap, lv.emit, lv.emitCount,
                                                                 lv.emitCap, lv.emitBase, lv.err);
   L.post("k_dt_alloc");
@@ -1394,17 +1404,17 @@ launch_dt_level(Launch & L, int ptype, const DtLevel & lv)
   switch (ptype)
   {
     case MCI_U8:
-      k_dt_emit<uint8_t><<<itemGrid, 256, 0, L.stream>>>(lv.work, lv.witems, lv.witemCount, lv.scratch, lv.arena,
+      launch_pdl(k_dt_emit<uint8_t>, itemGrid, 256, 0, L.stream, lv.work, lv.witems, lv.witemCount, lv.scratch, lv.arena,
                                                           (const uint8_t *)lv.in, (uint8_t *)lv.out, lv.dims[0], lv.dims[1],
                                                           lv.dims[2]);
       break;
     case MCI_U16:
-      k_dt_emit<uint16_t><<<itemGrid, 256, 0, L.stream>>>(lv.work, lv.witems, lv.witemCount, lv.scratch, lv.arena,
+      launch_pdl(k_dt_emit<uint16_t>, itemGrid, 256, 0, L.stream, lv.work, lv.witems, lv.witemCount, lv.scratch, lv.arena,
                                                            (const uint16_t *)lv.in, (uint16_t *)lv.out, lv.dims[0], lv.dims[1],
                                                            lv.dims[2]);
       break;
     default:
-      k_dt_emit<int16_t><<<itemGrid, 256, 0, L.stream>>>(lv.work, lv.witems, lv.witemCount, lv.scratch, lv.arena,
+      launch_pdl(k_dt_emit<int16_t>, itemGrid, 256, 0, L.stream, lv.work, lv.witems, lv.witemCount, lv.scratch, lv.arena,
                                                           (const int16_t *)lv.in, (int16_t *)lv.out, lv.dims[0], lv.dims[1],
                                                           lv.dims[2]);
   }

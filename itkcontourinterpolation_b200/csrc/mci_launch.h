@@ -93,6 +93,34 @@ struct Launch
   }
 };
 
+// Programmatic dependent launch: the kernel is queued with programmatic stream serialization, so its launch is
+// processed while its predecessor in the stream still runs; it calls pdl_wait() before touching anything the
+// predecessor wrote (no early trigger is used: its CTAs start when the predecessor has completed and flushed).
+// Shaves the launch gap off chains of short dependent kernels (the six kernels of a distance-transform level).
+template <typename... KArgs, typename... Args>
+inline void
+launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void
+pdl_wait()
+{
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
+
 struct DtLevel
 {
   const Node * nodes;

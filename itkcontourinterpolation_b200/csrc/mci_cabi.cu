@@ -189,6 +189,7 @@ struct TableSegs
 };
 __global__ void __launch_bounds__(256) k_table_copy(TableSegs t)
 {
+  pdl_wait();
   for (int k = 0; k < t.n; ++k)
   {
     const TableSeg sg = t.s[k];
@@ -224,7 +225,7 @@ struct TableCopy
       return;
     const int grid = (int)std::max(1u, std::min((maxWords + 1023) / 1024, 64u));
     L.pre("k_table_copy");
-    k_table_copy<<<grid, 256, 0, L.stream>>>(t);
+    launch_pdl(k_table_copy, grid, 256, 0, L.stream, t);
     L.post("k_table_copy");
   }
 };
@@ -1278,7 +1279,7 @@ extern "C"
         levelCap[d] += nn;
         levelScratch[d] += (u64)nn * (3 * nodeWords + (u64)bh + (u64)bh / 8 + 16);
         levelItems[d] += (u64)nn * (nodeWords / 256 + 1);
-        levelHItems[d] += (u64)nn * (nodeWords / 8 + 1);
+        levelHItems[d] += (u64)nn * (nodeWords / MCI_DT_HCHUNK + 1);
       }
     }
 

@@ -24,6 +24,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_slice_bits(const T * __restrict__ in, const SliceDev * __restrict__ slices, const RowTile * __restrict__ tiles, uint32_t * bitsAll)
 {
+  pdl_wait();
   const RowTile tile = tiles[blockIdx.x];
   const SliceDev S = slices[tile.item];
   const int cw = (S.w + 31) >> 5;
@@ -78,6 +79,7 @@ k_cc_runs(const SliceDev * __restrict__ slices, const uint32_t * __restrict__ bi
           uint32_t * runScratch, int fully, int * ncompArr, int * compBaseArr, int * totalComp, CompStat * stats, int statCap,
           int maxPerSlice, int * err)
 {
+  pdl_wait();
   extern __shared__ uint32_t smem[];
   __shared__ int s_wsum[CC_THREADS / 32];
   __shared__ int s_carry, s_total, s_base;
@@ -327,6 +329,7 @@ __global__ void __launch_bounds__(256)
 k_cc_paint(const SliceDev * __restrict__ slices, const RowTile * __restrict__ tiles, const uint32_t * __restrict__ bitsAll,
            const uint32_t * __restrict__ wordRunAll, const uint32_t * __restrict__ runCompAll, uint16_t * connAll)
 {
+  pdl_wait();
   const RowTile tile = tiles[blockIdx.x];
   const SliceDev S = slices[tile.item];
   const int cw = (S.w + 31) >> 5;
@@ -366,24 +369,24 @@ launch_cc(Launch & L, int ptype, const void * in, const SliceDev * slices, int n
   switch (ptype)
   {
     case MCI_U8:
-      k_slice_bits<uint8_t><<<ntiles, 256, 0, L.stream>>>((const uint8_t *)in, slices, tiles, bits);
+      launch_pdl(k_slice_bits<uint8_t>, ntiles, 256, 0, L.stream, (const uint8_t *)in, slices, tiles, bits);
       break;
     case MCI_U16:
-      k_slice_bits<uint16_t><<<ntiles, 256, 0, L.stream>>>((const uint16_t *)in, slices, tiles, bits);
+      launch_pdl(k_slice_bits<uint16_t>, ntiles, 256, 0, L.stream, (const uint16_t *)in, slices, tiles, bits);
       break;
     default:
-      k_slice_bits<int16_t><<<ntiles, 256, 0, L.stream>>>((const int16_t *)in, slices, tiles, bits);
+      launch_pdl(k_slice_bits<int16_t>, ntiles, 256, 0, L.stream, (const int16_t *)in, slices, tiles, bits);
   }
   L.post("k_slice_bits");
   L.ensure_max_smem(k_cc_runs, 0, L.maxSmem - 2048);
   const int smemBytes = ((maxRows + 1) + 3 * CC_SMEM_RUNS) * 4;
   const int maxPer = ptype == MCI_U8 ? 255 : (ptype == MCI_U16 ? 65535 : 32767);
   L.pre("k_cc_runs");
-  k_cc_runs<<<nslices, CC_THREADS, smemBytes, L.stream>>>(slices, bits, wordRun, runComp, runScratch, fully, ncomp, compBase, total,
+  launch_pdl(k_cc_runs, nslices, CC_THREADS, smemBytes, L.stream, slices, bits, wordRun, runComp, runScratch, fully, ncomp, compBase, total,
                                                            stats, statCap, maxPer, err);
   L.post("k_cc_runs");
   L.pre("k_cc_paint");
-  k_cc_paint<<<ntiles, 256, 0, L.stream>>>(slices, tiles, bits, wordRun, runComp, conn);
+  launch_pdl(k_cc_paint, ntiles, 256, 0, L.stream, slices, tiles, bits, wordRun, runComp, conn);
   L.post("k_cc_paint");
 }
 

@@ -311,6 +311,7 @@ k_dil_nodes(const Node * __restrict__ nodes, const int * __restrict__ count, Nod
             long long VY, long long VZ, int ball, unsigned * stepHistAll, uint32_t * slabAll, unsigned long long slabWords,
             unsigned short * arrAll, unsigned long long arrPixels, int smemWords, EmitRec * emit, int * emitCount, int emitCap, unsigned long long emitBase, int * err)
 {
+  pdl_wait();
   extern __shared__ uint32_t smem[];
   __shared__ DilShared sh;
   unsigned * hI = stepHistAll + (size_t)blockIdx.x * 2 * DIL_STEPS; // hI[s], s = 1..Ki: pixels of i\\j joining at step s
@@ -663,7 +664,7 @@ launch_dil_t(Launch & L, const Node * nodes, const int * count, int maxNodes, No
   L.ensure_max_smem(k_dil_nodes<T>, 3 + (int)sizeof(T) + (std::is_signed<T>::value ? 1 : 0), L.maxSmem - 2048);
   const int g = std::max(1, std::min(grid, maxNodes));
   L.pre("k_dil_nodes");
-  k_dil_nodes<T><<<g, DIL_THREADS, smemBytes, L.stream>>>(nodes, count, next, nextCount, nextCap, arena, arenaTop, arenaCap,
+  launch_pdl(k_dil_nodes<T>, g, DIL_THREADS, smemBytes, L.stream, nodes, count, next, nextCount, nextCap, arena, arenaTop, arenaCap,
                                                           (const T *)in, (T *)out, dims[0], dims[1], dims[2], ball, stepHist, slab,
                                                           slabWords, arr, arrPixels, smemBytes / 4, emit, emitCount, emitCap, emitBase, err);
   L.post("k_dil_nodes");

@@ -21,7 +21,7 @@ namespace mci
 {
 
 #define DT_CHUNK 256 // words of a node's bit rows per work item (one CTA: 8 warps x 32 words)
-#define DT_HCHUNK 8  // words per histogram work item (one warp), emitted only where (i xor j) pixels exist
+#define DT_HCHUNK MCI_DT_HCHUNK // words per histogram work item (one warp), emitted only where (i xor j) pixels exist
 #define DT_BIG_STRIDE (2 * 65536 + 2048) // wrapped-bin table: counts of both sides + bitmap of touched bins
 
 __device__ __forceinline__ uint32_t
@@ -257,7 +257,7 @@ k_dt_prep(const Node * __restrict__ nodes, const int * __restrict__ count, NodeW
       }
       rowInfo[h + bnd] = b >= 0 ? pack_row(a, b, false) : 0u;
     }
-    // histogram work items: 8-word chunks that hold (i xor j) pixels (skipped when the intersection is empty)
+    // histogram work items: DT_HCHUNK-word chunks that hold (i xor j) pixels (skipped when the intersection is empty)
     if (s_r1 >= 0)
     {
       const int nChunks = (words + DT_HCHUNK - 1) / DT_HCHUNK;
@@ -408,7 +408,7 @@ k_dt_hist(NodeWork * work, const DtItem * __restrict__ items, const int * __rest
     unsigned * h0 = hist + (size_t)item.node * histStride;
     int maxSmall = -1, maxBig = -1;
     const int wBeg = item.w0;
-    // lane i < 8 owns word wBeg+i; the pixels of the chunk are dealt out one per lane
+    // lane i < DT_HCHUNK owns word wBeg+i; the pixels of the chunk are dealt out one per lane
     const int myIdx = wBeg + lane;
     const bool mine = lane < DT_HCHUNK && myIdx < words;
     const uint32_t myS = mine ? __ldg(Sb + myIdx) : 0u;
@@ -1092,6 +1092,7 @@ __global__ void __launch_bounds__(256)
 k_apply_masks(const EmitRec * __restrict__ recs, int nrecsHost, const int * __restrict__ nrecsDev, const uint32_t * __restrict__ words,
               const T * __restrict__ in, T * out, long long VX, long long VY, long long VZ, int skipAxis0)
 {
+  pdl_wait();
   const int nrecs = nrecsDev ? min(*nrecsDev, nrecsHost) : nrecsHost; // device-side count capped by the list capacity
   constexpr int VPQ = 8 / sizeof(T);
   constexpr int GPW = 32 / VPQ + 1;
@@ -1201,6 +1202,7 @@ k_apply_axis0(const Axis0Group * __restrict__ groups, int ngroups, int parts, co
               const int * __restrict__ slots, const uint32_t * __restrict__ words, const T * __restrict__ in, T * out, long long VX,
               long long VY, long long VZ)
 {
+  pdl_wait();
   constexpr int VPQ = 8 / sizeof(T);
   __shared__ EmitRec s_rec[32];
   __shared__ int s_box[4];
@@ -1309,15 +1311,15 @@ launch_apply_masks(Launch & L, int ptype, const EmitRec * recs, int nrecs, const
   switch (ptype)
   {
     case MCI_U8:
-      k_apply_masks<uint8_t><<<grid, 256, 0, L.stream>>>(recs, nrecs, nrecsDev, words, (const uint8_t *)in, (uint8_t *)out, dims[0], dims[1],
+      launch_pdl(k_apply_masks<uint8_t>, grid, 256, 0, L.stream, recs, nrecs, nrecsDev, words, (const uint8_t *)in, (uint8_t *)out, dims[0], dims[1],
                                                          dims[2], skipAxis0);
       break;
     case MCI_U16:
-      k_apply_masks<uint16_t><<<grid, 256, 0, L.stream>>>(recs, nrecs, nrecsDev, words, (const uint16_t *)in, (uint16_t *)out, dims[0],
+      launch_pdl(k_apply_masks<uint16_t>, grid, 256, 0, L.stream, recs, nrecs, nrecsDev, words, (const uint16_t *)in, (uint16_t *)out, dims[0],
                                                            dims[1], dims[2], skipAxis0);
       break;
     default:
-      k_apply_masks<int16_t><<<grid, 256, 0, L.stream>>>(recs, nrecs, nrecsDev, words, (const int16_t *)in, (int16_t *)out, dims[0], dims[1],
+      launch_pdl(k_apply_masks<int16_t>, grid, 256, 0, L.stream, recs, nrecs, nrecsDev, words, (const int16_t *)in, (int16_t *)out, dims[0], dims[1],
                                                           dims[2], skipAxis0);
   }
   L.post("k_apply_masks");
@@ -1335,15 +1337,15 @@ launch_apply_axis0(Launch & L, int ptype, const Axis0Group * groups, int ngroups
   switch (ptype)
   {
     case MCI_U8:
-      k_apply_axis0<uint8_t><<<grid, 256, 0, L.stream>>>(groups, ngroups, parts, recs, slots, words, (const uint8_t *)in, (uint8_t *)out, dims[0],
+      launch_pdl(k_apply_axis0<uint8_t>, grid, 256, 0, L.stream, groups, ngroups, parts, recs, slots, words, (const uint8_t *)in, (uint8_t *)out, dims[0],
                                                          dims[1], dims[2]);
       break;
     case MCI_U16:
-      k_apply_axis0<uint16_t><<<grid, 256, 0, L.stream>>>(groups, ngroups, parts, recs, slots, words, (const uint16_t *)in, (uint16_t *)out, dims[0],
+      launch_pdl(k_apply_axis0<uint16_t>, grid, 256, 0, L.stream, groups, ngroups, parts, recs, slots, words, (const uint16_t *)in, (uint16_t *)out, dims[0],
                                                           dims[1], dims[2]);
       break;
     default:
-      k_apply_axis0<int16_t><<<grid, 256, 0, L.stream>>>(groups, ngroups, parts, recs, slots, words, (const int16_t *)in, (int16_t *)out, dims[0],
+      launch_pdl(k_apply_axis0<int16_t>, grid, 256, 0, L.stream, groups, ngroups, parts, recs, slots, words, (const int16_t *)in, (int16_t *)out, dims[0],
                                                          dims[1], dims[2]);
   }
   L.post("k_apply_axis0");

@@ -331,6 +331,7 @@ __global__ void __launch_bounds__(256) k_detect_marked(const T * __restrict__ in
                                                        long long Z, int axisSel, int * bbox, int nl, uint32_t * sliceBits,
                                                        int wordsPerLabel, int wo1, int wo2, const uint32_t * __restrict__ chunkBits)
 {
+  pdl_wait();
   constexpr int VEC = 16 / sizeof(T);
   const long long n = X * Y * Z;
   const long long nfull = n / VEC;
@@ -395,6 +396,7 @@ __global__ void
 k_compact_labels(const int * __restrict__ bbox, int nl, const uint32_t * __restrict__ sliceBits, int wordsPerLabel, int wo1,
                  int wo2, int signedLabels, mci_label_info * labels, mci_labeled_slice * slices, int capSlices, int * counters)
 {
+  pdl_wait();
   int li = blockIdx.x * blockDim.x + threadIdx.x;
   if (li >= nl)
     return;
@@ -465,15 +467,15 @@ launch_detect(Launch & L, int ptype, const void * in, void * out, const long lon
   switch (ptype)
   {
     case MCI_U8:
-      k_detect_marked<uint8_t><<<gridB, 256, 0, L.stream>>>((const uint8_t *)in, (uint8_t *)out, dims[0], dims[1], dims[2], axisSel,
+      launch_pdl(k_detect_marked<uint8_t>, gridB, 256, 0, L.stream, (const uint8_t *)in, (uint8_t *)out, dims[0], dims[1], dims[2], axisSel,
                                                             bbox, nl, sliceBits, wordsPerLabel, wo1, wo2, chunkBits);
       break;
     case MCI_U16:
-      k_detect_marked<uint16_t><<<gridB, 256, 0, L.stream>>>((const uint16_t *)in, (uint16_t *)out, dims[0], dims[1], dims[2],
+      launch_pdl(k_detect_marked<uint16_t>, gridB, 256, 0, L.stream, (const uint16_t *)in, (uint16_t *)out, dims[0], dims[1], dims[2],
                                                              axisSel, bbox, nl, sliceBits, wordsPerLabel, wo1, wo2, chunkBits);
       break;
     default:
-      k_detect_marked<int16_t><<<gridB, 256, 0, L.stream>>>((const int16_t *)in, (int16_t *)out, dims[0], dims[1], dims[2], axisSel,
+      launch_pdl(k_detect_marked<int16_t>, gridB, 256, 0, L.stream, (const int16_t *)in, (int16_t *)out, dims[0], dims[1], dims[2], axisSel,
                                                             bbox, nl, sliceBits, wordsPerLabel, wo1, wo2, chunkBits);
   }
   L.post("k_detect_marked");
@@ -484,7 +486,7 @@ launch_compact_labels(Launch & L, const int * bbox, int nl, const uint32_t * sli
                       int signedLabels, mci_label_info * labels, mci_labeled_slice * slices, int capSlices, int * counters)
 {
   L.pre("k_compact_labels");
-  k_compact_labels<<<(nl + 255) / 256, 256, 0, L.stream>>>(bbox, nl, sliceBits, wordsPerLabel, wo1, wo2, signedLabels, labels,
+  launch_pdl(k_compact_labels, (nl + 255) / 256, 256, 0, L.stream, bbox, nl, sliceBits, wordsPerLabel, wo1, wo2, signedLabels, labels,
                                                           slices, capSlices, counters);
   L.post("k_compact_labels");
 }
@@ -549,6 +551,7 @@ k_pairs(const SliceDev * __restrict__ slices, const SegDev * __restrict__ segs, 
         const uint16_t * __restrict__ connAll, u64 * table, uint32_t tableMask, mci_pair * pairs, int capPairs, int * nPairs,
         int * err)
 {
+  pdl_wait();
   const RowTile tile = tiles[blockIdx.x];
   const SegDev G = segs[tile.item];
   const SliceDev A = slices[G.si], B = slices[G.sj];
@@ -610,7 +613,7 @@ launch_pairs(Launch & L, const SliceDev * slices, const SegDev * segs, const Row
   if (ntiles == 0)
     return;
   L.pre("k_pairs");
-  k_pairs<<<ntiles, 256, 0, L.stream>>>(slices, segs, tiles, conn, table, tableMask, pairs, capPairs, nPairs, err);
+  launch_pdl(k_pairs, ntiles, 256, 0, L.stream, slices, segs, tiles, conn, table, tableMask, pairs, capPairs, nPairs, err);
   L.post("k_pairs");
 }
 
@@ -621,6 +624,7 @@ __global__ void __launch_bounds__(256)
 k_extract(const SliceDev * __restrict__ slices, const ExtractJob * __restrict__ jobs, const uint16_t * __restrict__ connAll,
           uint32_t * arena)
 {
+  pdl_wait();
   const ExtractJob J = jobs[blockIdx.x];
   const SliceDev S = slices[J.slice];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -648,7 +652,7 @@ launch_extract(Launch & L, const SliceDev * slices, const ExtractJob * jobs, int
   if (njobs == 0)
     return;
   L.pre("k_extract");
-  k_extract<<<njobs, 256, 0, L.stream>>>(slices, jobs, conn, arena);
+  launch_pdl(k_extract, njobs, 256, 0, L.stream, slices, jobs, conn, arena);
   L.post("k_extract");
 }
 
@@ -903,6 +907,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS)
 k_align(const AlignJob * __restrict__ jobs, int njobs, const MaskRef * __restrict__ refs, const uint32_t * __restrict__ arena,
         uint32_t * gscratch, int heuristic, int2 * result, int4 * dbg, int * err)
 {
+  pdl_wait();
   extern __shared__ uint32_t smem[];
   __shared__ AlignBfsShared s_bfs;
   __shared__ AlignShape s_A, s_B[ALIGN_MAX_STAGED];
@@ -1041,7 +1046,7 @@ launch_align(Launch & L, const AlignJob * jobs, int njobs, const MaskRef * refs,
   L.ensure_max_smem(k_align, 1, L.maxSmem - 1024);
   int grid = std::min(njobs, L.sms * 8);
   L.pre("k_align");
-  k_align<<<grid, ALIGN_THREADS, smemBytes + ALIGN_MASK_WORDS * 4, L.stream>>>(jobs, njobs, refs, arena, gscratch, heuristic,
+  launch_pdl(k_align, grid, ALIGN_THREADS, smemBytes + ALIGN_MASK_WORDS * 4, L.stream, jobs, njobs, refs, arena, gscratch, heuristic,
                                                                               result, dbg, err);
   L.post("k_align");
 }
@@ -1121,11 +1126,58 @@ k_split(const SplitJob * __restrict__ jobs, const MaskRef * __restrict__ refs, u
   const bool has0 = idx0 < words;
   const int r0 = has0 ? idx0 / A.pitch : 0, wi0 = has0 ? idx0 - r0 * A.pitch : 0;
   const uint32_t m0 = has0 ? mask[idx0] : 0u;
+  // One word per thread (fast): a word is recomputed only if its row or a neighbouring row changed in the previous
+  // step -- the growth front is thin, most words are idle most of the time.  s_rowLast[b][r] = last step with
+  // parity b in which row r changed; an idle word's planes are already equal in both buffers (it did not change
+  // in the previous step either), so skipping it leaves the ping-pong consistent.
+  __shared__ int s_rowLast[2][SPLIT_THREADS];
+  const bool fast = inSmem && words <= (int)blockDim.x; // then A.h <= words <= SPLIT_THREADS
+  if (fast)
+    for (int r = threadIdx.x; r < A.h; r += blockDim.x)
+      s_rowLast[0][r] = s_rowLast[1][r] = -1;
+  __syncthreads();
+  int hasFree0 = 0;
   for (int step = 0; step < maxSteps && pending; ++step)
   {
     const uint32_t * C = curIsFirst ? firstBuf : secondBuf;
     uint32_t * N = curIsFirst ? secondBuf : firstBuf;
     int flag = 0;
+    if (fast)
+    {
+      if (has0 && !(settled & 1u))
+      {
+        bool act = step == 0;
+        if (!act)
+        {
+          const int * rl = s_rowLast[(step - 1) & 1];
+          act = rl[r0] == step - 1 || (r0 > 0 && rl[r0 - 1] == step - 1) || (r0 + 1 < A.h && rl[r0 + 1] == step - 1);
+        }
+        if (act)
+        {
+          uint32_t owned = 0;
+          for (int k = 0; k < nB; ++k)
+            owned |= C[(size_t)k * words + idx0];
+          const uint32_t freeBits = m0 & ~owned;
+          uint32_t taken = 0;
+          for (int k = 0; k < nB; ++k)
+          {
+            const uint32_t * c = C + (size_t)k * words;
+            const uint32_t g = freeBits ? (dilate_word(c, A.h, A.pitch, r0, wi0, ball != 0) & freeBits & ~taken) : 0u;
+            N[(size_t)k * words + idx0] = c[idx0] | g;
+            taken |= g;
+          }
+          if (taken)
+            s_rowLast[step & 1][r0] = step;
+          hasFree0 = (freeBits & ~taken) != 0u;
+          if (!freeBits)
+            settled |= 1u;
+        }
+        flag = hasFree0;
+      }
+      pending = __syncthreads_or(flag);
+      curIsFirst = !curIsFirst;
+      continue;
+    }
     int j = 0;
     for (int idx = idx0; idx < words; idx += blockDim.x, ++j)
     {
@@ -1198,6 +1250,7 @@ __global__ void
 k_make_roots(const RootJob * __restrict__ roots, int nroots, MaskRef * refs, uint32_t * arena, const int2 * __restrict__ trans,
              Node * nodes)
 {
+  pdl_wait();
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nroots)
     return;
@@ -1267,7 +1320,7 @@ launch_make_roots(Launch & L, const RootJob * roots, int nroots, MaskRef * refs,
   if (nroots == 0)
     return;
   L.pre("k_make_roots");
-  k_make_roots<<<(nroots + 127) / 128, 128, 0, L.stream>>>(roots, nroots, refs, arena, trans, nodes);
+  launch_pdl(k_make_roots, (nroots + 127) / 128, 128, 0, L.stream, roots, nroots, refs, arena, trans, nodes);
   L.post("k_make_roots");
 }
 

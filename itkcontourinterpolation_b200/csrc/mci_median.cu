@@ -122,6 +122,7 @@ template <typename T, int R>
 __global__ void __launch_bounds__(MED_THREADS) k_median3d(const T * __restrict__ in, T * __restrict__ out, int X, int Y, int Z,
                                                           int tilesX, int tilesY, int tilesZ, const unsigned * __restrict__ summary)
 {
+  pdl_wait();
   constexpr int HY = MED_TY + 2 * R, HZ = MED_TZ + 2 * R;
   constexpr int NROWS = HY * HZ;            // halo rows
   constexpr int C0 = MED_PADL - R;          // column of the window's first pixel for output ox = 0
@@ -549,13 +550,13 @@ launch_median_typed(Launch & L, const T * in, T * out, const long long dims[3], 
   switch (radius)
   {
     case 1:
-      k_median3d<T, 1><<<grid3, MED_THREADS, 0, L.stream>>>(in, out, X, Y, Z, tilesX, tilesY, tilesZ, summary);
+      launch_pdl(k_median3d<T, 1>, grid3, MED_THREADS, 0, L.stream, in, out, X, Y, Z, tilesX, tilesY, tilesZ, summary);
       break;
     case 2:
-      k_median3d<T, 2><<<grid3, MED_THREADS, 0, L.stream>>>(in, out, X, Y, Z, tilesX, tilesY, tilesZ, summary);
+      launch_pdl(k_median3d<T, 2>, grid3, MED_THREADS, 0, L.stream, in, out, X, Y, Z, tilesX, tilesY, tilesZ, summary);
       break;
     default:
-      k_median3d<T, 3><<<grid3, MED_THREADS, 0, L.stream>>>(in, out, X, Y, Z, tilesX, tilesY, tilesZ, summary);
+      launch_pdl(k_median3d<T, 3>, grid3, MED_THREADS, 0, L.stream, in, out, X, Y, Z, tilesX, tilesY, tilesZ, summary);
   }
   L.post("k_median3d");
 }

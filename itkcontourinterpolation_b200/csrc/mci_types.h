@@ -10,6 +10,11 @@ namespace mci
 
 typedef unsigned long long u64;
 
+// Words (32 pixels each) per histogram work item of the distance-transform median: one warp searches the nearest
+// intersection pixel for every (i xor j) pixel of the item, and a level lasts as long as its slowest item, so items are
+// kept small (2 words = at most two pixels per lane) -- the host sizes the item list with the same constant.
+#define MCI_DT_HCHUNK 2
+
 // A bit-packed 2-D mask living in the mask arena.  Pixel (x, y) of the slice, with
 // x0 <= x < x0+w and y0 <= y < y0+h, is bit ((x-x0)&31) of word off + (y-y0)*pitch + ((x-x0)>>5).
 // Bits at or beyond w in the last word of a row are always 0.

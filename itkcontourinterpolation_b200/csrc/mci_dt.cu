@@ -392,7 +392,9 @@ k_dt_hist(NodeWork * work, const DtItem * __restrict__ items, const int * __rest
 {
   pdl_wait();
   const int lane = threadIdx.x & 31;
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  // consecutive items belong to one node and cost about the same (far pixels search many rows): deal them to
+  // consecutive CTAs, not to the warps of one CTA, so that no SM collects a run of expensive ones
+  const int gw = (threadIdx.x >> 5) * gridDim.x + blockIdx.x, nw = (gridDim.x * blockDim.x) >> 5;
   const int nItems = min(*itemCount, itemCap);
   constexpr bool kBinsOnly = sizeof(T) == 1; // uchar: 256 wrapped bins, indexed directly
   constexpr int kSmall = PixTraits<T>::kNoWrapD2;

@@ -662,7 +662,7 @@ launch_extract(Launch & L, const SliceDev * slices, const ExtractJob * jobs, int
 // queued-but-unscored entries are scored in parallel (one warp each); one thread then replays the
 // reference's sequential pop / compare / expand logic over those scores, which pushes the next wave.
 // ================================================================================================
-#define ALIGN_THREADS 512
+#define ALIGN_THREADS 1024
 #define ALIGN_MASK_WORDS 12288 // shared-memory budget (words) for staging the shapes of one job
 #define ALIGN_MAX_STAGED 8     // components of the other slice kept staged / addressed per job
 
@@ -1126,58 +1126,11 @@ k_split(const SplitJob * __restrict__ jobs, const MaskRef * __restrict__ refs, u
   const bool has0 = idx0 < words;
   const int r0 = has0 ? idx0 / A.pitch : 0, wi0 = has0 ? idx0 - r0 * A.pitch : 0;
   const uint32_t m0 = has0 ? mask[idx0] : 0u;
-  // One word per thread (fast): a word is recomputed only if its row or a neighbouring row changed in the previous
-  // step -- the growth front is thin, most words are idle most of the time.  s_rowLast[b][r] = last step with
-  // parity b in which row r changed; an idle word's planes are already equal in both buffers (it did not change
-  // in the previous step either), so skipping it leaves the ping-pong consistent.
-  __shared__ int s_rowLast[2][SPLIT_THREADS];
-  const bool fast = inSmem && words <= (int)blockDim.x; // then A.h <= words <= SPLIT_THREADS
-  if (fast)
-    for (int r = threadIdx.x; r < A.h; r += blockDim.x)
-      s_rowLast[0][r] = s_rowLast[1][r] = -1;
-  __syncthreads();
-  int hasFree0 = 0;
   for (int step = 0; step < maxSteps && pending; ++step)
   {
     const uint32_t * C = curIsFirst ? firstBuf : secondBuf;
     uint32_t * N = curIsFirst ? secondBuf : firstBuf;
     int flag = 0;
-    if (fast)
-    {
-      if (has0 && !(settled & 1u))
-      {
-        bool act = step == 0;
-        if (!act)
-        {
-          const int * rl = s_rowLast[(step - 1) & 1];
-          act = rl[r0] == step - 1 || (r0 > 0 && rl[r0 - 1] == step - 1) || (r0 + 1 < A.h && rl[r0 + 1] == step - 1);
-        }
-        if (act)
-        {
-          uint32_t owned = 0;
-          for (int k = 0; k < nB; ++k)
-            owned |= C[(size_t)k * words + idx0];
-          const uint32_t freeBits = m0 & ~owned;
-          uint32_t taken = 0;
-          for (int k = 0; k < nB; ++k)
-          {
-            const uint32_t * c = C + (size_t)k * words;
-            const uint32_t g = freeBits ? (dilate_word(c, A.h, A.pitch, r0, wi0, ball != 0) & freeBits & ~taken) : 0u;
-            N[(size_t)k * words + idx0] = c[idx0] | g;
-            taken |= g;
-          }
-          if (taken)
-            s_rowLast[step & 1][r0] = step;
-          hasFree0 = (freeBits & ~taken) != 0u;
-          if (!freeBits)
-            settled |= 1u;
-        }
-        flag = hasFree0;
-      }
-      pending = __syncthreads_or(flag);
-      curIsFirst = !curIsFirst;
-      continue;
-    }
     int j = 0;
     for (int idx = idx0; idx < words; idx += blockDim.x, ++j)
     {
@@ -1205,7 +1158,9 @@ k_split(const SplitJob * __restrict__ jobs, const MaskRef * __restrict__ refs, u
       for (int k = 0; k < nB; ++k)
       {
         const uint32_t * c = C + (size_t)k * words;
-        const uint32_t g = freeBits ? (dilate_word(c, A.h, A.pitch, r, wi, ball != 0) & freeBits & ~taken) : 0u;
+        // unconditional: a step is latency bound (a few hundred of them in a row, one barrier each), so the neighbour
+        // loads must not wait for the `owned` loads above
+        const uint32_t g = dilate_word(c, A.h, A.pitch, r, wi, ball != 0) & freeBits & ~taken;
         N[(size_t)k * words + idx] = c[idx] | g;
         taken |= g;
       }
@@ -1234,8 +1189,8 @@ launch_split(Launch & L, const SplitJob * jobs, int njobs, const MaskRef * refs,
 {
   if (njobs == 0)
     return;
-  L.ensure_max_smem(k_split, 2, L.maxSmem - 1024);
   const int smemBytes = 160 * 1024;
+  L.ensure_max_smem(k_split, 2, smemBytes);
   L.pre("k_split");
   // one word per thread where the shapes allow it; fewer warps make the per-step barrier cheaper
   const int threads = std::max(128, std::min(SPLIT_THREADS, (maxWords + 31) / 32 * 32));

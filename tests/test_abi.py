@@ -68,3 +68,42 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.lower() or f == "synthetic.py", f
+
+
+def test_entry_points_reject_bad_arguments_without_touching_a_device():
+    # status codes, never exceptions or crashes ("All functions return int status (0 = ok), never throw")
+    lib = L.lib()
+    opt = L.FilterOptions()
+    lib.mci_filter_default_options(ctypes.byref(opt))
+    dims = (ctypes.c_int64 * 3)(4, 4, 4)
+    buf = (ctypes.c_uint16 * 64)()
+    assert lib.mci_filter_run(None, ctypes.byref(opt), buf, buf, dims, L.U16, None, 0, None) != 0
+    assert lib.mci_filter_run_resident(None, ctypes.byref(opt), None, 0, None) != 0
+    assert lib.mci_filter_run_batch(None, 1, ctypes.byref(opt), None, None, 0, dims, L.U16, None) != 0
+    one = (ctypes.c_void_p * 1)(None)
+    assert lib.mci_filter_run_batch(one, 1, ctypes.byref(opt), None, None, 0, dims, L.U16, None) != 0   # null context in the list
+    assert lib.mci_median_filter_run(None, buf, buf, dims, L.U16, 1) != 0
+    assert lib.mci_median_filter_resident(None, 1) != 0
+    assert lib.mci_set_wait_mode(None, 1) != 0
+    assert lib.mci_synchronize(None) != 0
+    assert lib.mci_upload_volume(None, buf, dims, L.U16) != 0
+    assert lib.mci_filter_schedule_pairs(None, 1, 1, None, 0, None, None, 0, None) != 0
+    assert lib.mci_last_error(None) == b"null context"
+    lib.mci_destroy(None)       # no-op
+    lib.mci_host_free(None)     # no-op
+
+
+def test_cpp_header_declares_the_reference_interface():
+    # every public method of the reference class (H:85-224) exists in the C++ mirror
+    text = open(os.path.join(ROOT, "include", "mci_b200_filter.hpp")).read()
+    for name in ("SetLabel", "GetLabel", "SetAxis", "GetAxis", "SetHeuristicAlignment", "GetHeuristicAlignment",
+                 "SetUseDistanceTransform", "GetUseDistanceTransform", "SetUseCustomSlicePositions", "GetUseCustomSlicePositions",
+                 "SetUseExtrapolation", "SetUseBallStructuringElement", "GetUseBallStructuringElement", "DetermineSliceOrientations",
+                 "ClearLabeledSliceIndices", "SetLabeledSliceIndices", "GetLabeledSliceIndices", "SliceSetType", "SliceIndicesType",
+                 "New()", "Update()", "GetOutput()", "SetInput"):
+        if name.startswith(("Set", "Get")) and name.endswith(("Label", "Axis", "Alignment", "Transform", "Positions", "Element")) \
+                and name not in ("SetUseExtrapolation",):
+            stem = name[3:]
+            assert ("MCI_B200_SET_GET(%s," % stem) in text or name in text, name
+        else:
+            assert name in text, name

@@ -51,31 +51,54 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """SM clock and throttle reasons sampled WHILE the timed region runs.  The region lasts tens of milliseconds, so the
+    samples come from NVML in a thread (one query every millisecond); nvidia-smi -lms is the fall-back."""
 
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.sm, self.mask, self.max_mhz = [], 0, None
+        self.stop = threading.Event()
+        self.thread = None
         self.proc = None
+        self.rows = []
+
+    def _nvml_loop(self, nv, h):
+        while not self.stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
+            self.thread = None
+            try:
+                q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                    "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                              "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                threading.Thread(target=lambda: [self.rows.append([c.strip() for c in l.split(",")]) for l in self.proc.stdout],
+                                 daemon=True).start()
+            except Exception:
+                self.proc = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def __exit__(self, *a):
+        self.stop.set()
+        if self.thread:
+            self.thread.join(timeout=1)
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
@@ -85,19 +108,20 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        reasons = [name for bit, name in self.REASONS if self.mask & bit]
+        sm, mx = list(self.sm), self.max_mhz
+        for r in self.rows:  # nvidia-smi fall-back
             try:
                 sm.append(float(r[0]))
-                mx.append(float(r[1]))
+                mx = max(mx or 0.0, float(r[1]))
             except Exception:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active") and name not in reasons:
+                    reasons.append(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def oracle_time(vol, cfg, threads, runs):
@@ -118,7 +142,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C3", choices=["C3", "C4", "C5"])
     ap.add_argument("--scale", type=float, default=1.0)
-    ap.add_argument("--depth", type=int, default=3, help="volumes in flight per GPU in the e2e throughput measurement")
+    ap.add_argument("--depth", type=int, default=0, help="volumes in flight per GPU in the e2e throughput measurement "
+                    "(0 = 3 on one GPU, fewer when several GPUs share the host's I/O path: 2 on two, 1 beyond)")
     ap.add_argument("--no-check", action="store_true", help="skip the bit-exact check against the oracle before timing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
@@ -282,7 +307,9 @@ def main():
     # ---- e2e, throughput mode: a series of volumes through mci_filter_run_batch -- `depth` contexts (own stream, own
     # host thread, own pinned in/out buffers each), so H2D of one volume, kernels of another and D2H of a third overlap.
     # Every volume still crosses PCIe in both directions inside the timed region.
-    depth = max(1, args.depth)
+    # one box's host memory / I/O path saturates near 105 GB/s whatever the GPU count: more volumes in
+    # flight than that path can feed only make the copies of all GPUs fight
+    depth = args.depth if args.depth > 0 else max(1, min(3, 4 // world))
     ctxs = [ctx]
     for _ in range(depth - 1):
         c = ctypes.c_void_p()

@@ -1045,9 +1045,12 @@ launch_align(Launch & L, const AlignJob * jobs, int njobs, const MaskRef * refs,
     return;
   L.ensure_max_smem(k_align, 1, L.maxSmem - 1024);
   int grid = std::min(njobs, L.sms * 8);
+  // at most one job per SM: the launch lasts as long as its slowest job, and more warps shorten every scoring wave;
+  // many jobs per SM: two smaller CTAs per SM keep the SM busy while one of them replays its queue
+  const int threads = njobs > L.sms ? ALIGN_THREADS / 2 : ALIGN_THREADS;
   L.pre("k_align");
-  launch_pdl(k_align, grid, ALIGN_THREADS, smemBytes + ALIGN_MASK_WORDS * 4, L.stream, jobs, njobs, refs, arena, gscratch, heuristic,
-                                                                              result, dbg, err);
+  launch_pdl(k_align, grid, threads, smemBytes + ALIGN_MASK_WORDS * 4, L.stream, jobs, njobs, refs, arena, gscratch, heuristic,
+             result, dbg, err);
   L.post("k_align");
 }
 

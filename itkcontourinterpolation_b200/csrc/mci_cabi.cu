@@ -1331,15 +1331,16 @@ extern "C"
     // ---- launches
     launch_extract(ctx->L, ctx->dSlices, (ExtractJob *)(jb + oExtract), (int)extracts.size(), (uint16_t *)ctx->dConn.p,
                    (uint32_t *)ctx->dArena.p);
-    // Align the 1-to-N jobs first; their splits then run on a second stream beside the alignment of the rest
+    // The 1-to-N jobs (alignment, then the split) take a second stream: they are few, and their chain is longer than
+    // the alignment of all the other jobs, which runs beside it on the main stream
     int4 * dDbg = (int4 *)((uint8_t *)ctx->dTrans.p + ((size_t(njobs) * sizeof(int2) + 15) & ~size_t(15)));
-    launch_align(ctx->L, (AlignJob *)(jb + oAlign), nSplitJobs, dRefs, (uint32_t *)ctx->dArena.p, (uint32_t *)ctx->dScratch.p,
-                 prm->heuristic_alignment, (int2 *)ctx->dTrans.p, dDbg, alignSmem, ctx->dErr);
     if (!splits.empty())
     {
-      CK(cudaEventRecord(ctx->evAlignedSplits, s));
+      CK(cudaEventRecord(ctx->evAlignedSplits, s)); // masks extracted
       CK(cudaStreamWaitEvent(ctx->stream2, ctx->evAlignedSplits, 0));
       ctx->L.stream = ctx->stream2;
+      launch_align(ctx->L, (AlignJob *)(jb + oAlign), nSplitJobs, dRefs, (uint32_t *)ctx->dArena.p, (uint32_t *)ctx->dScratch.p,
+                   prm->heuristic_alignment, (int2 *)ctx->dTrans.p, dDbg, alignSmem, ctx->dErr);
       launch_split(ctx->L, (SplitJob *)(jb + oSplit), (int)splits.size(), dRefs, (uint32_t *)ctx->dArena.p,
                    (uint32_t *)ctx->dScratch.p, (int2 *)ctx->dTrans.p, prm->use_ball, maxSplitWords, ctx->dErr);
       ctx->L.stream = s;

@@ -665,7 +665,6 @@ launch_extract(Launch & L, const SliceDev * slices, const ExtractJob * jobs, int
 #define ALIGN_THREADS 1024
 #define ALIGN_MASK_WORDS 12288 // shared-memory budget (words) for staging the shapes of one job
 #define ALIGN_MAX_STAGED 8     // components of the other slice kept staged / addressed per job
-#define ALIGN_PART_E 16        // translations per wave that the split scoring of 1-to-N jobs handles
 
 // a shape as the scoring loop sees it: geometry + where its rows live (arena or shared memory) + row pitch there
 struct AlignShape
@@ -749,8 +748,6 @@ align_shape(const MaskRef & m, const uint32_t * arena)
 struct AlignBfsShared
 {
   int head, tail, scored, done;
-  // 1-to-N jobs with few queued translations: per (translation, component) counts gathered from several warps
-  unsigned part[ALIGN_PART_E * ALIGN_MAX_STAGED];
 };
 __device__ __forceinline__ void
 align_bfs(const AlignJob & J, const AlignShape & A, const AlignShape * sB, const MaskRef * __restrict__ refs,
@@ -778,8 +775,6 @@ align_bfs(const AlignJob & J, const AlignShape & A, const AlignShape * sB, const
       st->scored = 0;
       st->done = 0;
     }
-    for (int k = threadIdx.x; k < ALIGN_PART_E * ALIGN_MAX_STAGED; k += blockDim.x)
-      st->part[k] = 0u;
     __syncthreads();
     for (;;)
     {
@@ -808,34 +803,6 @@ align_bfs(const AlignJob & J, const AlignShape & A, const AlignShape * sB, const
           unsigned c = align_count(A, sB[0], qx[e & qmask], qy[e & qmask], part, G, lane);
           if (lane == 0 && c)
             atomicAdd(&qs[e & qmask], c);
-        }
-      }
-      else if (J.nB <= ALIGN_MAX_STAGED && to - from <= ALIGN_PART_E && 2 * (to - from) * J.nB <= nwarps)
-      {
-        // few translations queued (every early wave): several warps share each (translation, component) count, so a
-        // wave costs one pass over a fraction of the rows instead of nB passes over all of them
-        const int nE = to - from, tasks = nE * J.nB, G = nwarps / tasks;
-        if (warp < tasks * G)
-        {
-          const int t = warp / G, part = warp - t * G, el = t / J.nB, k = t - el * J.nB;
-          const unsigned c = align_count(A, sB[k], qx[(from + el) & qmask], qy[(from + el) & qmask], part, G, lane);
-          if (lane == 0 && c)
-            atomicAdd((unsigned *)&st->part[el * ALIGN_MAX_STAGED + k], c);
-        }
-        __syncthreads();
-        // iConn must intersect every listed component of jConn, else the score is 0 (X:1068-1075)
-        if ((int)threadIdx.x < nE)
-        {
-          unsigned total = 0;
-          bool ok = true;
-          for (int k = 0; k < J.nB; ++k)
-          {
-            const unsigned c = st->part[threadIdx.x * ALIGN_MAX_STAGED + k];
-            st->part[threadIdx.x * ALIGN_MAX_STAGED + k] = 0u;
-            ok = ok && c != 0u;
-            total += c;
-          }
-          qs[(from + threadIdx.x) & qmask] = ok ? total : 0u;
         }
       }
       else

@@ -184,18 +184,23 @@ k_dt_prep(const Node * __restrict__ nodes, const int * __restrict__ count, NodeW
     uint32_t * Ib = Xb + words;
     uint32_t * Sb = Ib + words;
     uint32_t * rowInfo = Sb + words;
-    // translate, binarise, intersect (X:610-666); one warp per row so that row extents come for free
+    // translate, binarise, intersect (X:610-666); a group of GW lanes per row (GW = row pitch rounded up to a power of
+    // two, 32 / GW rows per warp at once) so that row extents come for free and narrow shapes still fill the warp
+    const int GW = pitch <= 1 ? 1 : (pitch <= 2 ? 2 : (pitch <= 4 ? 4 : (pitch <= 8 ? 8 : (pitch <= 16 ? 16 : 32))));
+    const int RPW = 32 / GW, sub = lane / GW, sl = lane - sub * GW;
     int r0 = 0x7FFFFFFF, r1 = -1;
-    for (int r = warp; r < h; r += 8)
+    for (int rb = warp * RPW; rb < h; rb += 8 * RPW)
     {
+      const int r = rb + sub;
+      const bool rowOk = r < h;
       const int y = uy0 + r;
       int first = 0x7FFFFFFF, last = -1, runs = 0;
       uint32_t prevTop = 0;
-      for (int wb = 0; wb < pitch; wb += 32)
+      for (int wb = 0; wb < pitch; wb += GW)
       {
-        const int wi = wb + lane;
+        const int wi = wb + sl;
         uint32_t a = 0, b = 0;
-        if (wi < pitch)
+        if (rowOk && wi < pitch)
         {
           const int x = ux0 + 32 * wi;
           a = mask_word(arena, nd.A, y - iT[1], x - iT[0]);
@@ -207,8 +212,8 @@ k_dt_prep(const Node * __restrict__ nodes, const int * __restrict__ count, NodeW
         }
         const uint32_t xw = a & b;
         // run starts in this word: set bits whose lower neighbour (previous bit, or top bit of the previous word) is clear
-        uint32_t below = __shfl_up_sync(0xFFFFFFFFu, xw, 1);
-        if (lane == 0)
+        uint32_t below = __shfl_up_sync(0xFFFFFFFFu, xw, 1, GW);
+        if (sl == 0)
           below = prevTop;
         const uint32_t starts = xw & ~((xw << 1) | (below >> 31));
         runs += __popc(starts);
@@ -217,16 +222,15 @@ k_dt_prep(const Node * __restrict__ nodes, const int * __restrict__ count, NodeW
           first = min(first, 32 * wi + __ffs(xw) - 1);
           last = max(last, 32 * wi + 31 - __clz(xw));
         }
-        prevTop = __shfl_sync(0xFFFFFFFFu, xw, 31);
+        prevTop = __shfl_sync(0xFFFFFFFFu, xw, GW - 1, GW);
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
+      for (int o = GW >> 1; o > 0; o >>= 1)
       {
         first = min(first, __shfl_xor_sync(0xFFFFFFFFu, first, o));
         last = max(last, __shfl_xor_sync(0xFFFFFFFFu, last, o));
         runs += __shfl_xor_sync(0xFFFFFFFFu, runs, o);
       }
-      if (lane == 0)
+      if (sl == 0 && rowOk)
       {
         rowInfo[r] = last >= 0 ? pack_row(first, last, runs == 1) : 0u;
         if (last >= 0)
@@ -235,6 +239,13 @@ k_dt_prep(const Node * __restrict__ nodes, const int * __restrict__ count, NodeW
           r1 = max(r1, r);
         }
       }
+    }
+    // rows of the whole warp (one leader lane per group held them)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      r0 = min(r0, __shfl_xor_sync(0xFFFFFFFFu, r0, o));
+      r1 = max(r1, __shfl_xor_sync(0xFFFFFFFFu, r1, o));
     }
     if (lane == 0 && r1 >= 0)
     {

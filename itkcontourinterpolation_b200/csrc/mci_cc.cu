@@ -93,25 +93,30 @@ k_cc_runs(const SliceDev * __restrict__ slices, const uint32_t * __restrict__ bi
   // shared: rowBase[h + 1]
   int * rowBase = (int *)smem;
 
+  // a group of GW lanes per row (GW = words per row rounded up to a power of two), 32 / GW rows per warp at once:
+  // label bounding boxes are a few words wide, a whole warp per row would leave most lanes idle
+  const int GW = cw <= 1 ? 1 : (cw <= 2 ? 2 : (cw <= 4 ? 4 : (cw <= 8 ? 8 : (cw <= 16 ? 16 : 32))));
+  const int RPW = 32 / GW, sub = lane / GW, sl = lane - sub * GW;
   // ---- 1. run starts per row
-  for (int y = warp; y < S.h; y += NW)
+  for (int yb = warp * RPW; yb < S.h; yb += NW * RPW)
   {
+    const int y = yb + sub;
+    const bool rowOk = y < S.h;
     int cnt = 0;
     uint32_t prevTop = 0;
-    for (int wb = 0; wb < cw; wb += 32)
+    for (int wb = 0; wb < cw; wb += GW)
     {
-      const int wi = wb + lane;
-      const uint32_t w = wi < cw ? bits[(size_t)y * cw + wi] : 0u;
-      uint32_t below = __shfl_up_sync(0xFFFFFFFFu, w, 1);
-      if (lane == 0)
+      const int wi = wb + sl;
+      const uint32_t w = (rowOk && wi < cw) ? bits[(size_t)y * cw + wi] : 0u;
+      uint32_t below = __shfl_up_sync(0xFFFFFFFFu, w, 1, GW);
+      if (sl == 0)
         below = prevTop;
       cnt += __popc(w & ~((w << 1) | (below >> 31)));
-      prevTop = __shfl_sync(0xFFFFFFFFu, w, 31);
+      prevTop = __shfl_sync(0xFFFFFFFFu, w, GW - 1, GW);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
+    for (int o = GW >> 1; o > 0; o >>= 1)
       cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
-    if (lane == 0)
+    if (sl == 0 && rowOk)
       rowBase[y] = cnt;
   }
   if (tid == 0)
@@ -169,36 +174,38 @@ k_cc_runs(const SliceDev * __restrict__ slices, const uint32_t * __restrict__ bi
   }
   __syncthreads();
   // ---- 3. run records (k-th start of a row pairs with its k-th end) and per-word run numbering
-  for (int y = warp; y < S.h; y += NW)
+  for (int yb = warp * RPW; yb < S.h; yb += NW * RPW)
   {
-    int nS = rowBase[y], nE = rowBase[y];
+    const int y = yb + sub;
+    const bool rowOk = y < S.h;
+    int nS = rowOk ? rowBase[y] : 0, nE = nS;
     uint32_t prevTop = 0;
-    for (int wb = 0; wb < cw; wb += 32)
+    for (int wb = 0; wb < cw; wb += GW)
     {
-      const int wi = wb + lane;
-      const uint32_t w = wi < cw ? bits[(size_t)y * cw + wi] : 0u;
-      uint32_t below = __shfl_up_sync(0xFFFFFFFFu, w, 1);
-      if (lane == 0)
+      const int wi = wb + sl;
+      const bool wordOk = rowOk && wi < cw;
+      const uint32_t w = wordOk ? bits[(size_t)y * cw + wi] : 0u;
+      uint32_t below = __shfl_up_sync(0xFFFFFFFFu, w, 1, GW);
+      if (sl == 0)
         below = prevTop;
-      uint32_t above = __shfl_down_sync(0xFFFFFFFFu, w, 1);
-      if (lane == 31)
-        above = (wb + 32 < cw) ? bits[(size_t)y * cw + wb + 32] : 0u;
+      uint32_t above = __shfl_down_sync(0xFFFFFFFFu, w, 1, GW);
+      if (sl == GW - 1)
+        above = (rowOk && wb + GW < cw) ? bits[(size_t)y * cw + wb + GW] : 0u;
       const uint32_t starts = w & ~((w << 1) | (below >> 31));
       const uint32_t ends = w & ~((w >> 1) | (above << 31));
       int cs = __popc(starts), ce = __popc(ends);
       int is = cs, ie = ce;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1)
+      for (int o = 1; o < GW; o <<= 1)
       {
-        int a = __shfl_up_sync(0xFFFFFFFFu, is, o), b = __shfl_up_sync(0xFFFFFFFFu, ie, o);
-        if (lane >= o)
+        int a = __shfl_up_sync(0xFFFFFFFFu, is, o, GW), b = __shfl_up_sync(0xFFFFFFFFu, ie, o, GW);
+        if (sl >= o)
         {
           is += a;
           ie += b;
         }
       }
       int ks = nS + is - cs, ke = nE + ie - ce;
-      if (wi < cw)
+      if (wordOk)
         wordRun[(size_t)y * cw + wi] = (uint32_t)ks;
       uint32_t m = starts;
       while (m)
@@ -210,8 +217,8 @@ k_cc_runs(const SliceDev * __restrict__ slices, const uint32_t * __restrict__ bi
         parent[ks] = (uint32_t)ks;
         ++ks;
       }
-      nS += __shfl_sync(0xFFFFFFFFu, is, 31);
-      prevTop = __shfl_sync(0xFFFFFFFFu, w, 31);
+      nS += __shfl_sync(0xFFFFFFFFu, is, GW - 1, GW);
+      prevTop = __shfl_sync(0xFFFFFFFFu, w, GW - 1, GW);
       // ends are written after all starts of the row are in place (same warp, program order)
       __syncwarp();
       m = ends;
@@ -222,7 +229,7 @@ k_cc_runs(const SliceDev * __restrict__ slices, const uint32_t * __restrict__ bi
         atomicOr(&runX[ke], (uint32_t)(wi * 32 + b) << 16);
         ++ke;
       }
-      nE += __shfl_sync(0xFFFFFFFFu, ie, 31);
+      nE += __shfl_sync(0xFFFFFFFFu, ie, GW - 1, GW);
     }
   }
   __syncthreads();

@@ -3,8 +3,8 @@
 //
 //   k_dt_prep    per node : translation halving, union region, translate+binarise+AND into bit rows,
 //                           per-row extents of the intersection, work items            (X:570-666)
-//   k_dt_hist    per item : exact squared distance of every (i xor j) pixel to the intersection,
-//                           histograms per side                                          (X:413-459)
+//   k_dt_hist    per item : exact squared distance d2 of every (i xor j) pixel to the intersection,
+//                           histograms per side over bin = PixelType(10 * sqrtf(d2))     (X:413-459)
 //   k_dt_scan    per node : prefix sums, first bin minimising the score, threshold       (X:461-494)
 //   k_dt_median  per item : median = intersection | (xor pixels with d2 <= threshold), bounding box (X:497-515)
 //   k_dt_alloc   per node : crop/clip, allocate the mid shape, spawn the children        (X:679-729, 766-792)
@@ -99,11 +99,15 @@ dt_edt_sq(const uint32_t * __restrict__ Xb, const uint32_t * __restrict__ rowInf
   return best;
 }
 
+// Histogram bin of a pixel at squared distance d2 from the intersection.  The reference's sdf is ITK's signed
+// Maurer map with SquaredDistance off (its default; X:395-402 never sets it), i.e. float(sqrt(d2)) outside the
+// object, and `PixelType dist = fractioning * sdf` (X:431) is a float multiply, a truncating conversion and a
+// narrowing to the pixel type.  __fsqrt_rn / __fmul_rn are the same IEEE operations the host code performs.
 template <typename T>
 __device__ __forceinline__ int
 dt_bin(int d2, int * err)
 {
-  int q = __float2int_rz(__fmul_rn(10.0f, (float)d2)); // `PixelType dist = fractioning * sdf` (X:431)
+  int q = __float2int_rz(__fmul_rn(10.0f, __fsqrt_rn((float)d2)));
   if (sizeof(T) == 1)
     return q & 0xFF;
   if (std::is_signed<T>::value)
@@ -117,6 +121,20 @@ dt_bin(int d2, int * err)
     return v;
   }
   return q & 0xFFFF;
+}
+
+// `sdf <= float(bestBin) / fractioning` (X:497-508) as a threshold on the integer d2: the largest n with
+// float(sqrt(n)) <= upper (sqrt is monotone, so {sdf <= upper} = {d2 <= n}).
+__device__ __forceinline__ int
+dt_threshold_d2(int bestBin)
+{
+  const float upper = __fdiv_rn((float)bestBin, 10.0f);
+  int n = (int)(upper * upper);
+  while (__fsqrt_rn((float)(n + 1)) <= upper)
+    ++n;
+  while (n > 0 && __fsqrt_rn((float)n) > upper)
+    --n;
+  return n;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -407,8 +425,6 @@ k_dt_hist(NodeWork * work, const DtItem * __restrict__ items, const int * __rest
   // consecutive CTAs, not to the warps of one CTA, so that no SM collects a run of expensive ones
   const int gw = (threadIdx.x >> 5) * gridDim.x + blockIdx.x, nw = (gridDim.x * blockDim.x) >> 5;
   const int nItems = min(*itemCount, itemCap);
-  constexpr bool kBinsOnly = sizeof(T) == 1; // uchar: 256 wrapped bins, indexed directly
-  constexpr int kSmall = PixTraits<T>::kNoWrapD2;
   for (int it = gw; it < nItems; it += nw) // one warp per item
   {
     const DtItem item = items[it];
@@ -450,8 +466,10 @@ k_dt_hist(NodeWork * work, const DtItem * __restrict__ items, const int * __rest
         const int r = idx / pitch, wi = idx - r * pitch;
         d2 = dt_edt_sq(Xb, rowInfo, pitch, nodeH, xr0, xr1, wi * 32 + bit, r, 0x7FFFFFFF);
         side = (iw >> bit) & 1u ? 0 : 1;
-        const int direct = kBinsOnly ? dt_bin<T>(d2, err) : d2;
-        if (kBinsOnly || d2 <= kSmall)
+        // the node's own table is indexed by bin (10 bins per pixel of distance: uchar all 256 wrapped bins,
+        // the 16-bit types distances below histSide / 10 pixels); farther pixels go to a wrapped-bin table
+        const int direct = dt_bin<T>(d2, err);
+        if (direct < histSide)
         {
           atomicAdd(&h0[side * histSide + direct], 1u);
           unsigned * tw = h0 + 2 * histSide + (direct >> 5); // bitmap of touched entries
@@ -472,7 +490,7 @@ k_dt_hist(NodeWork * work, const DtItem * __restrict__ items, const int * __rest
         bi = __shfl_sync(0xFFFFFFFFu, bi, leader);
         if (over)
         {
-          int bin = dt_bin<T>(d2, err);
+          const int bin = dt_bin<T>(d2, err);
           unsigned * bh = bigHist + (size_t)bi * DT_BIG_STRIDE;
           atomicAdd(&bh[side * 65536 + bin], 1u);
           unsigned * tw = bh + 2 * 65536 + (bin >> 5);
@@ -511,7 +529,6 @@ k_dt_scan(NodeWork * work, const int * __restrict__ count, unsigned * hist, int 
   __shared__ int bestI[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = *count;
-  constexpr bool kBinsOnly = sizeof(T) == 1;
   for (int nidx = blockIdx.x; nidx < n; nidx += gridDim.x)
   {
     NodeWork * W = work + nidx;
@@ -529,8 +546,8 @@ k_dt_scan(NodeWork * work, const int * __restrict__ count, unsigned * hist, int 
     __syncthreads();
     if (big)
     {
-      // Some distance wrapped (or exceeded the directly indexed table): work in the wrapped-bin domain of
-      // X:431; fold the directly indexed part in (bin = 10*d2 below the wrap).
+      // Some bin exceeded the node's own table: work in the full wrapped-bin table of X:431 and fold the
+      // node's table in (same bin numbers).
       unsigned * bh = bigHist + (size_t)bi * DT_BIG_STRIDE;
       unsigned * bbm = bh + 2 * 65536;
       for (int wI = tid; wI < smallWords; wI += 256)
@@ -544,7 +561,7 @@ k_dt_scan(NodeWork * work, const int * __restrict__ count, unsigned * hist, int 
           int b = __ffs(bits) - 1;
           bits &= bits - 1;
           const int k = wI * 32 + b;
-          const int bin = kBinsOnly ? k : 10 * k;
+          const int bin = k;
           atomicAdd(&bh[bin], hs[k]);
           atomicAdd(&bh[65536 + bin], hs[histSide + k]);
           atomicOr(&bbm[bin >> 5], 1u << (bin & 31));
@@ -669,8 +686,7 @@ k_dt_scan(NodeWork * work, const int * __restrict__ count, unsigned * hist, int 
           bd = bestD[k];
           bidx = bestI[k];
         }
-      // threshold `sdf <= float(bestBin) / 10` on integer d2 (X:497-508); directly indexed: bestBin = 10 * d2
-      thr = (big || kBinsOnly) ? (int)floorf(__fdiv_rn((float)bidx, 10.0f)) : bidx;
+      thr = dt_threshold_d2(bidx); // bidx = bestBin (X:481-494)
     }
     if (tid == 0)
       W->thr = thr;

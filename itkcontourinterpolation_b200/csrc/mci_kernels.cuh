@@ -141,21 +141,18 @@ template <>
 struct PixTraits<uint8_t>
 {
   static const int kMaxComp = 255;
-  static const int kNoWrapD2 = 25; // 10*d2 <= 255
   static const int kBins = 256;
 };
 template <>
 struct PixTraits<uint16_t>
 {
   static const int kMaxComp = 65535;
-  static const int kNoWrapD2 = 6553;
   static const int kBins = 65536;
 };
 template <>
 struct PixTraits<int16_t>
 {
   static const int kMaxComp = 32767;
-  static const int kNoWrapD2 = 3276;
   static const int kBins = 32768;
 };
 

@@ -688,10 +688,16 @@ public:
     std::vector<int64_t> d2;
     edt_squared(*intersection, d2);
     const size_t N = iMask->px.size();
-    // sdf as the float image the reference sees: +d^2 outside, <=0 inside, FLT_MAX if the object is empty
+    // sdf as the float image the reference sees.  SignedMaurerDistanceMapImageFilter is used with its default
+    // SquaredDistance = false (X:395-402 never sets it), so outside pixels hold the Euclidean distance itself:
+    // ITK's last pass writes float(std::sqrt(double(|d^2|))).  Inside pixels are <= 0 (only the sign matters
+    // here), FLT_MAX if the object is empty.  Pinned by the upstream baseline ManyToMany_T.nrrd (whose sha512
+    // is reproduced with this convention and with no other; tests/test_upstream_baselines.py).
     std::vector<float> sdf(N);
     for (size_t p = 0; p < N; ++p)
-      sdf[p] = intersection->px[p] ? -1.0f : (d2[p] >= EDT_INF ? std::numeric_limits<float>::max() : float(d2[p]));
+      sdf[p] = intersection->px[p]
+                 ? -1.0f
+                 : (d2[p] >= EDT_INF ? std::numeric_limits<float>::max() : float(std::sqrt(double(float(d2[p])))));
 
     BoolPtr orImage = std::make_shared<BoolSlice>();
     orImage->alloc(iMask->r);

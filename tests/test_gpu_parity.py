@@ -104,11 +104,12 @@ def test_int16_and_uint8_pixel_types(flt):
 
 
 def test_int16_distance_bin_overflow_fails_cleanly(flt):
-    # d2 >= 3277 makes `short dist = 10 * sdf` negative: the reference indexes out of bounds (X:431-437);
-    # both the oracle and the CUDA path report an error instead
-    v = np.zeros((9, 60, 230), np.int16)
-    v[0, 2:58, 2:228] = 1
-    v[8, 28:32, 110:116] = 1
+    # a distance of 3276.8 pixels or more makes `short dist = 10 * sdf` negative: the reference indexes out of
+    # bounds (X:431-437); both the oracle and the CUDA path report an error instead
+    v = np.zeros((9, 24, 3400), np.int16)
+    v[0, 2:22, 2:22] = 1       # block + long thin bar: the alignment keeps the blocks on top of each other,
+    v[0, 11:13, 2:3398] = 1    # so the far end of the bar is ~3380 pixels from the intersection
+    v[8, 2:22, 2:22] = 1
     with pytest.raises(O.OracleError):
         O.interpolate(v)
     with pytest.raises(L.MciError):
@@ -116,6 +117,18 @@ def test_int16_distance_bin_overflow_fails_cleanly(flt):
     # the context stays usable
     w = cases.handcrafted()["SimplestOneToOne"]
     assert_same(run_gpu(flt, w), O.interpolate(w), "after error")
+
+
+@pytest.mark.parametrize("dt", [np.uint8, np.uint16, np.int16])
+def test_far_distances_use_the_wrapped_bin_tables(flt, dt):
+    # bins beyond a node's own table (16-bit types: distances of 656 / 330 pixels and more) and, for uchar, bins
+    # wrapped modulo 256 many times over
+    w = np.zeros((9, 24, 1500), dt)
+    w[0, 2:22, 2:22] = 3
+    w[0, 11:13, 2:1498] = 3
+    w[8, 2:22, 2:22] = 3
+    w[0, 4:20, 700:1400] = 3
+    assert_same(run_gpu(flt, w), O.interpolate(w), "far distances %s" % np.dtype(dt).name)
 
 
 def test_empty_and_no_slices_identity(flt):

@@ -121,5 +121,42 @@ def test_distance_bin_wrap_depends_on_pixel_type():
     m8 = O.median(i, j, dtype=np.uint8)
     m16 = O.median(i, j, dtype=np.uint16)
     assert not np.array_equal(m8, m16)
+    assert np.array_equal(O.median(i, j, dtype=np.int16), m16)  # no wrap below 3276 pixels of distance
+    xx = np.arange(3400)[None, :].repeat(5, 0)
+    i = xx >= 0
+    j = xx < 6
     with pytest.raises(O.OracleError):
-        O.median(i, j, dtype=np.int16)  # d2 >= 3277: negative bin, the reference indexes out of bounds
+        O.median(i, j, dtype=np.int16)  # distance >= 3276.8: negative bin, the reference indexes out of bounds
+    assert O.median(i, j, dtype=np.uint16).any()
+
+
+def _median_distances_literal(i, j, dtype):
+    """FindMedianImageDistances restated independently with scipy (X:405-516): the signed Maurer map with
+    SquaredDistance off is the Euclidean distance to the intersection for pixels outside it."""
+    x = i & j
+    sdf = ndimage.distance_transform_edt(~x).astype(np.float32)  # float(sqrt(double(d2)))
+    bins = (np.float32(10) * sdf).astype(np.int32).astype(dtype).astype(np.int64)
+    ih = np.bincount(bins[i & ~j], minlength=1) if (i & ~j).any() else np.zeros(0, np.int64)
+    jh = np.bincount(bins[j & ~i], minlength=1) if (j & ~i).any() else np.zeros(0, np.int64)
+    n = max(len(ih), len(jh))
+    if n == 0:
+        return x
+    ih = np.pad(ih, (0, n - len(ih)))
+    jh = np.pad(jh, (0, n - len(jh)))
+    isum, jsum = np.cumsum(ih), np.cumsum(jh)
+    diff = np.abs(np.abs(isum[-1] - isum + jsum) - np.abs(jsum[-1] - jsum + isum))
+    best = int(np.argmin(diff))  # first minimum
+    upper = np.float32(best) / np.float32(10)
+    return ((sdf <= upper) | x) & (i | j)
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.int16])
+def test_median_distances_against_independent_restatement(dtype):
+    yy, xx = np.mgrid[:48, :90]
+    shapes = [((yy - 24) ** 2 + (xx - 28) ** 2 <= 18 ** 2, (yy - 20) ** 2 + (xx - 24) ** 2 <= 7 ** 2),
+              ((abs(yy - 24) < 15) & (abs(xx - 45) < 40), (yy - 24) ** 2 + (xx - 30) ** 2 <= 64),
+              ((yy - 24) ** 2 / 4 + (xx - 28) ** 2 <= 100, (yy - 24) ** 2 + (xx - 28) ** 2 / 4 <= 100)]
+    for i, j in shapes:
+        for a, b in ((i, j), (j, i)):
+            got = O.median(a, b, dtype=dtype).astype(bool)
+            assert np.array_equal(got, _median_distances_literal(a, b, dtype))

@@ -6,13 +6,16 @@
 // (connected components, signed Maurer distance map, binary dilation) restated
 // from their documented behaviour.
 //
-// PARITY UNPINNED: ITK is not installed in this environment and none of the
-// reference's 360 regression baselines have payloads offline (they are
-// .sha512 content links), so this oracle cannot be checked against output of
-// the real reference.  It is pinned instead by (i) brute-force cross-checks of
-// each primitive (tests/test_oracle_primitives.py: scipy.ndimage.label,
-// O(A^2) EDT, literal dilation), and (ii) the invariants the reference's own
-// tests state (tests/test_oracle_invariants.py).
+// PARITY: ITK is not installed in this environment, so the real reference cannot
+// be built or run here (no oracle/_ref).  The oracle is pinned instead by
+// (i) four of the reference's own regression baselines: SevenLabels_B,
+// ManyToMany_B, ManyToMany_C and ManyToMany_T (test/Baseline/*.nrrd.sha512) --
+// its output, written through ITK's NRRD byte layout, reproduces their sha512
+// content links, i.e. is voxel-exact against output of the real ITK filter
+// (tests/test_upstream_baselines.py; SevenLabels_C / _T are NOT reproduced, see
+// DESIGN.md section 0); (ii) brute-force / scipy / independent restatements of
+// each primitive (tests/test_oracle_primitives.py); (iii) the invariants the
+// reference's own tests state (tests/test_oracle_invariants.py).
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 // reference legs may load this library.  The product (libmci_b200.so) never

@@ -2,8 +2,9 @@
 /root/reference/examples/*.nrrd, available only in the build container) as .npy inputs, and
 golden.json = sha256 of the ORACLE's output for a matrix of inputs x settings.
 
-PARITY UNPINNED: these goldens freeze the oracle restatement, not output of the real ITK filter
-(ITK is absent here; see oracle/mci_oracle.cpp header and DESIGN.md).
+These goldens freeze the ORACLE restatement, not output of the real ITK filter (ITK is absent here).  The oracle
+itself is pinned against four of the reference's own regression baselines by tests/test_upstream_baselines.py
+(see DESIGN.md section 0).
 
     python tests/make_golden.py
 """

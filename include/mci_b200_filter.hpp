@@ -161,10 +161,45 @@ public:
     return m_MTime;
   }
 
+  /** Geometry carried through unchanged (the filter works in index space, X:397): origin and the three
+   *  "space directions" (direction cosines scaled by the spacing), as file formats store them. */
+  using PointType = std::array<double, VDimension>;
+  using SpaceDirectionsType = std::array<PointType, VDimension>;
+  void
+  SetOrigin(const PointType & o)
+  {
+    m_Origin = o;
+  }
+  const PointType &
+  GetOrigin() const
+  {
+    return m_Origin;
+  }
+  void
+  SetSpaceDirections(const SpaceDirectionsType & d)
+  {
+    m_SpaceDirections = d;
+  }
+  const SpaceDirectionsType &
+  GetSpaceDirections() const
+  {
+    return m_SpaceDirections;
+  }
+  /** itk::Image::CopyInformation: geometry only, not the buffer. */
+  template <typename TOther>
+  void
+  CopyInformation(const TOther * other)
+  {
+    m_Origin = other->GetOrigin();
+    m_SpaceDirections = other->GetSpaceDirections();
+  }
+
 protected:
   Image() = default;
 
 private:
+  PointType           m_Origin{ { 0, 0, 0 } };
+  SpaceDirectionsType m_SpaceDirections{ { { { 1, 0, 0 } }, { { 0, 1, 0 } }, { { 0, 0, 1 } } } };
   SizeType            m_Size{ { 0, 0, 0 } };
   std::vector<TPixel> m_Buffer;
   unsigned long       m_MTime{ detail::NextModifiedTime() };
@@ -383,6 +418,7 @@ protected:
     int64_t dims[3];
     this->Dims(input, dims);
     m_Output->SetRegions(input->GetSize());
+    m_Output->CopyInformation(input);
     m_Output->Allocate(true);
     mci_filter_options   opt = this->Options();
     std::vector<int64_t> custom;
@@ -561,6 +597,7 @@ public:
     for (int a = 0; a < 3; ++a)
       dims[a] = int64_t(m_Input->GetSize()[a]);
     m_Output->SetRegions(m_Input->GetSize());
+    m_Output->CopyInformation(m_Input.get());
     m_Output->Allocate();
     int rc = mci_median_filter_run(m_Ctx, m_Input->GetBufferPointer(), m_Output->GetBufferPointer(), dims,
                                    detail::PixelTypeCode<PixelType>::value, int(m_Radius));

@@ -62,14 +62,15 @@ def build_cpp_driver(verbose=False):
     lib = build(verbose=verbose)
     root = os.path.join(_HERE, "..")
     src = os.path.join(root, "tests", "cpp", "mci_filter_test.cpp")
-    hdrs = [os.path.join(root, "include", "mci_b200_filter.hpp"), os.path.join(root, "include", "mci_b200.h"), lib]
+    hdrs = [os.path.join(root, "include", "mci_b200_filter.hpp"), os.path.join(root, "include", "mci_b200_io.hpp"),
+            os.path.join(root, "include", "mci_b200.h"), lib]
     if not os.path.exists(src):
         if os.path.exists(DRIVER):
             return DRIVER
         raise RuntimeError("mci_filter_test.cpp missing and no prebuilt driver present")
     if _newer(DRIVER, [src] + hdrs):
         cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-Wall", "-Wextra", "-I", os.path.join(root, "include"), src,
-               "-o", DRIVER, "-L", OUT, "-lmci_b200", "-Wl,-rpath,$ORIGIN"]
+               "-o", DRIVER, "-L", OUT, "-lmci_b200", "-lz", "-Wl,-rpath,$ORIGIN"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

@@ -3,9 +3,14 @@
 // label on the filter, write the filter's output.  Images are raw x-fastest voxel files here (ITK's readers are not
 // available): the pytest side converts fixtures and compares the written output with the oracle.
 //
+//   mci_filter_test inputImage.nrrd outputImage.nrrd [algorithm B|C|T] [axis] [label]
+//                                the reference driver's own command line on NRRD files: pixel type chosen as it
+//                                chooses it (3-D short / ushort -> Image<short,3>), output written with compression;
+//                                the written file is byte-compatible with ITK's writer (include/mci_b200_io.hpp)
 //   mci_filter_test inputRaw outputRaw X Y Z uchar|ushort|short [algorithm B|C|T|D] [axis] [label]
 //   mci_filter_test --example inputRaw outputRaw X Y Z uchar|ushort|short [smoothingRadius=2]
 //                                the reference's example program (examples/mciExample.cxx): interpolate, median-smooth
+//   mci_filter_test --copy in.nrrd out.nrrd   reader -> writer only (Image<short,3>, compressed); needs no GPU
 //   mci_filter_test --api        interface checks that need no GPU (defaults, Modified(), error behaviour)
 #include <cctype>
 #include <cstdio>
@@ -16,6 +21,7 @@
 #include <string>
 
 #include "mci_b200_filter.hpp"
+#include "mci_b200_io.hpp"
 
 namespace
 {
@@ -101,6 +107,41 @@ doExample(const std::string & inFilename, const std::string & outFilename, size_
           std::streamsize(out->GetNumberOfPixels() * sizeof(typename ImageType::PixelType)));
   if (!f)
     throw mci_b200::ExceptionObject(MCI_ERR_ARG, "cannot write " + outFilename);
+}
+
+// test/itkMorphologicalContourInterpolationTest.cxx:25-49, on NRRD files
+template <typename ImageType>
+void
+doFileTest(const std::string & inFilename, const std::string & outFilename, bool UseDistanceTransform, bool ball, int axis, int label)
+{
+  using ReaderType = mci_b200::ImageFileReader<ImageType>;
+  typename ReaderType::Pointer reader = ReaderType::New();
+  reader->SetFileName(inFilename);
+  reader->Update();
+
+  typename ImageType::Pointer test = reader->GetOutput();
+
+  using mciType = mci_b200::MorphologicalContourInterpolator<ImageType>;
+  typename mciType::Pointer mci = mciType::New();
+  mci->SetInput(test);
+  mci->SetUseDistanceTransform(UseDistanceTransform);
+  mci->SetUseBallStructuringElement(ball);
+  mci->SetAxis(axis);
+  mci->SetLabel(typename ImageType::PixelType(label));
+  mci->Update();
+
+  using WriterType = mci_b200::ImageFileWriter<ImageType>;
+  typename WriterType::Pointer writer = WriterType::New();
+  writer->SetFileName(outFilename);
+  writer->SetInput(mci->GetOutput());
+  writer->SetUseCompression(true);
+  writer->Update();
+}
+
+bool
+endsWith(const std::string & s, const std::string & suffix)
+{
+  return s.size() >= suffix.size() && s.compare(s.size() - suffix.size(), suffix.size(), suffix) == 0;
 }
 
 #define EXPECT(cond)                                                                                                           \
@@ -214,6 +255,63 @@ main(int argc, char * argv[])
       return EXIT_FAILURE;
     }
     return EXIT_SUCCESS;
+  }
+  if (argc == 4 && std::string(argv[1]) == "--copy")
+  {
+    // reader -> writer without the filter (needs no GPU): Image<short,3>, compression on
+    try
+    {
+      auto reader = mci_b200::ImageFileReader<mci_b200::Image<short, 3>>::New();
+      reader->SetFileName(argv[2]);
+      reader->Update();
+      auto writer = mci_b200::ImageFileWriter<mci_b200::Image<short, 3>>::New();
+      writer->SetFileName(argv[3]);
+      writer->SetInput(reader->GetOutput());
+      writer->SetUseCompression(true);
+      writer->Update();
+    }
+    catch (mci_b200::ExceptionObject & error)
+    {
+      std::cerr << "Error: " << error.what() << std::endl;
+      return EXIT_FAILURE;
+    }
+    return EXIT_SUCCESS;
+  }
+  if (argc >= 3 && endsWith(argv[1], ".nrrd"))
+  {
+    // the reference driver's command line (test/itkMorphologicalContourInterpolationTest.cxx:52-140)
+    bool dt = false, ball = true;
+    int  axis = -1, label = 0;
+    if (argc >= 4)
+    {
+      char algo = char(std::toupper(argv[3][0]));
+      if (algo == 'T')
+        dt = true;
+      else if (algo == 'C')
+        ball = false;
+    }
+    if (argc >= 5)
+      axis = int(std::strtol(argv[4], nullptr, 10));
+    if (argc >= 6)
+      label = int(std::strtol(argv[5], nullptr, 10));
+    try
+    {
+      std::string pixelType;
+      size_t      numDimensions = 0;
+      mci_b200::ImageFileReader<mci_b200::Image<short, 3>>::ReadImageInformation(argv[1], pixelType, numDimensions);
+      if (numDimensions == 3 && (pixelType == "short" || pixelType == "unsigned short"))
+      {
+        doFileTest<mci_b200::Image<short, 3>>(argv[1], argv[2], dt, ball, axis, label);
+        return EXIT_SUCCESS;
+      }
+      std::cerr << "Unsupported image type:\n  Dimensions: " << numDimensions << "\n  Pixel type:" << pixelType << std::endl;
+      return EXIT_FAILURE;
+    }
+    catch (mci_b200::ExceptionObject & error)
+    {
+      std::cerr << "Error: " << error.what() << std::endl;
+      return EXIT_FAILURE;
+    }
   }
   if (argc < 7)
   {

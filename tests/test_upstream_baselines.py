@@ -16,6 +16,7 @@ expected failures so that any future change that reproduces them is noticed.
 import hashlib
 import json
 import os
+import subprocess
 
 import numpy as np
 import pytest
@@ -75,3 +76,47 @@ def test_cuda_path_reproduces_upstream_baseline(name, algo):
     finally:
         f.close()
     assert file_hash(name, out) == PINS[name]["baselines"][algo]["sha512"]
+
+
+# ---- the same through the C++ class and its file reader / writer, driven by the reference driver's command line ----
+def write_upstream_input(name, path):
+    p = PINS[name]
+    vol = np.load(os.path.join(cases.GOLDEN, name + ".npy"))
+    data = nrrd_bytes(vol, p["space_directions"], p["space_origin"], encoding="raw")
+    assert hashlib.sha512(data).hexdigest() == p["input_sha512"]
+    with open(path, "wb") as f:
+        f.write(data)
+
+
+@pytest.fixture(scope="module")
+def driver():
+    from itkcontourinterpolation_b200 import build as B
+    return B.build_cpp_driver()
+
+
+@pytest.mark.parametrize("name", sorted(PINS))
+def test_cpp_reader_and_writer_are_byte_compatible_with_itk(driver, tmp_path, name):
+    # no GPU: read the upstream test input as Image<short,3>, write it compressed; the bytes must be what ITK's writer
+    # produces for that volume (the layout that reproduces the baselines)
+    src, dst = str(tmp_path / (name + ".nrrd")), str(tmp_path / "copy.nrrd")
+    write_upstream_input(name, src)
+    r = subprocess.run([driver, "--copy", src, dst], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    p = PINS[name]
+    assert open(dst, "rb").read() == nrrd_bytes(load_as_short(name), p["space_directions"], p["space_origin"], **p["writer"])
+    # a compressed input reads back to the same voxels
+    r = subprocess.run([driver, "--copy", dst, str(tmp_path / "copy2.nrrd")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert open(tmp_path / "copy2.nrrd", "rb").read() == open(dst, "rb").read()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,algo", REPRODUCED)
+def test_upstream_regression_test_through_the_cpp_driver(driver, tmp_path, name, algo):
+    """itk_add_test(... --compare DATA{Baseline/X_algo.nrrd} out itkMorphologicalContourInterpolationTest
+    DATA{Input/X.nrrd} out algo) of test/CMakeLists.txt:51-55, with hash equality in place of --compare."""
+    src, dst = str(tmp_path / (name + ".nrrd")), str(tmp_path / ("%s_%s.nrrd" % (name, algo)))
+    write_upstream_input(name, src)
+    r = subprocess.run([driver, src, dst, algo], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert hashlib.sha512(open(dst, "rb").read()).hexdigest() == PINS[name]["baselines"][algo]["sha512"]

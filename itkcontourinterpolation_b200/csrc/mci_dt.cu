@@ -334,8 +334,6 @@ k_dt_prep(const Node * __restrict__ nodes, const int * __restrict__ count, NodeW
       nw.mid = mid;
       nw.xr0 = s_r0;
       nw.xr1 = s_r1;
-      nw.maxIdx = -1;
-      nw.maxBig = -1;
       nw.bigIdx = -1;
       nw.thr = 0;
       nw.bx0 = nw.by0 = 0x7FFFFFFF;
@@ -435,7 +433,6 @@ k_dt_hist(NodeWork * work, const DtItem * __restrict__ items, const int * __rest
     const uint32_t * Sb = Ib + words;
     const uint32_t * rowInfo = Sb + words;
     unsigned * h0 = hist + (size_t)item.node * histStride;
-    int maxSmall = -1, maxBig = -1;
     const int wBeg = item.w0;
     // lane i < DT_HCHUNK owns word wBeg+i; the pixels of the chunk are dealt out one per lane
     const int myIdx = wBeg + lane;
@@ -475,7 +472,6 @@ k_dt_hist(NodeWork * work, const DtItem * __restrict__ items, const int * __rest
           unsigned * tw = h0 + 2 * histSide + (direct >> 5); // bitmap of touched entries
           if (!(__ldcg(tw) & (1u << (direct & 31))))
             atomicOr(tw, 1u << (direct & 31));
-          maxSmall = max(maxSmall, direct);
         }
         else
           over = true;
@@ -496,22 +492,8 @@ k_dt_hist(NodeWork * work, const DtItem * __restrict__ items, const int * __rest
           unsigned * tw = bh + 2 * 65536 + (bin >> 5);
           if (!(__ldcg(tw) & (1u << (bin & 31))))
             atomicOr(tw, 1u << (bin & 31));
-          maxBig = max(maxBig, bin);
         }
       }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-    {
-      maxSmall = max(maxSmall, __shfl_xor_sync(0xFFFFFFFFu, maxSmall, o));
-      maxBig = max(maxBig, __shfl_xor_sync(0xFFFFFFFFu, maxBig, o));
-    }
-    if (lane == 0)
-    {
-      if (maxSmall >= 0)
-        atomicMax(&W->maxIdx, maxSmall);
-      if (maxBig >= 0)
-        atomicMax(&W->maxBig, maxBig);
     }
   }
 }

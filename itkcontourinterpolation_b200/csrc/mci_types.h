@@ -121,7 +121,7 @@ struct NodeWork
   int ux0, uy0, w, h, pitch, words; // working region = union of the two translated shapes' regions
   int iTx, iTy, jTx, jTy, mid;
   int xr0, xr1;                     // first / last row holding intersection pixels
-  int maxIdx, maxBig, bigIdx;       // histogram extents; slot of the wrapped-bin table (-1: none)
+  int bigIdx;                       // slot of the wrapped-bin table (-1: none)
   int thr;                          // d2 threshold of the median (-1: the median is the intersection)
   int bx0, by0, bx1, by1;           // bounding box of the clipped median
   int alive;

@@ -160,3 +160,14 @@ def test_median_distances_against_independent_restatement(dtype):
         for a, b in ((i, j), (j, i)):
             got = O.median(a, b, dtype=dtype).astype(bool)
             assert np.array_equal(got, _median_distances_literal(a, b, dtype))
+
+
+def test_float_sqrt_equals_double_sqrt_rounded_to_float():
+    # The CUDA path bins with __fsqrt_rn(float(d2)); ITK (and the oracle) compute float(std::sqrt(double(float(d2)))).
+    # The two agree for every d2 an 8191-pixel-wide region can produce, and so do the bins 10 * sdf.
+    for lo in range(0, 1 << 25, 1 << 22):
+        d = np.arange(lo, lo + (1 << 22), dtype=np.int64).astype(np.float32)
+        a = np.sqrt(d)
+        b = np.sqrt(d.astype(np.float64)).astype(np.float32)
+        assert np.array_equal(a, b)
+        assert np.array_equal((np.float32(10) * a).astype(np.int32), (np.float32(10) * b).astype(np.int32))

@@ -12,8 +12,10 @@ sparse-annotated label volume.  Metric: interpolated Mvoxel/s per label-volume =
           copies of every volume inside the timed region: mci_filter_run_batch with --depth volumes in flight
           (throughput; the headline), and mci_filter_run one volume at a time (latency; e2e.one_volume_at_a_time)
 
-N > 1 (torchrun, one rank per GPU): the path partitions into independent label volumes, one per GPU, no
-data-path collective; value = voxels all ranks processed / max-over-ranks time; scaling "weak".
+N > 1 (torchrun, one rank per GPU): `value` = independent label volumes, one per GPU, no data-path collective (voxels
+all ranks processed / max-over-ranks time; scaling "weak"); `sharded` = ONE C5 volume cut into one z-slab per GPU
+(strong scaling, the north-star split), with the same volume on one GPU measured beside it.
+N = 1 also reports C4 and C5 (`extra.workloads`), checked against the frozen oracle output of tests/golden/large.json.
 --impl reference times the CPU restatement of the reference (oracle/, all host threads) on rank 0.
 """
 import argparse
@@ -134,6 +136,210 @@ def oracle_time(vol, cfg, threads, runs):
     return statistics.median(times[1:]), out
 
 
+def frozen(key):
+    """tests/golden/large.json: sha256 + per-plane CRC-32 of the ORACLE's output for the full-size configurations"""
+    p = os.path.join(ROOT, "tests", "golden", "large.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(key)
+
+
+def plane_crcs(a):
+    import zlib
+    return [zlib.crc32(np.ascontiguousarray(a[z]).data) for z in range(a.shape[0])]
+
+
+def extra_workload(lib, L, torch, local_rank, name, steps, warmup):
+    """one more BASELINE.json configuration on this GPU: resident and host-to-host times, checked against the frozen
+    oracle output (per-plane CRC-32)"""
+    vol, _, cfg = make_config(name, 1.0, want_dense=False)
+    gold = frozen(name)
+    ctx = ctypes.c_void_p()
+    if lib.mci_create(ctypes.byref(ctx), local_rank):
+        raise SystemExit("mci_create failed")
+
+    def check(rc):
+        if rc:
+            raise SystemExit("mci error %d: %s" % (rc, lib.mci_last_error(ctx).decode()))
+
+    try:
+        opt = L.FilterOptions()
+        lib.mci_filter_default_options(ctypes.byref(opt))
+        opt.axis = cfg["axis"]
+        opt.use_distance_transform = int(cfg["use_dt"])
+        opt.use_ball_structuring_element = int(cfg["ball"])
+        dims = (ctypes.c_int64 * 3)(*cfg["dims"])
+        nbytes = vol.nbytes
+        h_in, h_out = lib.mci_host_alloc(nbytes), lib.mci_host_alloc(nbytes)
+        ctypes.memmove(h_in, vol.ctypes.data, nbytes)
+        stats = L.FilterStats()
+        stream = torch.cuda.ExternalStream(lib.mci_stream(ctx), device=torch.device("cuda", local_rank))
+
+        def timed(fn):
+            for _ in range(warmup):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                fn()
+            e1.record(stream)
+            e1.synchronize()
+            return e0.elapsed_time(e1) / steps
+
+        ms_e2e = timed(lambda: check(lib.mci_filter_run(ctx, ctypes.byref(opt), h_in, h_out, dims, L.U16, None, 0, ctypes.byref(stats))))
+        got = np.ctypeslib.as_array(ctypes.cast(h_out, ctypes.POINTER(ctypes.c_uint16)), shape=vol.shape)
+        bit_exact = None
+        if gold is not None:
+            bit_exact = bool(plane_crcs(got) == gold["output_plane_crc32"] and plane_crcs(vol) == gold["input_plane_crc32"])
+            if not bit_exact:
+                raise SystemExit("%s: GPU output differs from the frozen oracle output -- no number reported" % name)
+        job = stats.as_dict()
+        check(lib.mci_upload_volume(ctx, h_in, dims, L.U16))
+        check(lib.mci_synchronize(ctx))
+        l0 = lib.mci_launch_count(ctx)
+        ms_res = timed(lambda: check(lib.mci_filter_run_resident(ctx, ctypes.byref(opt), None, 0, ctypes.byref(stats))))
+        launches = (lib.mci_launch_count(ctx) - l0) // (steps + warmup)
+        nvox = int(vol.size)
+        peak, _ = measured_peak()
+        lib.mci_host_free(h_in)
+        lib.mci_host_free(h_out)
+        return {"workload": "%s: %s" % (name, WORKLOAD_DESC[name]), "dims": list(cfg["dims"]), "steps": steps, "warmup": warmup,
+                "ms_per_step": ms_res, "value": nvox / (ms_res * 1e-3) / 1e6, "unit": "Mvoxel/s",
+                "e2e": {"ms_per_step": ms_e2e, "value": nvox / (ms_e2e * 1e-3) / 1e6, "call": "mci_filter_run, one volume at a time",
+                        "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes},
+                "whole_step_frac": 2.0 * nbytes / (ms_res * 1e-3) / 1e9 / peak, "gpu_launches_per_step": int(launches),
+                "bit_exact": bit_exact, "checked_against": "tests/golden/large.json (oracle output, CRC-32 per z-plane)" if gold else None,
+                "job": {k: job[k] for k in ("n_labels", "n_annotated_slices", "n_segments", "n_jobs")}}
+    finally:
+        lib.mci_destroy(ctx)
+
+
+def sharded_c5(torch, dist, L, local_rank, rank, world, scale, steps, warmup, lib):
+    """ONE C5 volume, one z-slab per GPU (itkcontourinterpolation_b200.distributed.SlabShardedInterpolator): every rank
+    generates, uploads, interpolates and downloads only its planes (+ the annotated planes bounding the segments that
+    reach into its slab).  Returns the `sharded` object of the JSON line (rank 0) or None."""
+    from itkcontourinterpolation_b200.distributed import SlabShardedInterpolator, slab_bounds
+    from itkcontourinterpolation_b200.synthetic import CONFIGS
+    cfg = CONFIGS["C5"]
+    dims = tuple(max(8, int(round(d * scale))) for d in cfg["dims"])
+    X, Y, Z = dims
+    z0, z1 = slab_bounds(Z, world)[rank]
+    nth = cfg["nth"][2]
+    w0, w1 = max(0, z0 - nth), min(Z, z1 + nth + 1)  # annotated every nth plane: the bounding planes are that close
+    win, _, _ = make_config("C5", scale, z_range=(w0, w1), want_dense=False)
+    gold = frozen("C5" if scale == 1.0 else ("C5_half" if scale == 0.5 else "-"))
+    f = SlabShardedInterpolator(local_rank, dims, torch.uint16, margin=nth + 1)
+    try:
+        f.set_options(axis=2, use_distance_transform=int(cfg["use_dt"]), use_ball_structuring_element=int(cfg["ball"]))
+        host = torch.from_numpy(win).pin_memory()
+        out = torch.empty((z1 - z0, Y, X), dtype=torch.uint16).pin_memory()
+
+        def barrier():
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+
+        def timed(fn):
+            for _ in range(warmup):
+                fn()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(f.stream)
+            for _ in range(steps):
+                fn()
+            e1.record(f.stream)
+            e1.synchronize()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item()) / steps
+
+        ms_e2e = timed(lambda: f.run_host(host, w0, out))
+        ok = True
+        if gold is not None:
+            ok = plane_crcs(out.numpy()) == gold["output_plane_crc32"][z0:z1]
+        f.load_slab(host[z0 - w0:z1 - w0])
+        f.nvlink_bytes = f.table_bytes = 0
+        ms_res = timed(f.run_resident)
+        per_step = lambda v: v / float(steps + warmup)
+        nv, tb = per_step(f.nvlink_bytes), per_step(f.table_bytes)
+        if gold is not None:
+            ok = ok and plane_crcs(f.output_slab().cpu().numpy()) == gold["output_plane_crc32"][z0:z1]
+        flags = torch.tensor([1 if ok else 0, int(nv), int(tb), f.last_stats.get("n_segments", 0)], device="cuda", dtype=torch.int64)
+        allf = torch.empty((world, 4), dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(allf.view(-1), flags)
+        allf = allf.cpu().numpy()
+    finally:
+        f.close()
+    del host, out, win
+    # the same volume on ONE GPU, measured by rank 0 in the same run (the others wait)
+    one = None
+    if rank == 0:
+        vol, _, _ = make_config("C5", scale, want_dense=False)
+        ctx = ctypes.c_void_p()
+        if lib.mci_create(ctypes.byref(ctx), local_rank):
+            raise SystemExit("mci_create failed")
+        opt = L.FilterOptions()
+        lib.mci_filter_default_options(ctypes.byref(opt))
+        opt.axis = 2
+        opt.use_distance_transform = int(cfg["use_dt"])
+        opt.use_ball_structuring_element = int(cfg["ball"])
+        cd = (ctypes.c_int64 * 3)(*dims)
+        h_in, h_out = lib.mci_host_alloc(vol.nbytes), lib.mci_host_alloc(vol.nbytes)
+        ctypes.memmove(h_in, vol.ctypes.data, vol.nbytes)
+        st = L.FilterStats()
+        stream = torch.cuda.ExternalStream(lib.mci_stream(ctx), device=torch.device("cuda", local_rank))
+
+        def t1(fn):
+            for _ in range(warmup):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                fn()
+            e1.record(stream)
+            e1.synchronize()
+            return e0.elapsed_time(e1) / steps
+
+        def must(rc):
+            if rc:
+                raise SystemExit("mci error %d: %s" % (rc, lib.mci_last_error(ctx).decode()))
+
+        one_e2e = t1(lambda: must(lib.mci_filter_run(ctx, ctypes.byref(opt), h_in, h_out, cd, L.U16, None, 0, ctypes.byref(st))))
+        must(lib.mci_upload_volume(ctx, h_in, cd, L.U16))
+        must(lib.mci_synchronize(ctx))
+        one_res = t1(lambda: must(lib.mci_filter_run_resident(ctx, ctypes.byref(opt), None, 0, ctypes.byref(st))))
+        one = (one_res, one_e2e, int(st.n_segments))
+        lib.mci_host_free(h_in)
+        lib.mci_host_free(h_out)
+        lib.mci_destroy(ctx)
+    dist.barrier()
+    if rank != 0:
+        return None
+    nvox = X * Y * Z
+    bit_exact = bool(allf[:, 0].min() == 1) if gold is not None else None
+    if bit_exact is False:
+        raise SystemExit("sharded C5: some rank's planes differ from the frozen oracle output -- no number reported")
+    return {"workload": "C5: %s" % WORKLOAD_DESC["C5"] + ("" if scale == 1.0 else " (scaled by %g)" % scale), "dims": list(dims),
+            "partition": "one z-slab of %d planes per GPU; segments assigned by the slab their mid slices fall in; every output "
+                         "voxel is produced by exactly one rank (no combine step)" % (Z // world),
+            "steps": steps, "warmup": warmup, "scaling": "strong",
+            "ms_per_volume": ms_res, "value": nvox / (ms_res * 1e-3) / 1e6, "unit": "Mvoxel/s",
+            "e2e": {"ms_per_volume": ms_e2e, "value": nvox / (ms_e2e * 1e-3) / 1e6,
+                    "h2d_bytes_per_step_per_gpu": int((z1 - z0 + 2) * X * Y * 2), "d2h_bytes_per_step_per_gpu": int((z1 - z0) * X * Y * 2)},
+            "one_gpu": {"ms_per_volume": one[0], "e2e_ms_per_volume": one[1], "n_segments": one[2]},
+            "speedup_vs_1gpu": one[0] / ms_res, "e2e_speedup_vs_1gpu": one[1] / ms_e2e,
+            "bit_exact": bit_exact, "checked_against": "tests/golden/large.json (oracle output, CRC-32 per z-plane)" if gold else None,
+            "collective": "resident mode: NCCL send/recv of whole annotated planes from the owner's HBM (halo planes for slice "
+                          "detection + the planes bounding segments that cross a slab boundary) and one all-gather of the "
+                          "per-rank detection tables; host mode: the all-gather only",
+            "bytes_on_nvlink": {"planes_per_step_max_rank": int(allf[:, 1].max()), "planes_per_step_all_ranks": int(allf[:, 1].sum()),
+                                "tables_per_step_per_rank": int(allf[:, 2].max())},
+            "segments_per_rank": [int(v) for v in allf[:, 3]]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -145,6 +351,9 @@ def main():
     ap.add_argument("--depth", type=int, default=0, help="volumes in flight per GPU in the e2e throughput measurement "
                     "(0 = 3 on one GPU, fewer when several GPUs share the host's I/O path: 2 on two, 1 beyond)")
     ap.add_argument("--no-check", action="store_true", help="skip the bit-exact check against the oracle before timing")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C4 / C5 lines (extra.workloads) of a single-GPU run")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the slab-sharded C5 volume (sharded)")
+    ap.add_argument("--sharded-scale", type=float, default=1.0, help="scale of the sharded C5 volume (tests)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
 
@@ -356,6 +565,13 @@ def main():
     ms_batch /= args.steps
     clocks_batch = cs_b.summary()
 
+    extra = None
+    if world == 1 and not args.no_extra and args.workload == "C3" and args.scale == 1.0:
+        extra = {"workloads": [extra_workload(lib, L, torch, local_rank, name, 5, 3) for name in ("C4", "C5")]}
+    sharded = None
+    if world > 1 and not args.no_sharded:
+        sharded = sharded_c5(torch, dist, L, local_rank, rank, world, args.sharded_scale, min(args.steps, 10), 3, lib)
+
     if rank == 0:
         peak, peak_src = measured_peak()
         # dominant kernel = largest share of device time; the HBM-streaming kernel of this path is k_copy_flag
@@ -376,11 +592,16 @@ def main():
                     traffic = json.load(open(prof)).get("k_copy_flag", {}).get("dram_bytes_per_launch")
                 except Exception:
                     traffic = None
-            roof = {"bound": "hbm", "kernel": "k_copy_flag", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
-                    "avg_launch_ms": avg_ms, "dominant_kernel_by_time": dom,
-                    "whole_step_frac": alg / (ms_res * 1e-3) / 1e9 / peak,
-                    "with_detect_marked_frac": alg / ((t_ms + kernels.get("k_detect_marked", (1, 0.0))[1]) / n_l * 1e-3) / 1e9 / peak}
+            step_gbs = alg / (ms_res * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": dom, "scope": "whole step: the volume's algorithmic bytes (read every input voxel "
+                    "once, write every output voxel once) over the step time; `kernel` is the kernel with the largest share of "
+                    "device time, which works on L2-resident bit-packed shapes and moves next to no DRAM bytes itself",
+                    "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak, "traffic": traffic,
+                    "peak_source": peak_src, "algorithmic_bytes_per_step": alg, "step_ms": ms_res,
+                    "dominant_kernel_share": (kernels[dom][1] / total_kernel_ms) if dom else None,
+                    "streaming_kernel": {"kernel": "k_copy_flag", "achieved": achieved, "frac": achieved / peak, "avg_launch_ms": avg_ms,
+                                         "algorithmic_bytes_per_launch": alg, "traffic": traffic,
+                                         "with_detect_marked_frac": alg / ((t_ms + kernels.get("k_detect_marked", (1, 0.0))[1]) / n_l * 1e-3) / 1e9 / peak}}
         line = {"metric": "interpolated Mvoxel/s per label-volume", "value": world * nvox / (ms_res * 1e-3) / 1e6, "unit": "Mvoxel/s", "n_gpus": n_gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u16", "data": "synthetic", "config": config, "clocks": clocks,
@@ -395,6 +616,10 @@ def main():
                 "kernels_note": "second pass of the same steps with CUDA events around every launch (%.3f ms/step)" % ms_res_profiled,
                 "job": {k: job_stats[k] for k in ("n_labels", "n_annotated_slices", "n_segments", "n_pairs", "n_jobs", "n_components")},
                 "bit_exact_vs_oracle": (not args.no_check)}
+        if extra is not None:
+            line["extra"] = extra
+        if sharded is not None:
+            line["sharded"] = sharded
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()
     for a, b in zip(ins, outs):

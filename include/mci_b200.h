@@ -69,6 +69,11 @@ int mci_profile_read(mci_ctx * ctx, mci_kernel_time * out, int32_t cap, int32_t 
 
 /* ---- volume ------------------------------------------------------------------------------- */
 /* Replaces GetInput()/AllocateOutputs() (X:1541-1565).  dims = {X, Y, Z}, X fastest.
+ * LIMITS: every dimension must be in [1, 8192] (the bound the device-side tables, tile grids and 32-bit distance
+ * arithmetic are sized for: a slice diagonal squared stays below 2^28), a slice may hold at most 65 535 connected components of one label (the
+ * component images are uint16; 255 for uint8 volumes, as in the reference, whose component image has the volume's
+ * pixel type), and labels are the non-zero values of the pixel type (negative int16 labels included).  Violations
+ * return MCI_ERR_ARG / MCI_ERR_PIXELTYPE; nothing is truncated silently.
  * mci_upload_volume copies host voxels to the device; mci_attach_device_volume adopts
  * caller-owned device buffers (input is read-only; output must hold X*Y*Z pixels). */
 int mci_upload_volume(mci_ctx * ctx, const void * host_voxels, const int64_t dims[3], int pixel_type);
@@ -234,6 +239,20 @@ int mci_filter_run(mci_ctx * ctx, const mci_filter_options * opt, const void * h
 /* same, input already on the device (mci_upload_volume / mci_attach_device_volume) and output left there */
 int mci_filter_run_resident(mci_ctx * ctx, const mci_filter_options * opt, const int64_t * custom_slices,
                             int64_t n_custom, mci_filter_stats * stats);
+/* Slab-sharded run (multi-GPU, one process per GPU; replaces the per-thread segment loop of X:1523-1537 by a partition
+ * of the segments over GPUs by the slab their mid slices fall in).  The context's volume (mci_attach_device_volume /
+ * mci_upload_volume) is a contiguous range of the whole volume along the interpolation axis: this rank's slab plus
+ * the annotated slices bounding the segments that reach into it.  `labels` (bounding boxes, X:148-159) and `slices`
+ * (m_LabeledSlices, X:161-197) are the detection tables MERGED OVER ALL RANKS (each rank runs mci_detect_slices on
+ * its slab plus one halo slice per side and contributes the entries of its own slices), shifted into the coordinates
+ * of the range; slices outside the range are left out.  Only segments with a mid slice in [keep_lo, keep_hi) of the
+ * range are interpolated.  The output buffer must already hold a copy of the input over [keep_lo, keep_hi)
+ * (mci_detect_slices does that for the range it ran on; mci_copy_input_range for anything else).  Synchronises. */
+int mci_filter_run_with_detection(mci_ctx * ctx, const mci_filter_options * opt, const mci_label_info * labels,
+                                  int32_t n_labels, const mci_labeled_slice * slices, int32_t n_slices, int32_t keep_lo,
+                                  int32_t keep_hi, mci_filter_stats * stats);
+/* out[first_voxel ... first_voxel + n_voxels) = in[...] on the context's stream (device to device) */
+int mci_copy_input_range(mci_ctx * ctx, int64_t first_voxel, int64_t n_voxels);
 /* Throughput mode for a series of independent label volumes (same dims and pixel type): volume k goes through
  * ctxs[k % ...] -- n_ctx contexts, each with its own stream, driven by one host thread each -- so the H2D copy of
  * one volume, the kernels of another and the D2H copy of a third overlap (PCIe is full duplex; a single mci_filter_run

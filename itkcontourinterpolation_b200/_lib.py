@@ -116,6 +116,9 @@ SYMBOLS = [
     ("mci_filter_run", _I, [_P, ctypes.POINTER(FilterOptions), _P, _P, ctypes.POINTER(ctypes.c_int64), _I, _P,
                             ctypes.c_int64, ctypes.POINTER(FilterStats)]),
     ("mci_filter_run_resident", _I, [_P, ctypes.POINTER(FilterOptions), _P, ctypes.c_int64, ctypes.POINTER(FilterStats)]),
+    ("mci_filter_run_with_detection", _I, [_P, ctypes.POINTER(FilterOptions), _P, ctypes.c_int32, _P, ctypes.c_int32,
+                                           ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(FilterStats)]),
+    ("mci_copy_input_range", _I, [_P, ctypes.c_int64, ctypes.c_int64]),
     ("mci_filter_run_batch", _I, [_P, ctypes.c_int32, ctypes.POINTER(FilterOptions), _P, _P, ctypes.c_int32,
                                   ctypes.POINTER(ctypes.c_int64), _I, _P]),
     ("mci_filter_detect", _I, [_P, ctypes.POINTER(FilterOptions), ctypes.POINTER(ctypes.c_int64)]),

@@ -300,6 +300,13 @@ extern "C"
     }
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
+    if (prop.major != 10)
+    {
+      // the library holds sm_100a SASS only: on any other GPU every launch would fail with "no kernel image"
+      cudaStreamDestroy(ctx->L.stream);
+      delete ctx;
+      return MCI_ERR_NO_DEVICE;
+    }
     ctx->L.sms = prop.multiProcessorCount;
     ctx->L.maxSmem = (int)prop.sharedMemPerBlockOptin;
     ctx->L.count = 0;
@@ -496,6 +503,18 @@ extern "C"
       return rc;
     ctx->dIn = const_cast<void *>(dev_in);
     ctx->dOut = dev_out;
+    return MCI_OK;
+  }
+
+  int mci_copy_input_range(mci_ctx * ctx, int64_t first, int64_t n)
+  {
+    if (!ctx || !ctx->dIn || !ctx->dOut || first < 0 || n < 0 || size_t(first) + size_t(n) > ctx->nvox)
+      return MCI_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const size_t s = ctx->ptype == MCI_U8 ? 1 : 2;
+    if (n)
+      CK(cudaMemcpyAsync((char *)ctx->dOut + size_t(first) * s, (const char *)ctx->dIn + size_t(first) * s, size_t(n) * s,
+                         cudaMemcpyDeviceToDevice, ctx->L.stream));
     return MCI_OK;
   }
 

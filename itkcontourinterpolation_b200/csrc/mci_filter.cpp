@@ -17,8 +17,17 @@
 
 #include "../../include/mci_b200.h"
 
+// NVTX ranges per phase of a run: visible in Nsight Systems / ncu --nvtx; free when no tool is attached
+#include <nvtx3/nvToolsExt.h>
+
 namespace
 {
+
+struct NvtxRange
+{
+  explicit NvtxRange(const char * name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct Box
 {
@@ -237,6 +246,10 @@ detect_into_state(mci_ctx * ctx, const mci_filter_options * opt, FilterState & s
   return MCI_OK;
 }
 
+int
+run_from_state(mci_ctx * ctx, const mci_filter_options * opt, const int64_t dims[3], FilterState & st, int keepLo, int keepHi,
+               mci_filter_stats * stats, double t1);
+
 // GenerateData (X:1559-1637) on a volume already resident on the device.
 int
 run_core(mci_ctx * ctx, const mci_filter_options * opt, const int64_t dims[3], const int64_t * custom, int64_t nCustom,
@@ -244,7 +257,11 @@ run_core(mci_ctx * ctx, const mci_filter_options * opt, const int64_t dims[3], c
 {
   FilterState & st = state_of(ctx);
   double t0 = now_ms();
-  int rc = detect_into_state(ctx, opt, st); // also initialises the output with a copy of the input
+  int rc;
+  {
+    NvtxRange r("mci.detect_slices");
+    rc = detect_into_state(ctx, opt, st); // also initialises the output with a copy of the input
+  }
   if (rc)
     return rc;
   if (opt->use_custom_slice_positions)
@@ -261,6 +278,16 @@ run_core(mci_ctx * ctx, const mci_filter_options * opt, const int64_t dims[3], c
   }
   double t1 = now_ms();
   stats->ms_detect = t1 - t0;
+  return run_from_state(ctx, opt, dims, st, 0, -1, stats, t1);
+}
+
+// Everything of GenerateData after slice detection.  keepLo <= keepHi restricts the run to the segments with a mid
+// slice inside [keepLo, keepHi) along their axis (slab-sharded runs: the context holds a z-range of the volume).
+int
+run_from_state(mci_ctx * ctx, const mci_filter_options * opt, const int64_t dims[3], FilterState & st, int keepLo, int keepHi,
+               mci_filter_stats * stats, double t1)
+{
+  int rc = MCI_OK;
   stats->n_labels = (int64_t)st.bboxes.size();
   for (int a = 0; a < 3; ++a)
     for (auto & kv : st.labeledSlices[a])
@@ -342,6 +369,8 @@ run_core(mci_ctx * ctx, const mci_filter_options * opt, const int64_t dims[3], c
       {
         if (positions[k - 1] + 1 < positions[k]) // only if they are not adjacent slices (X:1502)
         {
+          if (keepLo <= keepHi && (positions[k - 1] + 1 >= keepHi || positions[k] - 1 < keepLo))
+            continue; // slab-sharded run: no mid slice of this segment lies in the owned range
           Segment s;
           s.axis = axis;
           s.label = kv.first;
@@ -396,8 +425,10 @@ run_core(mci_ctx * ctx, const mci_filter_options * opt, const int64_t dims[3], c
     segDescs[k].slice_j = segments[k].sj;
   }
   int32_t nPairs = 0;
+  nvtxRangePushA("mci.components_and_pairs");
   rc = mci_label_and_match(ctx, (int32_t)sliceDescs.size(), sliceDescs.data(), opt->use_ball_structuring_element,
                            (int32_t)segDescs.size(), segDescs.data(), ncomp.data(), &nPairs);
+  nvtxRangePop();
   if (rc)
     return rc;
   for (int32_t c : ncomp)
@@ -418,8 +449,11 @@ run_core(mci_ctx * ctx, const mci_filter_options * opt, const int64_t dims[3], c
   // pair bookkeeping -> jobs
   std::vector<mci_job> jobs;
   std::vector<int32_t> bIds;
-  for (size_t k = 0; k < segments.size(); ++k)
-    schedule_segment(segments[k], perSegment[k], opt->use_extrapolation != 0, jobs, bIds);
+  {
+    NvtxRange r("mci.schedule_pairs");
+    for (size_t k = 0; k < segments.size(); ++k)
+      schedule_segment(segments[k], perSegment[k], opt->use_extrapolation != 0, jobs, bIds);
+  }
   stats->n_jobs = (int64_t)jobs.size();
 
   mci_params prm;
@@ -428,7 +462,10 @@ run_core(mci_ctx * ctx, const mci_filter_options * opt, const int64_t dims[3], c
   prm.use_ball = opt->use_ball_structuring_element;
   prm.min_align_iters = 8;   // pow(2, ImageDimension) with ImageDimension = 3 (X:87)
   prm.max_align_iters = 216; // pow(6, ImageDimension)                         (X:89)
-  rc = mci_interpolate(ctx, (int32_t)jobs.size(), jobs.data(), bIds.data(), (int32_t)bIds.size(), &prm);
+  {
+    NvtxRange r("mci.interpolate");
+    rc = mci_interpolate(ctx, (int32_t)jobs.size(), jobs.data(), bIds.data(), (int32_t)bIds.size(), &prm);
+  }
   if (rc)
     return rc;
   return MCI_OK;
@@ -505,6 +542,59 @@ extern "C"
     rc = mci_synchronize(ctx);
     double t1 = now_ms();
     stats->ms_interpolate = t1 - t0 - stats->ms_detect - stats->ms_components - stats->ms_pairs;
+    stats->ms_total = t1 - t0;
+    stats->n_launches = mci_launch_count(ctx) - l0;
+    return rc;
+  }
+
+  // Slab-sharded runs: the context holds a contiguous range of the volume along opt->axis (its own slab plus the
+  // annotated slices that bound the segments reaching into it); slice sets and bounding boxes are the merged tables
+  // of all ranks, already shifted into the range's coordinates.  See include/mci_b200.h.
+  int mci_filter_run_with_detection(mci_ctx * ctx, const mci_filter_options * opt, const mci_label_info * labels, int32_t nLabels,
+                                    const mci_labeled_slice * slices, int32_t nSlices, int32_t keepLo, int32_t keepHi,
+                                    mci_filter_stats * stats)
+  {
+    if (!ctx || !opt || opt->axis < -1 || opt->axis > 2 || nLabels < 0 || nSlices < 0 || (nLabels && !labels) || (nSlices && !slices))
+      return MCI_ERR_ARG;
+    mci_filter_stats local;
+    if (!stats)
+      stats = &local;
+    std::memset(stats, 0, sizeof(*stats));
+    int64_t l0 = mci_launch_count(ctx);
+    double t0 = now_ms();
+    int64_t dims[3];
+    int ptype = 0;
+    int rc = mci_volume_dims(ctx, dims, &ptype);
+    if (rc)
+      return rc;
+    FilterState & st = state_of(ctx);
+    st.labeledSlices.assign(3, std::map<int64_t, std::set<int>>());
+    st.bboxes.clear();
+    for (int32_t k = 0; k < nLabels; ++k)
+    {
+      Box b;
+      for (int a = 0; a < 3; ++a)
+      {
+        b.idx[a] = labels[k].bbox_index[a];
+        b.size[a] = labels[k].bbox_size[a];
+        if (b.idx[a] < 0 || b.size[a] < 1)
+          return MCI_ERR_ARG;
+      }
+      st.bboxes[labels[k].label] = b;
+    }
+    for (int32_t k = 0; k < nSlices; ++k)
+    {
+      if (slices[k].axis < 0 || slices[k].axis > 2)
+        return MCI_ERR_ARG;
+      if (opt->axis == -1 || opt->axis == slices[k].axis)
+        st.labeledSlices[(size_t)slices[k].axis][slices[k].label].insert(slices[k].slice);
+    }
+    rc = run_from_state(ctx, opt, dims, st, keepLo, keepHi, stats, t0);
+    if (rc)
+      return rc;
+    rc = mci_synchronize(ctx);
+    double t1 = now_ms();
+    stats->ms_interpolate = t1 - t0 - stats->ms_components - stats->ms_pairs;
     stats->ms_total = t1 - t0;
     stats->n_launches = mci_launch_count(ctx) - l0;
     return rc;

@@ -140,6 +140,9 @@ class ShardedInterpolator:
         return partial
 
     def _combine(self, dst, src):
+        # dst / src were produced by torch on ITS stream (clones, NCCL results); the library launches on the context's
+        # own non-blocking stream, which has no implicit ordering with it
+        self.torch.cuda.current_stream(self.device).synchronize()
         self._check(self.lib.mci_combine_max(self.ctx, dst.data_ptr(), src.data_ptr(), dst.numel(), self._ptype[dst.dtype]))
 
     def run(self, vol, gather=True, mode="masks", **options):
@@ -174,3 +177,341 @@ class ShardedInterpolator:
                 self._check(self.lib.mci_synchronize(self.ctx))
 
         return exchange_and_combine(partial, self.group, combine, gather)
+
+
+# =====================================================================================================================
+# Slab-sharded runs: nobody streams, uploads or downloads more than its own slab (+ the annotated slices that bound
+# the segments reaching into it).  Single-axis runs along z (SetAxis(2)): the unit of parallelism of the reference is
+# the segment (X:1523-1537) and a segment writes only the slices strictly between its two annotated slices
+# (X:743-764), so the segments -- and with them every voxel write -- partition by z.
+#
+#   rank r owns planes [z0, z1) of the volume.
+#   1. slice detection (X:128-201) on the slab plus one halo plane per side (the 6-neighbour test reads z +- 1);
+#      entries of halo planes are dropped, they belong to the neighbour.
+#   2. ONE small all-gather merges the per-rank tables: label bounding boxes (X:148-159) and slice sets (X:161-197).
+#   3. every rank lists the segments with a mid slice in its slab; those that cross the slab boundary need annotated
+#      planes a neighbour owns: fetched from the host volume (host mode) or from the owner's HBM over NVLink (resident
+#      mode, NCCL send / recv of whole planes) -- the only voxel traffic between GPUs.
+#   4. mci_filter_run_with_detection on the local plane range, restricted to those segments.  No combine step: every
+#      output voxel is produced by exactly one rank.
+# The plan functions are pure (tests/test_distributed_cpu.py drives them, and the table exchange, on gloo).
+# =====================================================================================================================
+def merge_detection(tables):
+    """tables: per rank (labels [n,7] = label, bbox index xyz, bbox size xyz; slices [m,2] = label, z), global
+    coordinates.  Returns (bboxes {label: (lo[3], hi[3])}, slices {label: sorted z list})."""
+    bboxes, slices = {}, {}
+    for labels, sl in tables:
+        for row in np.asarray(labels).reshape(-1, 7).tolist():
+            lab, lo, hi = row[0], row[1:4], [row[1 + a] + row[4 + a] - 1 for a in range(3)]
+            if lab in bboxes:
+                blo, bhi = bboxes[lab]
+                bboxes[lab] = ([min(a, b) for a, b in zip(blo, lo)], [max(a, b) for a, b in zip(bhi, hi)])
+            else:
+                bboxes[lab] = (lo, hi)
+        for lab, z in np.asarray(sl).reshape(-1, 2).tolist():
+            slices.setdefault(lab, set()).add(z)
+    return bboxes, {lab: sorted(zs) for lab, zs in slices.items()}
+
+
+def plan_slab(slices, z0, z1, label=0):
+    """Which planes rank [z0, z1) must hold: returns (zlo, zhi, needed) -- the contiguous range covering its slab and
+    both annotated slices of every segment (X:1492-1519: consecutive annotated slices i < j with i + 1 < j) that has a
+    mid slice in the slab, and the sorted annotated planes outside [z0, z1) among them."""
+    zlo, zhi, needed = z0, z1, set()
+    if z1 <= z0:
+        return zlo, zhi, []
+    for lab, zs in slices.items():
+        if label not in (0, lab):
+            continue
+        for i, j in zip(zs[:-1], zs[1:]):
+            if i + 1 < j and max(i + 1, z0) <= min(j - 1, z1 - 1):
+                zlo, zhi = min(zlo, i), max(zhi, j + 1)
+                for z in (i, j):
+                    if not z0 <= z < z1:
+                        needed.add(z)
+    return zlo, zhi, sorted(needed)
+
+
+def exchange_tables(labels, slices, group=None, device="cpu", cap_labels=1024, cap_slices=32768):
+    """All-gather of the per-rank detection tables (int32 rows).  One collective of fixed-size slots; a second, exact
+    one only if some rank's tables overflow the slot."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    labels = np.asarray(labels, dtype=np.int32).reshape(-1, 7)
+    slices = np.asarray(slices, dtype=np.int32).reshape(-1, 2)
+
+    def pack(cl, cs):
+        buf = np.zeros(4 + 7 * cl + 2 * cs, np.int32)
+        buf[0], buf[1] = len(labels), len(slices)
+        if len(labels) <= cl and len(slices) <= cs:
+            buf[4:4 + 7 * len(labels)] = labels.reshape(-1)
+            buf[4 + 7 * cl:4 + 7 * cl + 2 * len(slices)] = slices.reshape(-1)
+        return buf
+
+    def gather(cl, cs):
+        send = torch.from_numpy(pack(cl, cs)).to(device)
+        recv = torch.empty((world, send.numel()), dtype=torch.int32, device=device)
+        if hasattr(dist, "all_gather_into_tensor") and str(device) != "cpu":
+            dist.all_gather_into_tensor(recv.view(-1), send, group=group)
+        else:
+            dist.all_gather([recv[q] for q in range(world)], send, group=group)
+        return recv.cpu().numpy()
+
+    got = gather(cap_labels, cap_slices)
+    nl, ns = int(got[:, 0].max()), int(got[:, 1].max())
+    if nl > cap_labels or ns > cap_slices:
+        cap_labels, cap_slices = max(nl, 1), max(ns, 1)
+        got = gather(cap_labels, cap_slices)
+    out = []
+    for q in range(world):
+        a, b = int(got[q, 0]), int(got[q, 1])
+        out.append((got[q, 4:4 + 7 * a].reshape(-1, 7), got[q, 4 + 7 * cap_labels:4 + 7 * cap_labels + 2 * b].reshape(-1, 2)))
+    return out, int(got.nbytes)
+
+
+class SlabShardedInterpolator:
+    """One volume, one z-slab per GPU (one process per GPU, torch.distributed).  See the block comment above.
+
+    host mode:      run_host(window, window_z0, out_slab)  -- pinned host planes in, pinned host slab out (end to end)
+    resident mode:  load_slab(t) once, then run_resident() -- the slab stays in HBM, extra planes come from peers
+    """
+
+    def __init__(self, device, dims, dtype, group=None, margin=16):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        from . import _lib as L
+        self.L, self.ct, self.torch, self.dist = L, ctypes, torch, dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.device = torch.device("cuda", device)
+        self.X, self.Y, self.Z = (int(d) for d in dims)
+        self.dtype = dtype
+        self.bounds = slab_bounds(self.Z, self.world)
+        self.z0, self.z1 = self.bounds[self.rank]
+        self.lib = L.lib()
+        self.ctx = ctypes.c_void_p()
+        rc = self.lib.mci_create(ctypes.byref(self.ctx), device)
+        if rc:
+            raise L.MciError(rc, "mci_create failed (no usable CUDA device; there is no CPU fallback)")
+        self.opt = L.FilterOptions()
+        self.lib.mci_filter_default_options(ctypes.byref(self.opt))
+        self.opt.axis = 2
+        self.stream = torch.cuda.ExternalStream(self.lib.mci_stream(self.ctx), device=self.device)
+        self._ptype = {torch.uint8: L.U8, torch.uint16: L.U16, torch.int16: L.I16}[dtype]
+        self.margin = 0
+        self._alloc(margin)
+        self.nvlink_bytes = 0
+        self.table_bytes = 0
+        self.last_stats = {}
+        # NCCL moves device memory (NVLink); any other backend (gloo, in tests) gets the planes staged through the host
+        self._nccl = dist.is_initialized() and dist.get_backend(group) == "nccl"
+
+    def close(self):
+        if self.ctx:
+            self.lib.mci_destroy(self.ctx)
+            self.ctx = self.ct.c_void_p()
+
+    def _check(self, rc):
+        if rc:
+            raise self.L.MciError(rc, self.lib.mci_last_error(self.ctx).decode())
+
+    # device planes: global z lives at buffer plane z - z0 + margin
+    def _alloc(self, margin):
+        torch = self.torch
+        old = (self.buf_in, self.margin) if self.margin else None
+        n = (self.z1 - self.z0) + 2 * margin
+        self.buf_in = torch.zeros((n, self.Y, self.X), dtype=self.dtype, device=self.device)
+        self.buf_out = torch.zeros((n, self.Y, self.X), dtype=self.dtype, device=self.device)
+        if old is not None:
+            src, m = old
+            self.buf_in[margin - m:margin - m + src.shape[0]] = src
+        self.margin = margin
+
+    def _p(self, z):
+        return z - self.z0 + self.margin
+
+    def set_options(self, **options):
+        for k, v in options.items():
+            setattr(self.opt, k, int(v))
+        if self.opt.axis != 2:
+            raise ValueError("slab-sharded runs interpolate along z (SetAxis(2)); use ShardedInterpolator otherwise")
+
+    def _attach(self, zlo, zhi):
+        a, b = self._p(zlo), self._p(zhi)
+        tin, tout = self.buf_in[a:b], self.buf_out[a:b]
+        self._compact = None
+        if tin.data_ptr() % 16 or tout.data_ptr() % 16:  # odd plane sizes: work on aligned copies
+            with self.torch.cuda.stream(self.stream):
+                tin, tout = tin.clone(), tout.clone()
+            self._compact = (tout, a, b)
+        dims = (self.ct.c_int64 * 3)(self.X, self.Y, zhi - zlo)
+        self._check(self.lib.mci_attach_device_volume(self.ctx, tin.data_ptr(), tout.data_ptr(), dims, self._ptype))
+        self._attached = (tin, tout)
+
+    def _detach(self):
+        if self._compact is not None:
+            tout, a, b = self._compact
+            with self.torch.cuda.stream(self.stream):
+                self.buf_out[a:b] = tout
+            self._compact = None
+
+    def _detect(self):
+        """slab + halo planes -> this rank's tables in global coordinates (halo entries dropped)"""
+        ct, L = self.ct, self.L
+        h0, h1 = (1 if self.z0 > 0 else 0), (1 if self.z1 < self.Z else 0)
+        if self.z1 <= self.z0:
+            return np.zeros((0, 7), np.int32), np.zeros((0, 2), np.int32)
+        self._attach(self.z0 - h0, self.z1 + h1)
+        nl, ns = ct.c_int32(0), ct.c_int32(0)
+        self._check(self.lib.mci_detect_slices(self.ctx, 2, ct.byref(nl), ct.byref(ns)))
+        labels = (L.LabelInfo * max(nl.value, 1))()
+        slices = (L.LabeledSlice * max(ns.value, 1))()
+        self._check(self.lib.mci_get_detection(self.ctx, labels, slices))
+        self._detach()
+        base = self.z0 - h0
+        lab = np.array([[labels[k].label, labels[k].bbox_index[0], labels[k].bbox_index[1], labels[k].bbox_index[2] + base,
+                         labels[k].bbox_size[0], labels[k].bbox_size[1], labels[k].bbox_size[2]] for k in range(nl.value)],
+                       dtype=np.int32).reshape(-1, 7)
+        sl = np.array([[slices[k].label, slices[k].slice + base] for k in range(ns.value)
+                       if slices[k].axis == 2 and self.z0 <= slices[k].slice + base < self.z1], dtype=np.int32).reshape(-1, 2)
+        return lab, sl
+
+    def _gather_tables(self, lab, sl):
+        if self.world == 1:
+            return [(lab, sl)]
+        with self.torch.cuda.stream(self.stream):
+            tables, nbytes = exchange_tables(lab, sl, self.group, self.device if self._nccl else "cpu")
+        self.table_bytes += nbytes
+        return tables
+
+    def _run_local(self, bboxes, slices, zlo, zhi):
+        ct, L = self.ct, self.L
+        self._attach(zlo, zhi)
+        labs = sorted(bboxes)
+        li = (L.LabelInfo * max(len(labs), 1))()
+        for k, lab in enumerate(labs):
+            lo, hi = bboxes[lab]
+            li[k].label = lab
+            for a in range(3):
+                li[k].bbox_index[a] = lo[a]
+                li[k].bbox_size[a] = hi[a] - lo[a] + 1
+            li[k].bbox_index[2] = max(0, lo[2] - zlo)  # the z extent of the box is not used by runs along z
+            li[k].bbox_size[2] = 1
+        rows = [(lab, z - zlo) for lab, zs in slices.items() for z in zs if zlo <= z < zhi]
+        ls = (L.LabeledSlice * max(len(rows), 1))()
+        for k, (lab, z) in enumerate(rows):
+            ls[k].axis, ls[k].slice, ls[k].label = 2, z, lab
+        st = L.FilterStats()
+        self._check(self.lib.mci_filter_run_with_detection(self.ctx, ct.byref(self.opt), li, len(labs), ls, len(rows),
+                                                           self.z0 - zlo, self.z1 - zlo, ct.byref(st)))
+        self._detach()
+        self.last_stats = st.as_dict()
+
+    def _ensure_margin(self, zlo, zhi):
+        need = max(self.z0 - zlo, zhi - self.z1, 1)
+        if need > self.margin:
+            self._check(self.lib.mci_synchronize(self.ctx))
+            self._alloc(need)
+            with self.torch.cuda.stream(self.stream):  # detection had initialised the output of the old buffers
+                self.buf_out[self._p(self.z0):self._p(self.z1)] = self.buf_in[self._p(self.z0):self._p(self.z1)]
+            return True
+        return False
+
+    # ---- host mode ------------------------------------------------------------------------------------------------
+    def run_host(self, window, window_z0, out_slab, **options):
+        """window: pinned host tensor holding planes [window_z0, window_z0 + len) of the volume -- at least the slab
+        and whatever bounds the segments reaching into it (the whole volume always works).  out_slab: pinned host
+        tensor [z1 - z0, Y, X] that receives this rank's planes of the interpolated volume."""
+        torch = self.torch
+        self.set_options(**options)
+        z0, z1 = self.z0, self.z1
+
+        def h2d(za, zb):
+            if zb > za:
+                if za < window_z0 or zb > window_z0 + window.shape[0]:
+                    raise ValueError("host window [%d, %d) does not hold planes [%d, %d)" % (window_z0, window_z0 + window.shape[0], za, zb))
+                with torch.cuda.stream(self.stream):
+                    self.buf_in[self._p(za):self._p(zb)].copy_(window[za - window_z0:zb - window_z0], non_blocking=True)
+
+        h0, h1 = (1 if z0 > 0 else 0), (1 if z1 < self.Z else 0)
+        h2d(z0 - h0, z1 + h1)
+        lab, sl = self._detect()
+        bboxes, slices = merge_detection(self._gather_tables(lab, sl))
+        zlo, zhi, needed = plan_slab(slices, z0, z1, int(self.opt.label))
+        self._ensure_margin(zlo, zhi)
+        for z in needed:
+            if not z0 - h0 <= z < z1 + h1:
+                h2d(z, z + 1)
+        if z1 > z0:
+            self._run_local(bboxes, slices, zlo, zhi)
+            with torch.cuda.stream(self.stream):
+                out_slab.copy_(self.buf_out[self._p(z0):self._p(z1)], non_blocking=True)
+        self.stream.synchronize()
+        return out_slab
+
+    # ---- resident mode --------------------------------------------------------------------------------------------
+    def load_slab(self, slab):
+        """slab: tensor [z1 - z0, Y, X] (host or device) = this rank's planes of the input volume"""
+        with self.torch.cuda.stream(self.stream):
+            self.buf_in[self._p(self.z0):self._p(self.z1)].copy_(slab, non_blocking=True)
+        self.stream.synchronize()
+
+    def output_slab(self):
+        return self.buf_out[self._p(self.z0):self._p(self.z1)]
+
+    def _owner(self, z):
+        for q, (lo, hi) in enumerate(self.bounds):
+            if lo <= z < hi:
+                return q
+        raise ValueError(z)
+
+    def _fetch_planes(self, needs):
+        """needs[q] = planes rank q lacks (every rank passes the same table): owners send, over NCCL / NVLink"""
+        torch, dist = self.torch, self.dist
+        if self.world == 1:
+            return
+        ops, landed = [], []
+        plane_bytes = self.X * self.Y * self.buf_in.element_size()
+        if not self._nccl:
+            self.stream.synchronize()
+        for q in range(self.world):
+            for z in needs[q]:
+                o = self._owner(z)
+                if o == q:
+                    continue
+                plane = self.buf_in[self._p(z)].view(torch.uint8)
+                if o == self.rank:
+                    ops.append(dist.P2POp(dist.isend, plane if self._nccl else plane.cpu(), q, self.group))
+                elif q == self.rank:
+                    dst = plane if self._nccl else torch.empty(plane.shape, dtype=torch.uint8)
+                    landed.append((plane, dst))
+                    ops.append(dist.P2POp(dist.irecv, dst, o, self.group))
+                    self.nvlink_bytes += plane_bytes
+        if ops:
+            with torch.cuda.stream(self.stream):
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+                if not self._nccl:
+                    for plane, dst in landed:
+                        plane.copy_(dst)
+
+    def run_resident(self, **options):
+        """the slab loaded by load_slab is interpolated in place in HBM; returns the device tensor of output planes"""
+        self.set_options(**options)
+        bounds = self.bounds
+        halos = [[z for z in (lo - 1, hi) if 0 <= z < self.Z and hi > lo] for lo, hi in bounds]
+        self._fetch_planes(halos)
+        lab, sl = self._detect()
+        bboxes, slices = merge_detection(self._gather_tables(lab, sl))
+        plans = [plan_slab(slices, lo, hi, int(self.opt.label)) for lo, hi in bounds]
+        zlo, zhi, _ = plans[self.rank]
+        if self._ensure_margin(zlo, zhi):
+            self._fetch_planes(halos)
+        extra = [[z for z in plans[q][2] if z not in halos[q]] for q in range(self.world)]
+        self._fetch_planes(extra)
+        if self.z1 > self.z0:
+            self._run_local(bboxes, slices, zlo, zhi)
+        return self.output_slab()

@@ -81,13 +81,8 @@ class MorphologicalContourInterpolator:
         self._upload(vol)
         n = ctypes.c_int64(0)
         self._check(self._lib.mci_filter_detect(self._ctx, ctypes.byref(self._opt), ctypes.byref(n)))
-        trip = np.zeros((max(n.value, 1), 3), np.int64)
-        self._check(self._lib.mci_filter_get_labeled_slices(self._ctx, trip.ctypes.data))
-        table = {}
-        for a, l, s in trip[:n.value]:
-            table.setdefault(int(a), {}).setdefault(int(l), []).append(int(s))
-        self._detected = table
-        return table
+        self._detected = self._fetch_labeled_slices(n.value)
+        return self._detected
 
     # ---- pipeline ----
     def SetInput(self, vol):
@@ -96,6 +91,7 @@ class MorphologicalContourInterpolator:
             raise TypeError("expected a 3-D uint8/uint16/int16 label volume indexed [z, y, x]")
         self._input = vol
         self._output = None
+        self._detected = None  # slice sets of a previous input say nothing about this one
 
     def Update(self):
         vol = self._require_input()
@@ -112,8 +108,18 @@ class MorphologicalContourInterpolator:
         self._check(rc)
         self.last_stats = st.as_dict()
         self._output = out
-        n = ctypes.c_int64(0)
+        if not self._opt.use_custom_slice_positions:
+            # like the reference, whose GenerateData leaves m_LabeledSlices filled (X:1573-1576): what the run detected
+            self._detected = self._fetch_labeled_slices(int(st.n_annotated_slices))
         return out
+
+    def _fetch_labeled_slices(self, n):
+        trip = np.zeros((max(n, 1), 3), np.int64)
+        self._check(self._lib.mci_filter_get_labeled_slices(self._ctx, trip.ctypes.data))
+        table = {}
+        for a, l, s in trip[:n]:
+            table.setdefault(int(a), {}).setdefault(int(l), []).append(int(s))
+        return table
 
     def GetOutput(self):
         if self._output is None:

@@ -98,3 +98,64 @@ def test_combine_by_mid_slice_shapes(name, kw_gpu, kw_cpu):
     finally:
         for ctx in ctxs:
             lib.mci_destroy(ctx)
+
+
+# ---- slab-sharded path: one z-slab per process, several processes sharing this box's GPU, gloo for the plumbing ----
+def _slab_volume(name):
+    import test_slab_sharded_cpu as T
+    if name == "Staggered":
+        return T.volume(name)
+    return cases.synthetic_small()[name][0]
+
+
+def _slab_worker(rank, world, port, name, q):
+    import os
+    import torch.distributed as dist
+    from itkcontourinterpolation_b200.distributed import SlabShardedInterpolator
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        vol = _slab_volume(name)
+        Z, Y, X = vol.shape
+        f = SlabShardedInterpolator(0, (X, Y, Z), torch.int16, margin=2)  # small margin: the regrow path runs too
+        try:
+            host = torch.from_numpy(vol.view(np.int16)).pin_memory()
+            out = torch.empty((f.z1 - f.z0, Y, X), dtype=torch.int16).pin_memory()
+            f.run_host(host, 0, out)
+            e2e = out.numpy().view(np.uint16).copy()
+            st = dict(f.last_stats)
+            f.load_slab(host[f.z0:f.z1])
+            res = f.run_resident().cpu().numpy().view(np.uint16).copy()
+            q.put((rank, f.z0, f.z1, e2e, res, st, f.nvlink_bytes))
+        finally:
+            f.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,name", [(2, "Staggered"), (3, "Staggered"), (3, "C5"), (2, "Branching")])
+def test_slab_sharded_ranks_reproduce_their_planes(world, name):
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_slab_worker, args=(r, world, port, name, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    vol = _slab_volume(name)
+    ref, st_full = O.interpolate(vol, axis=2, return_stats=True)
+    nseg = 0
+    for rank, z0, z1, e2e, res, st, nv in results:
+        assert np.array_equal(e2e, ref[z0:z1]), "host mode, rank %d" % rank
+        assert np.array_equal(res, ref[z0:z1]), "resident mode, rank %d" % rank
+        nseg += st["n_segments"]
+    assert nseg >= st_full["segments"]  # a segment crossing a slab boundary is interpolated by both owners

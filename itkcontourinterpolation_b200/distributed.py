@@ -299,7 +299,11 @@ class SlabShardedInterpolator:
         self.opt = L.FilterOptions()
         self.lib.mci_filter_default_options(ctypes.byref(self.opt))
         self.opt.axis = 2
-        self.stream = torch.cuda.ExternalStream(self.lib.mci_stream(self.ctx), device=self.device)
+        # torch-side work (copies, NCCL) runs on a torch-owned stream; the library launches on the context's own
+        # stream and synchronises it before it returns, so the only ordering needed is "torch work done before a
+        # library call" (_lib_call).  (Wrapping the context's stream as a torch ExternalStream would leave pinned
+        # tensors that were copied on it recording events on a destroyed stream after close().)
+        self.stream = torch.cuda.Stream(device=self.device)
         self._ptype = {torch.uint8: L.U8, torch.uint16: L.U16, torch.int16: L.I16}[dtype]
         self.margin = 0
         self._alloc(margin)
@@ -311,23 +315,30 @@ class SlabShardedInterpolator:
 
     def close(self):
         if self.ctx:
+            self.stream.synchronize()
             self.lib.mci_destroy(self.ctx)
             self.ctx = self.ct.c_void_p()
+            self.buf_in = self.buf_out = self._attached = self._compact = None
 
     def _check(self, rc):
         if rc:
             raise self.L.MciError(rc, self.lib.mci_last_error(self.ctx).decode())
+
+    def _lib_call(self, fn, *args):
+        self.stream.synchronize()  # everything torch queued (uploads, received planes) has landed
+        self._check(fn(self.ctx, *args))
 
     # device planes: global z lives at buffer plane z - z0 + margin
     def _alloc(self, margin):
         torch = self.torch
         old = (self.buf_in, self.margin) if self.margin else None
         n = (self.z1 - self.z0) + 2 * margin
-        self.buf_in = torch.zeros((n, self.Y, self.X), dtype=self.dtype, device=self.device)
-        self.buf_out = torch.zeros((n, self.Y, self.X), dtype=self.dtype, device=self.device)
-        if old is not None:
-            src, m = old
-            self.buf_in[margin - m:margin - m + src.shape[0]] = src
+        with torch.cuda.stream(self.stream):
+            self.buf_in = torch.zeros((n, self.Y, self.X), dtype=self.dtype, device=self.device)
+            self.buf_out = torch.zeros((n, self.Y, self.X), dtype=self.dtype, device=self.device)
+            if old is not None:
+                src, m = old
+                self.buf_in[margin - m:margin - m + src.shape[0]] = src
         self.margin = margin
 
     def _p(self, z):
@@ -348,7 +359,7 @@ class SlabShardedInterpolator:
                 tin, tout = tin.clone(), tout.clone()
             self._compact = (tout, a, b)
         dims = (self.ct.c_int64 * 3)(self.X, self.Y, zhi - zlo)
-        self._check(self.lib.mci_attach_device_volume(self.ctx, tin.data_ptr(), tout.data_ptr(), dims, self._ptype))
+        self._lib_call(self.lib.mci_attach_device_volume, tin.data_ptr(), tout.data_ptr(), dims, self._ptype)
         self._attached = (tin, tout)
 
     def _detach(self):
@@ -366,7 +377,7 @@ class SlabShardedInterpolator:
             return np.zeros((0, 7), np.int32), np.zeros((0, 2), np.int32)
         self._attach(self.z0 - h0, self.z1 + h1)
         nl, ns = ct.c_int32(0), ct.c_int32(0)
-        self._check(self.lib.mci_detect_slices(self.ctx, 2, ct.byref(nl), ct.byref(ns)))
+        self._lib_call(self.lib.mci_detect_slices, 2, ct.byref(nl), ct.byref(ns))
         labels = (L.LabelInfo * max(nl.value, 1))()
         slices = (L.LabeledSlice * max(ns.value, 1))()
         self._check(self.lib.mci_get_detection(self.ctx, labels, slices))
@@ -405,15 +416,15 @@ class SlabShardedInterpolator:
         for k, (lab, z) in enumerate(rows):
             ls[k].axis, ls[k].slice, ls[k].label = 2, z, lab
         st = L.FilterStats()
-        self._check(self.lib.mci_filter_run_with_detection(self.ctx, ct.byref(self.opt), li, len(labs), ls, len(rows),
-                                                           self.z0 - zlo, self.z1 - zlo, ct.byref(st)))
+        self._lib_call(self.lib.mci_filter_run_with_detection, ct.byref(self.opt), li, len(labs), ls, len(rows),
+                       self.z0 - zlo, self.z1 - zlo, ct.byref(st))
         self._detach()
         self.last_stats = st.as_dict()
 
     def _ensure_margin(self, zlo, zhi):
         need = max(self.z0 - zlo, zhi - self.z1, 1)
         if need > self.margin:
-            self._check(self.lib.mci_synchronize(self.ctx))
+            self._lib_call(self.lib.mci_synchronize)
             self._alloc(need)
             with self.torch.cuda.stream(self.stream):  # detection had initialised the output of the old buffers
                 self.buf_out[self._p(self.z0):self._p(self.z1)] = self.buf_in[self._p(self.z0):self._p(self.z1)]
@@ -475,8 +486,7 @@ class SlabShardedInterpolator:
             return
         ops, landed = [], []
         plane_bytes = self.X * self.Y * self.buf_in.element_size()
-        if not self._nccl:
-            self.stream.synchronize()
+        self.stream.synchronize()
         for q in range(self.world):
             for z in needs[q]:
                 o = self._owner(z)
@@ -514,4 +524,5 @@ class SlabShardedInterpolator:
         self._fetch_planes(extra)
         if self.z1 > self.z0:
             self._run_local(bboxes, slices, zlo, zhi)
+        self.stream.synchronize()
         return self.output_slab()

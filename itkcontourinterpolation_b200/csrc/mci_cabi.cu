@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -1387,16 +1388,21 @@ extern "C"
       }
       const int histSide = ctx->ptype == MCI_U8 ? 256 : (ctx->ptype == MCI_U16 ? 6560 : 3296);
       const int histStride = 2 * histSide + histSide / 32; // counts of both sides + bitmap of touched entries
-      const int nbig = 128;
-      const size_t histBytes = size_t(maxLevelNodes) * histStride * 4;
+      static const bool useLevels = std::getenv("MCI_DT_LEVELS") != nullptr; // the level-synchronous path of round 1 (A/B runs)
+      const int treeGridMax = ctx->L.sms * 2; // two 512-thread CTAs per SM (1024 x 1: C3 0.37 vs 0.41 ms, but C5 6.5 vs 5.0 ms)
+      const int nbig = useLevels ? 128 : std::max(128, treeGridMax); // tree path: a CTA keeps one wrapped-bin table
+      const size_t histBytes = useLevels ? size_t(maxLevelNodes) * histStride * 4 : 0;
       const size_t bigBytes = size_t(nbig) * (2 * 65536 + 2048) * 4;
-      if (ctx->dHist.cap < histBytes)
-        ctx->histClean = false;
-      CK(ctx->dHist.ensure(histBytes));
-      if (!ctx->histClean)
+      if (useLevels)
       {
-        CK(cudaMemsetAsync(ctx->dHist.p, 0, ctx->dHist.cap, s));
-        ctx->histClean = true;
+        if (ctx->dHist.cap < histBytes)
+          ctx->histClean = false;
+        CK(ctx->dHist.ensure(histBytes));
+        if (!ctx->histClean)
+        {
+          CK(cudaMemsetAsync(ctx->dHist.p, 0, ctx->dHist.cap, s));
+          ctx->histClean = true;
+        }
       }
       if (ctx->dDtBig.cap < bigBytes)
         ctx->dtBigClean = false;
@@ -1406,55 +1412,109 @@ extern "C"
         CK(cudaMemsetAsync(ctx->dDtBig.p, 0, bigBytes, s));
         ctx->dtBigClean = true;
       }
-      CK(ctx->dWork.ensure(size_t(maxLevelNodes) * sizeof(NodeWork)));
-      CK(ctx->dItems.ensure(size_t(2 * itemCap + hitemCap + 4) * sizeof(DtItem)));
-      CK(ctx->dLevelScratch.ensure((scratchCap + 64) * 4));
-      // per level: [0] items, [1] write items, [2] wrapped-bin tables in use; and a 64-bit scratch top
-      CK(ctx->dDtCounters.ensure(size_t(maxDepth) * (4 * sizeof(int) + 8)));
-      CK(cudaMemsetAsync(ctx->dDtCounters.p, 0, size_t(maxDepth) * (4 * sizeof(int) + 8), s));
-      unsigned long long * tops = (unsigned long long *)ctx->dDtCounters.p;
-      int * ctrs = (int *)(tops + maxDepth);
-      for (int d = 0; d < maxDepth; ++d)
+      if (!useLevels)
       {
-        DtLevel lv;
-        lv.nodes = dNodes + off;
-        lv.count = dCounts + d;
-        lv.maxNodes = (int)levelCap[d];
-        lv.work = (NodeWork *)ctx->dWork.p;
-        lv.arena = (uint32_t *)ctx->dArena.p;
-        lv.arenaTop = (unsigned long long *)ctx->dArenaTop.p;
-        lv.arenaCap = arenaCap;
-        lv.scratch = (uint32_t *)ctx->dLevelScratch.p;
-        lv.scratchTop = tops + d;
-        lv.scratchCap = scratchCap;
-        lv.items = (DtItem *)ctx->dItems.p;
-        lv.itemCount = ctrs + 4 * d;
-        lv.witems = (DtItem *)ctx->dItems.p + itemCap + 1;
-        lv.witemCount = ctrs + 4 * d + 1;
-        lv.itemCap = (int)itemCap;
-        lv.hitems = (DtItem *)ctx->dItems.p + 2 * itemCap + 2;
-        lv.hitemCount = ctrs + 4 * d + 3;
-        lv.hitemCap = (int)hitemCap;
-        lv.hist = (unsigned *)ctx->dHist.p;
-        lv.histStride = histStride;
-        lv.histSide = histSide;
-        lv.bigHist = (unsigned *)ctx->dDtBig.p;
-        lv.bigCount = ctrs + 4 * d + 2;
-        lv.nbig = nbig;
-        lv.next = dNodes + off + levelCap[d];
-        lv.nextCount = dCounts + d + 1;
-        lv.nextCap = d + 1 < maxDepth ? (int)levelCap[d + 1] : 0;
-        lv.emit = dEmitRecs;
-        lv.emitCount = dEmitCount;
-        lv.emitCap = ctx->emitCap;
-        lv.emitBase = ctx->emitBase;
-        lv.in = ctx->dIn;
-        lv.out = ctx->dOut;
-        for (int a = 0; a < 3; ++a)
-          lv.dims[a] = ctx->dims[a];
-        lv.err = ctx->dErr;
-        launch_dt_level(ctx->L, ctx->ptype, lv);
-        off += levelCap[d];
+        // one CTA per recursion tree (k_dt_tree): a node's rows live in shared memory when they fit, else in the
+        // CTA's own slice of global scratch
+        const u64 perCta = 4 * maxNodeWords + 64;
+        int grid = (int)std::max<long long>(1, std::min<long long>(nodeTotal, treeGridMax)); // children spread over idle CTAs
+        while (grid > 1 && (u64)grid * perCta * 4 > (u64(2) << 30))
+          grid = (grid + 1) / 2;
+        CK(ctx->dLevelScratch.ensure(((u64)grid * perCta + 64) * 4));
+        // counters (head, wrapped-bin tables in use, tail, pushed, done) followed by one "published" flag per child slot
+        const long long childSlots = std::max<long long>(nodeTotal - nRootNodes, 0) + 1;
+        CK(ctx->dDtCounters.ensure(size_t(8 + childSlots) * sizeof(int)));
+        CK(cudaMemsetAsync(ctx->dDtCounters.p, 0, size_t(8 + childSlots) * sizeof(int), s));
+        TreeParams P;
+        P.roots = dNodes;
+        P.rootCount = dCounts;
+        P.rootNext = (int *)ctx->dDtCounters.p;
+        P.flags = (int *)ctx->dDtCounters.p + 8;
+        P.queueCap = (int)childSlots;
+        P.arena = (uint32_t *)ctx->dArena.p;
+        P.arenaTop = (unsigned long long *)ctx->dArenaTop.p;
+        P.arenaCap = arenaCap;
+        P.scratch = (uint32_t *)ctx->dLevelScratch.p;
+        P.scratchPerCta = perCta;
+        P.histSide = histSide;
+        P.bigHist = (unsigned *)ctx->dDtBig.p;
+        P.bigCount = (int *)ctx->dDtCounters.p + 1;
+        P.nbig = nbig;
+        P.emit = dEmitRecs;
+        P.emitCount = dEmitCount;
+        P.emitCap = ctx->emitCap;
+        P.emitBase = ctx->emitBase;
+        P.in = ctx->dIn;
+        P.out = ctx->dOut;
+        P.VX = ctx->dims[0];
+        P.VY = ctx->dims[1];
+        P.VZ = ctx->dims[2];
+        P.err = ctx->dErr;
+        if (std::getenv("MCI_TREE_PROFILE"))
+          CK(cudaMemsetAsync(P.scratch + (size_t)grid * perCta, 0, 64, s));
+        launch_dt_tree(ctx->L, ctx->ptype, P, nRootNodes, grid);
+        if (std::getenv("MCI_TREE_PROFILE"))
+        {
+          // cycles per phase summed over the CTAs (only meaningful in a -DMCI_TREE_PROFILE build)
+          unsigned long long ph[7];
+          CK(cudaMemcpyAsync(ph, P.scratch + (size_t)grid * perCta, sizeof(ph), cudaMemcpyDeviceToHost, s));
+          CK(cudaStreamSynchronize(s));
+          std::fprintf(stderr, "k_dt_tree phases (cycles / CTA, grid %d): prep %llu hist %llu scan %llu median %llu alloc %llu emit %llu other %llu\n",
+                       grid, ph[0] / grid, ph[1] / grid, ph[2] / grid, ph[3] / grid, ph[4] / grid, ph[5] / grid, ph[6] / grid);
+        }
+      }
+      else
+      {
+        CK(ctx->dWork.ensure(size_t(maxLevelNodes) * sizeof(NodeWork)));
+        CK(ctx->dItems.ensure(size_t(2 * itemCap + hitemCap + 4) * sizeof(DtItem)));
+        CK(ctx->dLevelScratch.ensure((scratchCap + 64) * 4));
+        // per level: [0] items, [1] write items, [2] wrapped-bin tables in use; and a 64-bit scratch top
+        CK(ctx->dDtCounters.ensure(size_t(maxDepth) * (4 * sizeof(int) + 8)));
+        CK(cudaMemsetAsync(ctx->dDtCounters.p, 0, size_t(maxDepth) * (4 * sizeof(int) + 8), s));
+        unsigned long long * tops = (unsigned long long *)ctx->dDtCounters.p;
+        int * ctrs = (int *)(tops + maxDepth);
+        for (int d = 0; d < maxDepth; ++d)
+        {
+          DtLevel lv;
+          lv.nodes = dNodes + off;
+          lv.count = dCounts + d;
+          lv.maxNodes = (int)levelCap[d];
+          lv.work = (NodeWork *)ctx->dWork.p;
+          lv.arena = (uint32_t *)ctx->dArena.p;
+          lv.arenaTop = (unsigned long long *)ctx->dArenaTop.p;
+          lv.arenaCap = arenaCap;
+          lv.scratch = (uint32_t *)ctx->dLevelScratch.p;
+          lv.scratchTop = tops + d;
+          lv.scratchCap = scratchCap;
+          lv.items = (DtItem *)ctx->dItems.p;
+          lv.itemCount = ctrs + 4 * d;
+          lv.witems = (DtItem *)ctx->dItems.p + itemCap + 1;
+          lv.witemCount = ctrs + 4 * d + 1;
+          lv.itemCap = (int)itemCap;
+          lv.hitems = (DtItem *)ctx->dItems.p + 2 * itemCap + 2;
+          lv.hitemCount = ctrs + 4 * d + 3;
+          lv.hitemCap = (int)hitemCap;
+          lv.hist = (unsigned *)ctx->dHist.p;
+          lv.histStride = histStride;
+          lv.histSide = histSide;
+          lv.bigHist = (unsigned *)ctx->dDtBig.p;
+          lv.bigCount = ctrs + 4 * d + 2;
+          lv.nbig = nbig;
+          lv.next = dNodes + off + levelCap[d];
+          lv.nextCount = dCounts + d + 1;
+          lv.nextCap = d + 1 < maxDepth ? (int)levelCap[d + 1] : 0;
+          lv.emit = dEmitRecs;
+          lv.emitCount = dEmitCount;
+          lv.emitCap = ctx->emitCap;
+          lv.emitBase = ctx->emitBase;
+          lv.in = ctx->dIn;
+          lv.out = ctx->dOut;
+          for (int a = 0; a < 3; ++a)
+            lv.dims[a] = ctx->dims[a];
+          lv.err = ctx->dErr;
+          launch_dt_level(ctx->L, ctx->ptype, lv);
+          off += levelCap[d];
+        }
       }
       // k_dt_emit wrote the slices of axes 1 and 2; the trees perpendicular to x go x-run by x-run
       launch_apply_axis0(ctx->L, ctx->ptype, (Axis0Group *)(jb + oGroups), (int)axis0Groups.size(), dEmitRecs, dSlots,

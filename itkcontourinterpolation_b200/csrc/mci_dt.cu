@@ -35,10 +35,20 @@ pack_row(int a, int b, bool single)
 // distance to the row is the distance to that interval); 0 = empty row.  bandInfo[b] is the same
 // extent over rows 8b..8b+7: a whole band is skipped when even its nearest row and nearest column
 // cannot beat the best distance so far.
-__device__ __forceinline__ int
-dt_probe_row(const uint32_t * __restrict__ Xb, const uint32_t * __restrict__ rowInfo, int pitch, int x, int rr, int dd, int best)
+// NC = true: the rows are read through the non-coherent path (__ldg; written by an earlier kernel); NC = false:
+// plain loads (k_dt_tree writes and reads them in one kernel, in shared memory when they fit)
+template <bool NC>
+__device__ __forceinline__ uint32_t
+dt_ld(const uint32_t * p)
 {
-  const uint32_t info = __ldg(rowInfo + rr);
+  return NC ? __ldg(p) : *p;
+}
+
+template <bool NC = true>
+__device__ __forceinline__ int
+dt_probe_row(const uint32_t * Xb, const uint32_t * rowInfo, int pitch, int x, int rr, int dd, int best)
+{
+  const uint32_t info = dt_ld<NC>(rowInfo + rr);
   if (!info)
     return best;
   const int a = info & 0x1FFF, b = (info >> 13) & 0x1FFF;
@@ -51,10 +61,11 @@ dt_probe_row(const uint32_t * __restrict__ Xb, const uint32_t * __restrict__ row
   return min(best, dd + row_nearest_sq(Xb + (size_t)rr * pitch, pitch, x, best - dd));
 }
 
+template <bool NC = true>
 __device__ __forceinline__ bool
-dt_band_prunable(const uint32_t * __restrict__ bandInfo, int band, int x, int dd, int best)
+dt_band_prunable(const uint32_t * bandInfo, int band, int x, int dd, int best)
 {
-  const uint32_t info = __ldg(bandInfo + band);
+  const uint32_t info = dt_ld<NC>(bandInfo + band);
   if (!info)
     return true;
   const int a = info & 0x1FFF, b = (info >> 13) & 0x1FFF;
@@ -62,9 +73,9 @@ dt_band_prunable(const uint32_t * __restrict__ bandInfo, int band, int x, int dd
   return dd + dx * dx >= best;
 }
 
+template <bool NC = true>
 __device__ __forceinline__ int
-dt_edt_sq(const uint32_t * __restrict__ Xb, const uint32_t * __restrict__ rowInfo, int pitch, int h, int xr0, int xr1, int x, int r,
-          int cap)
+dt_edt_sq(const uint32_t * Xb, const uint32_t * rowInfo, int pitch, int h, int xr0, int xr1, int x, int r, int cap)
 {
   const uint32_t * bandInfo = rowInfo + h;
   int best = cap;
@@ -74,12 +85,12 @@ dt_edt_sq(const uint32_t * __restrict__ Xb, const uint32_t * __restrict__ rowInf
     const int dy = rr - r, dd = dy * dy;
     if (dd >= best)
       break;
-    if ((rr & 7) == 0 && dt_band_prunable(bandInfo, rr >> 3, x, dd, best))
+    if ((rr & 7) == 0 && dt_band_prunable<NC>(bandInfo, rr >> 3, x, dd, best))
     {
       rr += 8;
       continue;
     }
-    best = dt_probe_row(Xb, rowInfo, pitch, x, rr, dd, best);
+    best = dt_probe_row<NC>(Xb, rowInfo, pitch, x, rr, dd, best);
     ++rr;
   }
   // rows above r
@@ -88,12 +99,12 @@ dt_edt_sq(const uint32_t * __restrict__ Xb, const uint32_t * __restrict__ rowInf
     const int dy = r - rr, dd = dy * dy;
     if (dd >= best)
       break;
-    if ((rr & 7) == 7 && dt_band_prunable(bandInfo, rr >> 3, x, dd, best))
+    if ((rr & 7) == 7 && dt_band_prunable<NC>(bandInfo, rr >> 3, x, dd, best))
     {
       rr -= 8;
       continue;
     }
-    best = dt_probe_row(Xb, rowInfo, pitch, x, rr, dd, best);
+    best = dt_probe_row<NC>(Xb, rowInfo, pitch, x, rr, dd, best);
     --rr;
   }
   return best;
@@ -1363,6 +1374,850 @@ launch_apply_axis0(Launch & L, int ptype, const Axis0Group * groups, int ngroups
 }
 
 // ---------------------------------------------------------------------------------------------------
+// ===================================================================================================
+// k_dt_tree: every Interpolate1to1 call of every recursion tree (X:556-793, FindMedianImageDistances X:405-516) in ONE
+// persistent launch instead of six grid-wide launches per level.  A CTA processes one node from start to end -- prep,
+// d2 histograms, scan, median, mid shape, volume write -- and then publishes the node's children (X:766-792) on a
+// global ready queue, from which idle CTAs take them: no level barrier anywhere, a tree is as deep as its longest
+// path and the GPU stays full whatever the mix of gaps.  The node's bit rows (intersection | i | i xor j -> median)
+// and row extents live in shared memory when they fit (else in this CTA's slice of global scratch), the two
+// histograms always do.  Mid shapes go to the arena as before; a child may run on another SM, so the parent fences
+// after storing its shape and before publishing, and shapes are read with L2-only loads (a 128-byte L1 line can hold
+// words of a neighbouring shape that was not written yet when the line was first fetched).  Everything downstream
+// (emit records, axis-0 slot table, multi-GPU replay) is unchanged.
+// Queue: slots [0, nRoots) are the root nodes (ready from the start); children go to slot nRoots + atomicAdd(tail).
+// A CTA claims slot atomicAdd(head) and, if the slot has not been produced yet, waits for its flag -- or for the end:
+// `pushed` counts published children, `done` finished nodes; all work is over when done == nRoots + pushed (read
+// `done` first: a node publishes its children before it counts as done).
+// ===================================================================================================
+// 32 bits of row y of a shape starting at slice column X, read from L2 (see k_dt_tree: shapes written by other SMs)
+__device__ __forceinline__ uint32_t
+mask_word_cg(const uint32_t * data, const MaskRef & m, int y, int X)
+{
+  int ry = y - m.y0;
+  if ((unsigned)ry >= (unsigned)m.h)
+    return 0u;
+  int rx = X - m.x0;
+  int wi = rx >> 5;
+  int sh = rx & 31;
+  const uint32_t * row = data + (size_t)ry * m.pitch;
+  uint32_t lo = ((unsigned)wi < (unsigned)m.pitch) ? __ldcg(row + wi) : 0u;
+  uint32_t hi = ((unsigned)(wi + 1) < (unsigned)m.pitch) ? __ldcg(row + wi + 1) : 0u;
+  return __funnelshift_r(lo, hi, sh);
+}
+
+#define TREE_THREADS 512
+#define TREE_WARPS (TREE_THREADS / 32)
+#define TREE_NODE_WORDS 12288 // shared-memory budget (words) for one node's rows: 3 * words + h + (h + 7) / 8
+#define TREE_HWORDS 8         // words per warp visit in the histogram phase (pixels are dealt one per lane)
+
+__device__ __forceinline__ int
+tree_get_big(int * sBig, int * bigCount, int nbig, int * err)
+{
+  int bi = atomicAdd(sBig, 0);
+  if (bi >= 0)
+    return bi;
+  if (bi == -1 && atomicCAS(sBig, -1, -2) == -1)
+  {
+    int v = atomicAdd(bigCount, 1);
+    if (v >= nbig)
+    {
+      atomicMax(err, ERR_SCRATCH);
+      v = nbig - 1;
+    }
+    __threadfence_block();
+    atomicExch(sBig, v);
+    return v;
+  }
+  do
+  {
+    bi = atomicAdd(sBig, 0); // another warp of this CTA is between its CAS and its exchange
+  } while (bi < 0);
+  return bi;
+}
+
+
+template <typename T>
+__global__ void __launch_bounds__(TREE_THREADS, 2)
+k_dt_tree(const TreeParams P)
+{
+  pdl_wait();
+  extern __shared__ uint32_t tsm[];
+  __shared__ __align__(16) Node s_child[2];
+  __shared__ __align__(16) Node s_nd;
+  __shared__ MaskRef s_M;
+  __shared__ int s_nchild, s_slot, s_r0, s_r1, s_big, s_thr, s_alive, s_bx0, s_bx1, s_by0, s_by1, s_maxBin;
+  __shared__ long long redA[TREE_WARPS], redB[TREE_WARPS], bestD[TREE_WARPS];
+  __shared__ int bestI[TREE_WARPS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int histSide = P.histSide, smallWords = histSide / 32;
+  unsigned * hs = tsm;                       // [2 * histSide] counts of both sides
+  unsigned * hsBm = hs + 2 * histSide;       // [histSide / 32] bitmap of touched bins
+  uint32_t * nodeSm = hsBm + smallWords;     // [TREE_NODE_WORDS]
+  uint32_t * nodeGl = P.scratch + (size_t)blockIdx.x * P.scratchPerCta;
+  const T * in = (const T *)P.in;
+  T * out = (T *)P.out;
+  const int nRoots = *P.rootCount;
+#ifdef MCI_TREE_PROFILE
+  long long phT[7] = { 0, 0, 0, 0, 0, 0, 0 }, phLast = clock64();
+  int phCur = 6;
+#define PH(k)                                                                                                                   \
+  do                                                                                                                            \
+  {                                                                                                                             \
+    const long long now_ = clock64();                                                                                           \
+    phT[phCur] += now_ - phLast;                                                                                                \
+    phLast = now_;                                                                                                              \
+    phCur = k;                                                                                                                  \
+  } while (0)
+#else
+#define PH(k) (void)0
+#endif
+  for (int k = tid; k < 2 * histSide + smallWords; k += TREE_THREADS)
+    hs[k] = 0u;
+  if (tid == 0)
+    s_big = -1;
+  __syncthreads();
+  volatile int * vflags = P.flags;
+  volatile int * vctr = P.rootNext;
+  for (;;)
+  {
+    {
+      __syncthreads();
+      if (tid == 0)
+      {
+        // claim a slot; wait until it has been produced, or until no work is left anywhere
+        const int slot = atomicAdd(P.rootNext, 1);
+        int got = slot < nRoots ? 1 : 0;
+        while (!got)
+        {
+          if (slot - nRoots < P.queueCap && vflags[slot - nRoots])
+          {
+            got = 1;
+            break;
+          }
+          const int d = vctr[4];
+          __threadfence();
+          const int pu = vctr[3];
+          if (d == nRoots + pu)
+            break;
+          __nanosleep(200);
+        }
+        if (got)
+        {
+          __threadfence();
+          const int4 * src = reinterpret_cast<const int4 *>(P.roots + slot);
+          int4 * dst = reinterpret_cast<int4 *>(&s_nd);
+#pragma unroll
+          for (int k = 0; k < (int)(sizeof(Node) / 16); ++k)
+            dst[k] = __ldcg(src + k);
+        }
+        s_slot = got ? slot : -1;
+        s_nchild = 0;
+        s_r0 = 0x7FFFFFFF;
+        s_r1 = -1;
+        s_bx0 = s_by0 = 0x7FFFFFFF;
+        s_bx1 = s_by1 = -0x7FFFFFFF;
+      }
+      __syncthreads();
+      if (s_slot < 0)
+        break;
+    }
+    do
+    {
+      const Node nd = s_nd;
+      PH(0);
+      // ---- prep: translation halving with carry, union region, translate + binarise + AND (X:570-666)
+      int t[2] = { nd.tx, nd.ty }, iT[2], jT[2];
+      bool carry = false;
+#pragma unroll
+      for (int d = 0; d < 2; ++d)
+      {
+        if (!carry)
+        {
+          iT[d] = t[d] / 2;
+          carry = (t[d] % 2) != 0;
+        }
+        else if (t[d] % 2 == 0)
+          iT[d] = t[d] / 2;
+        else
+        {
+          iT[d] = t[d] > 0 ? t[d] / 2 + 1 : t[d] / 2 - 1;
+          carry = false;
+        }
+        jT[d] = iT[d] - t[d];
+      }
+      const int mid = (nd.i + nd.j + (carry ? 1 : 0)) / 2;
+      const int ux0 = min(nd.A.x0 + iT[0], nd.B.x0 + jT[0]), uy0 = min(nd.A.y0 + iT[1], nd.B.y0 + jT[1]);
+      const int ux1 = max(nd.A.x0 + nd.A.w + iT[0], nd.B.x0 + nd.B.w + jT[0]);
+      const int uy1 = max(nd.A.y0 + nd.A.h + iT[1], nd.B.y0 + nd.B.h + jT[1]);
+      const int w = ux1 - ux0, h = uy1 - uy0;
+      const int pitch = (w + 31) >> 5;
+      const int words = h * pitch;
+      const unsigned long long need = 3ull * (unsigned long long)words + (unsigned long long)h + (unsigned long long)((h + 7) / 8);
+      if (need > P.scratchPerCta || w > 8191)
+      {
+        if (tid == 0)
+          atomicMax(P.err, ERR_SCRATCH);
+        break;
+      }
+      uint32_t * Xb = need <= TREE_NODE_WORDS ? nodeSm : nodeGl;
+      uint32_t * Ib = Xb + words;
+      uint32_t * Sb = Ib + words;
+      uint32_t * rowInfo = Sb + words;
+      const uint32_t * dataA = P.arena + nd.A.off;
+      const uint32_t * dataB = P.arena + nd.B.off;
+      {
+        const int GW = pitch <= 1 ? 1 : (pitch <= 2 ? 2 : (pitch <= 4 ? 4 : (pitch <= 8 ? 8 : (pitch <= 16 ? 16 : 32))));
+        const int RPW = 32 / GW, sub = lane / GW, sl = lane - sub * GW;
+        int r0 = 0x7FFFFFFF, r1 = -1;
+        for (int rb = warp * RPW; rb < h; rb += TREE_WARPS * RPW)
+        {
+          const int r = rb + sub;
+          const bool rowOk = r < h;
+          const int y = uy0 + r;
+          int first = 0x7FFFFFFF, last = -1, runs = 0;
+          uint32_t prevTop = 0;
+          for (int wb = 0; wb < pitch; wb += GW)
+          {
+            const int wi = wb + sl;
+            uint32_t a = 0, b = 0;
+            if (rowOk && wi < pitch)
+            {
+              const int x = ux0 + 32 * wi;
+              a = mask_word_cg(dataA, nd.A, y - iT[1], x - iT[0]);
+              b = mask_word_cg(dataB, nd.B, y - jT[1], x - jT[0]);
+              const size_t idx = (size_t)r * pitch + wi;
+              Xb[idx] = a & b;
+              Ib[idx] = a;
+              Sb[idx] = a ^ b;
+            }
+            const uint32_t xw = a & b;
+            uint32_t below = __shfl_up_sync(0xFFFFFFFFu, xw, 1, GW);
+            if (sl == 0)
+              below = prevTop;
+            const uint32_t starts = xw & ~((xw << 1) | (below >> 31));
+            runs += __popc(starts);
+            if (xw)
+            {
+              first = min(first, 32 * wi + __ffs(xw) - 1);
+              last = max(last, 32 * wi + 31 - __clz(xw));
+            }
+            prevTop = __shfl_sync(0xFFFFFFFFu, xw, GW - 1, GW);
+          }
+          for (int o = GW >> 1; o > 0; o >>= 1)
+          {
+            first = min(first, __shfl_xor_sync(0xFFFFFFFFu, first, o));
+            last = max(last, __shfl_xor_sync(0xFFFFFFFFu, last, o));
+            runs += __shfl_xor_sync(0xFFFFFFFFu, runs, o);
+          }
+          if (sl == 0 && rowOk)
+          {
+            rowInfo[r] = last >= 0 ? pack_row(first, last, runs == 1) : 0u;
+            if (last >= 0)
+            {
+              r0 = min(r0, r);
+              r1 = max(r1, r);
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+          r0 = min(r0, __shfl_xor_sync(0xFFFFFFFFu, r0, o));
+          r1 = max(r1, __shfl_xor_sync(0xFFFFFFFFu, r1, o));
+        }
+        if (lane == 0 && r1 >= 0)
+        {
+          atomicMin(&s_r0, r0);
+          atomicMax(&s_r1, r1);
+        }
+      }
+      __syncthreads();
+      for (int bnd = tid; bnd < (h + 7) / 8; bnd += TREE_THREADS)
+      {
+        int a = 0x7FFFFFFF, b = -1;
+        for (int q = 0; q < 8 && bnd * 8 + q < h; ++q)
+        {
+          const uint32_t info = rowInfo[bnd * 8 + q];
+          if (info)
+          {
+            a = min(a, (int)(info & 0x1FFF));
+            b = max(b, (int)((info >> 13) & 0x1FFF));
+          }
+        }
+        rowInfo[h + bnd] = b >= 0 ? pack_row(a, b, false) : 0u;
+      }
+      const int xr0 = s_r0, xr1 = s_r1;
+      __syncthreads();
+      if (xr1 < 0)
+        break; // empty intersection: both median finders give an empty image
+      PH(1);
+      // ---- histograms of bin = PixelType(10 * sqrtf(d2)) over the (i xor j) pixels, per side (X:413-459)
+      for (int wBeg = warp * TREE_HWORDS; wBeg < words; wBeg += TREE_WARPS * TREE_HWORDS)
+      {
+        const int myIdx = wBeg + lane;
+        const bool mine = lane < TREE_HWORDS && myIdx < words;
+        const uint32_t myS = mine ? Sb[myIdx] : 0u;
+        const uint32_t myI = mine ? Ib[myIdx] : 0u;
+        int incl = __popc(myS);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+          int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+          if (lane >= o)
+            incl += v;
+        }
+        const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        for (int base = 0; base < total; base += 32)
+        {
+          const int p = base + lane;
+          const bool on = p < total;
+          int src, bit;
+          warp_pixel(myS, incl, on ? p : total - 1, src, bit);
+          const uint32_t iw = __shfl_sync(0xFFFFFFFFu, myI, src);
+          int d2 = 0, side = 0;
+          bool over = false;
+          if (on)
+          {
+            const int idx = wBeg + src;
+            const int r = idx / pitch, wi = idx - r * pitch;
+            d2 = dt_edt_sq<false>(Xb, rowInfo, pitch, h, xr0, xr1, wi * 32 + bit, r, 0x7FFFFFFF);
+            side = (iw >> bit) & 1u ? 0 : 1;
+            const int direct = dt_bin<T>(d2, P.err);
+            if (direct < histSide)
+            {
+              atomicAdd(&hs[side * histSide + direct], 1u);
+              atomicOr(&hsBm[direct >> 5], 1u << (direct & 31));
+            }
+            else
+              over = true;
+          }
+          const unsigned needBig = __ballot_sync(0xFFFFFFFFu, over);
+          if (needBig)
+          {
+            const int leader = __ffs(needBig) - 1;
+            int bi = 0;
+            if (lane == leader)
+              bi = tree_get_big(&s_big, P.bigCount, P.nbig, P.err);
+            bi = __shfl_sync(0xFFFFFFFFu, bi, leader);
+            if (over)
+            {
+              const int bin = dt_bin<T>(d2, P.err);
+              unsigned * bh = P.bigHist + (size_t)bi * DT_BIG_STRIDE;
+              atomicAdd(&bh[side * 65536 + bin], 1u);
+              atomicOr(&bh[2 * 65536 + (bin >> 5)], 1u << (bin & 31));
+            }
+          }
+        }
+      }
+      __syncthreads();
+      PH(2);
+      // ---- scan: first bin minimising the score (X:461-494), threshold on d2 (X:497-508)
+      {
+        // a wrapped-bin table is in use for this node iff some bin reached it; the CTA keeps its table for later nodes,
+        // so "in use" is decided by its bitmap: any touched bin
+        unsigned * bh = s_big >= 0 ? P.bigHist + (size_t)s_big * DT_BIG_STRIDE : nullptr;
+        int anyBig = 0;
+        if (bh)
+        {
+          for (int k = tid; k < 2048; k += TREE_THREADS)
+            anyBig |= bh[2 * 65536 + k] != 0u;
+        }
+        const bool big = __syncthreads_or(anyBig) != 0;
+        unsigned * cntI = hs;
+        unsigned * cntJ = hs + histSide;
+        unsigned * bm = hsBm;
+        if (big)
+        {
+          unsigned * bbm = bh + 2 * 65536;
+          for (int wI = tid; wI < smallWords; wI += TREE_THREADS)
+          {
+            unsigned bits = hsBm[wI];
+            if (!bits)
+              continue;
+            hsBm[wI] = 0u;
+            while (bits)
+            {
+              int b = __ffs(bits) - 1;
+              bits &= bits - 1;
+              const int k = wI * 32 + b;
+              atomicAdd(&bh[k], hs[k]);
+              atomicAdd(&bh[65536 + k], hs[histSide + k]);
+              atomicOr(&bbm[k >> 5], 1u << (k & 31));
+              hs[k] = 0u;
+              hs[histSide + k] = 0u;
+            }
+          }
+          __syncthreads();
+          cntI = bh;
+          cntJ = bh + 65536;
+          bm = bbm;
+        }
+        // bins are dealt to the threads in contiguous ranges up to the highest touched bin (thread order = bin order).
+        // Untouched bins inside a range repeat the score of the bin before them and lose every tie, so visiting
+        // them is exact; bin 0 is visited by thread 0 whether touched or not (bestDiff starts at LLONG_MAX, X:482-494)
+        const int nWords = big ? 2048 : smallWords;
+        if (tid == 0)
+          s_maxBin = -1;
+        __syncthreads();
+        for (int wI = tid; wI < nWords; wI += TREE_THREADS)
+        {
+          const unsigned bits = bm[wI];
+          if (bits)
+          {
+            atomicMax(&s_maxBin, wI * 32 + 31 - __clz(bits));
+            bm[wI] = 0u; // leave the tables clean for the next node
+          }
+        }
+        __syncthreads();
+        const int nb = s_maxBin + 1;
+        const int per = (nb + TREE_THREADS - 1) / TREE_THREADS;
+        const int k0 = min(nb, tid * per), k1 = min(nb, k0 + per);
+        long long li = 0, lj = 0;
+        for (int k = k0; k < k1; ++k)
+        {
+          li += cntI[k];
+          lj += cntJ[k];
+        }
+        long long sa = li, sb = lj;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+          long long ta = __shfl_up_sync(0xFFFFFFFFu, sa, o), tb = __shfl_up_sync(0xFFFFFFFFu, sb, o);
+          if (lane >= o)
+          {
+            sa += ta;
+            sb += tb;
+          }
+        }
+        if (lane == 31)
+        {
+          redA[warp] = sa;
+          redB[warp] = sb;
+        }
+        __syncthreads();
+        long long oa = 0, ob = 0, iTot = 0, jTot = 0;
+        for (int k = 0; k < TREE_WARPS; ++k)
+        {
+          if (k < warp)
+          {
+            oa += redA[k];
+            ob += redB[k];
+          }
+          iTot += redA[k];
+          jTot += redB[k];
+        }
+        int thr = -1; // -1: no pixel outside the intersection, the median is the intersection (X:463-466)
+        if (iTot + jTot > 0) // block-uniform
+        {
+          long long si = oa + sa - li, sj = ob + sb - lj;
+          long long bd = 0x7FFFFFFFFFFFFFFFll;
+          int bidx = 0x7FFFFFFF;
+          for (int k = k0; k < k1; ++k)
+          {
+            si += cntI[k];
+            sj += cntJ[k];
+            const long long d = llabs(llabs(iTot - si + sj) - llabs(jTot - sj + si));
+            if (d < bd)
+            {
+              bd = d;
+              bidx = k;
+            }
+            cntI[k] = 0u;
+            cntJ[k] = 0u;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+          {
+            long long od = __shfl_xor_sync(0xFFFFFFFFu, bd, o);
+            int oi = __shfl_xor_sync(0xFFFFFFFFu, bidx, o);
+            if (od < bd || (od == bd && oi < bidx))
+            {
+              bd = od;
+              bidx = oi;
+            }
+          }
+          if (lane == 0)
+          {
+            bestD[warp] = bd;
+            bestI[warp] = bidx;
+          }
+          __syncthreads();
+          bd = bestD[0];
+          bidx = bestI[0];
+          for (int k = 1; k < TREE_WARPS; ++k)
+            if (bestD[k] < bd || (bestD[k] == bd && bestI[k] < bidx))
+            {
+              bd = bestD[k];
+              bidx = bestI[k];
+            }
+          thr = dt_threshold_d2(bidx);
+        }
+        if (tid == 0)
+          s_thr = thr;
+      }
+      __syncthreads();
+      PH(3);
+      // ---- median = intersection | (xor pixels with d2 <= threshold); bounding box inside the slice (X:497-515, 679-712)
+      {
+        const int thr = s_thr;
+        const int axis = nd.axis;
+        const int SU = (int)(axis == 0 ? P.VY : P.VX), SV = (int)(axis == 2 ? P.VY : P.VZ);
+        int bx0 = 0x7FFFFFFF, bx1 = -0x7FFFFFFF, by0 = 0x7FFFFFFF, by1 = -0x7FFFFFFF;
+        for (int myIdx = tid; myIdx < words; myIdx += TREE_THREADS)
+        {
+          const uint32_t myS = Sb[myIdx];
+          uint32_t m = Xb[myIdx];
+          const int r = myIdx / pitch, wi = myIdx - r * pitch;
+          if (thr >= 0 && myS)
+          {
+            const int x0 = wi * 32;
+            uint32_t pass = 0;
+            int R = (int)sqrtf((float)thr) + 1;
+            for (int k = 0; k * k <= thr; ++k)
+            {
+              while (R * R + k * k > thr)
+                --R;
+#pragma unroll
+              for (int sgn = 0; sgn < 2; ++sgn)
+              {
+                if (sgn && k == 0)
+                  continue;
+                const int rr = sgn ? r + k : r - k;
+                if (rr < xr0 || rr > xr1)
+                  continue;
+                const uint32_t info = rowInfo[rr];
+                if (!info)
+                  continue;
+                const int a = info & 0x1FFF, b = (info >> 13) & 0x1FFF;
+                if (a - R > x0 + 31 || b + R < x0)
+                  continue;
+                if ((info >> 26) & 1u)
+                  pass |= bit_range(max(a - R, x0) - x0, min(b + R, x0 + 31) - x0);
+                else
+                {
+                  const uint32_t * row = Xb + (size_t)rr * pitch;
+                  const int wlo = max(0, (x0 - R) >> 5), whi = min(pitch - 1, (x0 + 31 + R) >> 5);
+                  for (int ws = wlo; ws <= whi; ++ws)
+                  {
+                    uint32_t wv = row[ws];
+                    while (wv)
+                    {
+                      const int sbit = __ffs(wv) - 1;
+                      const uint32_t tt = ~(wv >> sbit);
+                      const int len = tt ? __ffs(tt) - 1 : 32 - sbit;
+                      const int lo = ws * 32 + sbit - R, hi = ws * 32 + sbit + len - 1 + R;
+                      if (hi >= x0 && lo <= x0 + 31)
+                        pass |= bit_range(max(lo, x0) - x0, min(hi, x0 + 31) - x0);
+                      wv = (len >= 32) ? 0u : (wv & ~(((1u << len) - 1u) << sbit));
+                    }
+                  }
+                }
+              }
+              if ((pass & myS) == myS)
+                break;
+            }
+            m |= pass & myS;
+          }
+          Ib[myIdx] = m; // the median rows take the place of the i rows (the xor rows are still being read by others)
+          const int y = uy0 + r;
+          if (m && y >= 0 && y < SV)
+          {
+            const int xa = ux0 + 32 * wi;
+            uint32_t c = m;
+            if (xa < 0)
+              c = (xa <= -32) ? 0u : (c & (0xFFFFFFFFu << (-xa)));
+            if (xa + 32 > SU)
+              c = (xa >= SU) ? 0u : (c & (0xFFFFFFFFu >> (xa + 32 - SU)));
+            if (c)
+            {
+              bx0 = min(bx0, xa + __ffs(c) - 1);
+              bx1 = max(bx1, xa + 31 - __clz(c));
+              by0 = min(by0, y);
+              by1 = max(by1, y);
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+          bx0 = min(bx0, __shfl_xor_sync(0xFFFFFFFFu, bx0, o));
+          by0 = min(by0, __shfl_xor_sync(0xFFFFFFFFu, by0, o));
+          bx1 = max(bx1, __shfl_xor_sync(0xFFFFFFFFu, bx1, o));
+          by1 = max(by1, __shfl_xor_sync(0xFFFFFFFFu, by1, o));
+        }
+        if (lane == 0 && by1 >= by0)
+        {
+          atomicMin(&s_bx0, bx0);
+          atomicMax(&s_bx1, bx1);
+          atomicMin(&s_by0, by0);
+          atomicMax(&s_by1, by1);
+        }
+      }
+      __syncthreads();
+      PH(4);
+      // ---- mid shape: allocate, record, spawn the children (X:714-729, 766-792)
+      if (tid == 0)
+      {
+        s_alive = 0;
+        if (s_by1 >= s_by0)
+        {
+          MaskRef M;
+          M.x0 = s_bx0;
+          M.y0 = s_by0;
+          M.w = s_bx1 - s_bx0 + 1;
+          M.h = s_by1 - s_by0 + 1;
+          M.pitch = (M.w + 31) >> 5;
+          M.pad = 0;
+          const int mwords = M.h * M.pitch;
+          M.off = atomicAdd(P.arenaTop, (unsigned long long)mwords);
+          if (M.off + (unsigned long long)mwords > P.arenaCap)
+            atomicMax(P.err, ERR_ARENA);
+          else
+          {
+            s_alive = 1;
+            s_M = M;
+            if (P.emit)
+            {
+              const int e = atomicAdd(P.emitCount, 1);
+              if (e < P.emitCap)
+              {
+                EmitRec rec;
+                rec.M = M;
+                rec.M.off = M.off - P.emitBase;
+                rec.axis = nd.axis;
+                rec.label = nd.label;
+                rec.mid = mid;
+                rec.pad = 0;
+                P.emit[e] = rec;
+                if (nd.slot0 >= 0)
+                  emit_slot_table(P.emit, P.emitCap)[nd.slot0 + mid - nd.lo - 1] = e;
+              }
+              else
+                atomicMax(P.err, ERR_NODE_LIST);
+            }
+            if (abs(nd.i - nd.j) > 2)
+            {
+              const bool first = abs(nd.i - mid) > 1, second = abs(nd.j - mid) > 1;
+              {
+                if (second)
+                {
+                  Node c;
+                  c.A = nd.B;
+                  c.B = M;
+                  c.tx = jT[0];
+                  c.ty = jT[1];
+                  c.i = nd.j;
+                  c.j = mid;
+                  c.axis = nd.axis;
+                  c.label = nd.label;
+                  c.slot0 = nd.slot0;
+                  c.lo = nd.lo;
+                  s_child[s_nchild++] = c;
+                }
+                if (first)
+                {
+                  Node c;
+                  c.A = nd.A;
+                  c.B = M;
+                  c.tx = iT[0];
+                  c.ty = iT[1];
+                  c.i = nd.i;
+                  c.j = mid;
+                  c.axis = nd.axis;
+                  c.label = nd.label;
+                  c.slot0 = nd.slot0;
+                  c.lo = nd.lo;
+                  s_child[s_nchild++] = c;
+                }
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();
+      if (!s_alive)
+        break;
+      PH(5);
+      // ---- store the mid shape and write it into the volume with the max rule (X:743-764)
+      {
+        constexpr int VPQ = 8 / sizeof(T);
+        constexpr int GPW = 32 / VPQ + 1;
+        const MaskRef M = s_M;
+        const int axis = nd.axis;
+        const T label = (T)nd.label;
+        const unsigned long long nvox = (unsigned long long)P.VX * P.VY * P.VZ;
+        long long su, sv;
+        unsigned long long vbase;
+        if (axis == 2)
+        {
+          su = 1;
+          sv = P.VX;
+          vbase = (unsigned long long)mid * P.VX * P.VY;
+        }
+        else if (axis == 1)
+        {
+          su = 1;
+          sv = P.VX * P.VY;
+          vbase = (unsigned long long)mid * P.VX;
+        }
+        else
+        {
+          su = P.VX;
+          sv = P.VX * P.VY;
+          vbase = (unsigned long long)mid;
+        }
+        const int mwords = M.h * M.pitch;
+        for (int wBeg = warp * 32; wBeg < mwords; wBeg += TREE_WARPS * 32)
+        {
+          const int wEnd = min(mwords, wBeg + 32);
+          uint32_t myM = 0;
+          {
+            const int cell = wBeg + lane;
+            if (cell < wEnd)
+            {
+              const int r = cell / M.pitch, wi = cell - r * M.pitch;
+              const int y = M.y0 + r, x = M.x0 + 32 * wi;
+              const uint32_t * row = Ib + (size_t)(y - uy0) * pitch;
+              const int rx = x - ux0; // >= 0
+              const int sw = rx >> 5, shf = rx & 31;
+              const uint32_t lo = row[sw];
+              const uint32_t hi = sw + 1 < pitch ? row[sw + 1] : 0u;
+              myM = __funnelshift_r(lo, hi, shf);
+              const int valid = M.w - 32 * wi;
+              if (valid < 32)
+                myM &= (1u << valid) - 1u;
+              P.arena[M.off + cell] = myM;
+            }
+          }
+          if (su == 1)
+          {
+            // x runs along the bits: aligned 8-byte groups; each lane keeps EMU groups in flight (loads first, then
+            // the compare-and-swaps), the latency of a group's read-modify-write being what this phase costs
+            constexpr int EMU = 3;
+            const int nTasks = (wEnd - wBeg) * GPW;
+            for (int tb = 0; tb < nTasks; tb += 32 * EMU)
+            {
+              unsigned long long g[EMU], qin[EMU], qout[EMU];
+              unsigned bits[EMU];
+#pragma unroll
+              for (int u = 0; u < EMU; ++u)
+              {
+                const int task = tb + u * 32 + lane;
+                const int c = min(task / GPW, wEnd - wBeg - 1), q = task % GPW;
+                const uint32_t m = __shfl_sync(0xFFFFFFFFu, myM, c);
+                bits[u] = 0u;
+                g[u] = 0ull;
+                if (task < nTasks && m)
+                {
+                  const int cell = wBeg + c;
+                  const int r = cell / M.pitch, wi = cell - r * M.pitch;
+                  const unsigned long long a0 = vbase + (unsigned long long)((long long)(M.x0 + 32 * wi) + (long long)(M.y0 + r) * sv);
+                  g[u] = (a0 & ~(unsigned long long)(VPQ - 1)) + (unsigned long long)q * VPQ;
+                  const long long sh = (long long)g[u] - (long long)a0; // in (-VPQ, 32]
+                  if (sh >= 32)
+                    bits[u] = 0u;
+                  else if (sh >= 0)
+                    bits[u] = (m >> sh) & ((1u << VPQ) - 1u);
+                  else
+                    bits[u] = (m << (-sh)) & ((1u << VPQ) - 1u);
+                  if (bits[u] && g[u] + VPQ > nvox)
+                  {
+                    for (int k = 0; k < VPQ; ++k) // last, partial group of the volume
+                      if (((bits[u] >> k) & 1u) && g[u] + k < nvox && in[g[u] + k] == 0)
+                        atomic_max_pixel(out + g[u] + k, label);
+                    bits[u] = 0u;
+                  }
+                }
+                if (bits[u])
+                {
+                  qin[u] = __ldg(reinterpret_cast<const unsigned long long *>(in + g[u]));
+                  qout[u] = *reinterpret_cast<const volatile unsigned long long *>(out + g[u]);
+                }
+              }
+#pragma unroll
+              for (int u = 0; u < EMU; ++u)
+                if (bits[u])
+                  write_group_loaded<T>(out, g[u], bits[u], label, qin[u], qout[u]);
+            }
+          }
+          else if (nd.slot0 < 0) // registered axis-0 trees are written x-run by x-run afterwards (k_apply_axis0)
+          {
+            for (int c = 0; c < wEnd - wBeg; ++c)
+            {
+              const uint32_t m = __shfl_sync(0xFFFFFFFFu, myM, c);
+              if ((m >> lane) & 1u)
+              {
+                const int cell = wBeg + c;
+                const int r = cell / M.pitch, wi = cell - r * M.pitch;
+                const unsigned long long a =
+                  vbase + (unsigned long long)((long long)(M.x0 + 32 * wi + lane) * su + (long long)(M.y0 + r) * sv);
+                if (in[a] == 0)
+                  atomic_max_pixel(out + a, label);
+              }
+            }
+          }
+        }
+      }
+    } while (0);
+    PH(6);
+    // node finished: every thread fences its arena stores, then one thread publishes the children and counts the
+    // node as done (children first: see the termination test above)
+    __threadfence();
+    __syncthreads();
+    if (tid == 0)
+    {
+      const int n = s_nchild;
+      if (n)
+      {
+        const int base = atomicAdd(P.rootNext + 2, n);
+        if (base + n > P.queueCap)
+          atomicMax(P.err, ERR_NODE_LIST);
+        else
+        {
+          for (int k = 0; k < n; ++k)
+            P.roots[nRoots + base + k] = s_child[k];
+          __threadfence();
+          for (int k = 0; k < n; ++k)
+            vflags[base + k] = 1;
+          atomicAdd(P.rootNext + 3, n);
+        }
+      }
+      __threadfence();
+      atomicAdd(P.rootNext + 4, 1);
+    }
+  }
+#ifdef MCI_TREE_PROFILE
+  if (tid == 0)
+    for (int k = 0; k < 7; ++k)
+      atomicAdd((unsigned long long *)(P.scratch + (size_t)gridDim.x * P.scratchPerCta) + k, (unsigned long long)phT[k]);
+#endif
+}
+
+void
+launch_dt_tree(Launch & L, int ptype, const TreeParams & P, int nRootsMax, int grid)
+{
+  if (nRootsMax <= 0)
+    return;
+  const int smem = (2 * P.histSide + P.histSide / 32 + TREE_NODE_WORDS) * 4;
+  L.pre("k_dt_tree");
+  switch (ptype)
+  {
+    case MCI_U8:
+      L.ensure_max_smem(k_dt_tree<uint8_t>, 8, smem);
+      launch_pdl(k_dt_tree<uint8_t>, grid, TREE_THREADS, smem, L.stream, P);
+      break;
+    case MCI_U16:
+      L.ensure_max_smem(k_dt_tree<uint16_t>, 9, smem);
+      launch_pdl(k_dt_tree<uint16_t>, grid, TREE_THREADS, smem, L.stream, P);
+      break;
+    default:
+      L.ensure_max_smem(k_dt_tree<int16_t>, 10, smem);
+      launch_pdl(k_dt_tree<int16_t>, grid, TREE_THREADS, smem, L.stream, P);
+  }
+  L.post("k_dt_tree");
+}
+
 void
 launch_dt_level(Launch & L, int ptype, const DtLevel & lv)
 {

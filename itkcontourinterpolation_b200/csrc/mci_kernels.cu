@@ -776,10 +776,16 @@ align_bfs(const AlignJob & J, const AlignShape & A, const AlignShape * sB, const
       st->done = 0;
     }
     __syncthreads();
+#ifdef MCI_ALIGN_PROFILE
+    long long tScore = 0, tReplay = 0;
+#endif
     for (;;)
     {
       const int from = st->scored, to = st->tail;
       ++nWaves;
+#ifdef MCI_ALIGN_PROFILE
+      const long long c0 = clock64();
+#endif
       if (J.kind == JOB_EXTRAPOLATE)
       {
         // the other shape is the phantom point: score = is the point, moved back by t, inside the shape (X:239-240)
@@ -830,62 +836,162 @@ align_bfs(const AlignJob & J, const AlignShape & A, const AlignShape * sB, const
         }
       }
       __syncthreads();
+#ifdef MCI_ALIGN_PROFILE
+      const long long c1 = clock64();
+      tScore += c1 - c0;
+#endif
       if (warp == 0)
       {
-        // the reference's sequential pop / compare / expand (X:1186-1219), replayed by one warp: all lanes
-        // carry the same state, lanes 0..3 test the four neighbours ("left", "right" per dimension, in order)
+        // The reference's sequential pop / compare / expand (X:1186-1219), replayed by one warp; all lanes carry the
+        // same state.  Up to 32 queue entries are replayed at once, one per lane: the running maximum is a prefix
+        // maximum, a neighbour is new when its bit is clear and no EARLIER entry of the chunk that expands is
+        // adjacent to it (pushes are ordered by entry, then left / right per dimension), and the iteration count
+        // before an entry is a prefix sum of the pushes.  The two `iter <=` tests of X:1198 are taken from the start
+        // of the chunk; iter only grows, so they are checked against the iteration count before the chunk's last
+        // entry, and the (at most two per job) chunks in which one of them flips are replayed entry by entry.
         int head = st->head, tail = to;
         while (head < to)
         {
-          const int tx = qx[head & qmask], ty = qy[head & qmask];
-          const unsigned sc = qs[head & qmask];
-          ++head;
-          if (sc > maxScore)
+          const int n = min(32, to - head);
+          int tx = 0, ty = 0;
+          unsigned sc = 0;
+          if (lane < n)
           {
-            maxScore = sc;
-            bestx = tx;
-            besty = ty;
+            const int sl = (head + lane) & qmask;
+            tx = qx[sl];
+            ty = qy[sl];
+            sc = qs[sl];
           }
-          // `score > maxScore * 0.9` in double (X:1198) == 10*score > 9*maxScore for integer scores below 2^32
-          const bool expand = !heuristic || maxScore == 0 || iter <= J.minIter ||
-                              (10ull * sc > 9ull * maxScore && iter <= J.maxIter);
-          if (expand)
+          unsigned pm = sc;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1)
           {
-            bool isNew = false;
-            int nx = tx, ny = ty;
-            if (lane < 4)
+            const unsigned v = __shfl_up_sync(0xFFFFFFFFu, pm, o);
+            if (lane >= o)
+              pm = max(pm, v);
+          }
+          const unsigned m = max(maxScore, pm); // maxScore once this entry has been compared (X:1191-1195)
+          const bool okMin = iter <= J.minIter, okMax = iter <= J.maxIter;
+          const bool ex = lane < n && (!heuristic || m == 0 || okMin || (10ull * sc > 9ull * m && okMax));
+          int cx[4], cy[4];
+          bool val[4];
+#pragma unroll
+          for (int nb = 0; nb < 4; ++nb)
+          {
+            cx[nb] = tx + (nb == 0 ? -1 : (nb == 1 ? 1 : 0));
+            cy[nb] = ty + (nb == 2 ? -1 : (nb == 3 ? 1 : 0));
+            const int rx = cx[nb] - J.sx0, ry = cy[nb] - J.sy0;
+            val[nb] = ex && (unsigned)rx < (unsigned)J.sw && (unsigned)ry < (unsigned)J.sh &&
+                      !((bitmap[ry * bpitch + (rx >> 5)] >> (rx & 31)) & 1u);
+          }
+          const unsigned exMask = __ballot_sync(0xFFFFFFFFu, ex);
+          for (int l = 0; l < n - 1; ++l)
+          {
+            const int px = __shfl_sync(0xFFFFFFFFu, tx, l), py = __shfl_sync(0xFFFFFFFFu, ty, l);
+            if (((exMask >> l) & 1u) && l < lane)
             {
-              nx = tx + (lane == 0 ? -1 : (lane == 1 ? 1 : 0));
-              ny = ty + (lane == 2 ? -1 : (lane == 3 ? 1 : 0));
-              const int rx = nx - J.sx0, ry = ny - J.sy0;
-              if ((unsigned)rx < (unsigned)J.sw && (unsigned)ry < (unsigned)J.sh)
-              {
-                const uint32_t bit = 1u << (rx & 31);
-                isNew = !(atomicOr(&bitmap[ry * bpitch + (rx >> 5)], bit) & bit);
-              }
+#pragma unroll
+              for (int nb = 0; nb < 4; ++nb)
+                if (abs(cx[nb] - px) + abs(cy[nb] - py) == 1)
+                  val[nb] = false;
             }
-            const unsigned vote = __ballot_sync(0xFFFFFFFFu, isNew);
-            const int nNew = __popc(vote);
-            if (nNew)
+          }
+          const int cnt = (int)val[0] + (int)val[1] + (int)val[2] + (int)val[3];
+          int incl = cnt;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1)
+          {
+            const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o)
+              incl += v;
+          }
+          const int excl = incl - cnt;
+          const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+          const long long iterLast = iter + __shfl_sync(0xFFFFFFFFu, excl, n - 1);
+          const bool flips = heuristic && (okMin != (iterLast <= J.minIter) || okMax != (iterLast <= J.maxIter));
+          if (!flips && tail + total - head <= J.qcap)
+          {
+            const unsigned cm = __shfl_sync(0xFFFFFFFFu, pm, 31);
+            if (cm > maxScore)
             {
-              if (tail + nNew - head > J.qcap)
+              const int f = __ffs(__ballot_sync(0xFFFFFFFFu, lane < n && sc == cm)) - 1; // first strictly greater
+              bestx = __shfl_sync(0xFFFFFFFFu, tx, f);
+              besty = __shfl_sync(0xFFFFFFFFu, ty, f);
+              maxScore = cm;
+            }
+            int pos = tail + excl;
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb)
+              if (val[nb])
               {
-                if (lane == 0)
-                  atomicMax(err, ERR_QUEUE);
+                const int rx = cx[nb] - J.sx0, ry = cy[nb] - J.sy0;
+                atomicOr(&bitmap[ry * bpitch + (rx >> 5)], 1u << (rx & 31));
+                qx[pos & qmask] = cx[nb];
+                qy[pos & qmask] = cy[nb];
+                qs[pos & qmask] = 0u;
+                ++pos;
               }
-              else
+            tail += total;
+            iter += total;
+            head += n;
+            __syncwarp();
+            continue;
+          }
+          // entry by entry
+          const int stop = head + n;
+          while (head < stop)
+          {
+            const int tx = qx[head & qmask], ty = qy[head & qmask];
+            const unsigned sc = qs[head & qmask];
+            ++head;
+            if (sc > maxScore)
+            {
+              maxScore = sc;
+              bestx = tx;
+              besty = ty;
+            }
+            // `score > maxScore * 0.9` in double (X:1198) == 10*score > 9*maxScore for integer scores below 2^32
+            const bool expand = !heuristic || maxScore == 0 || iter <= J.minIter ||
+                                (10ull * sc > 9ull * maxScore && iter <= J.maxIter);
+            if (expand)
+            {
+              bool isNew = false;
+              int nx = tx, ny = ty;
+              if (lane < 4)
               {
-                if (isNew)
+                nx = tx + (lane == 0 ? -1 : (lane == 1 ? 1 : 0));
+                ny = ty + (lane == 2 ? -1 : (lane == 3 ? 1 : 0));
+                const int rx = nx - J.sx0, ry = ny - J.sy0;
+                if ((unsigned)rx < (unsigned)J.sw && (unsigned)ry < (unsigned)J.sh)
                 {
-                  const int pos = (tail + __popc(vote & ((1u << lane) - 1u))) & qmask;
-                  qx[pos] = nx;
-                  qy[pos] = ny;
-                  qs[pos] = 0u;
+                  const uint32_t bit = 1u << (rx & 31);
+                  isNew = !(atomicOr(&bitmap[ry * bpitch + (rx >> 5)], bit) & bit);
                 }
-                tail += nNew;
               }
-              iter += nNew;
+              const unsigned vote = __ballot_sync(0xFFFFFFFFu, isNew);
+              const int nNew = __popc(vote);
+              if (nNew)
+              {
+                if (tail + nNew - head > J.qcap)
+                {
+                  if (lane == 0)
+                    atomicMax(err, ERR_QUEUE);
+                }
+                else
+                {
+                  if (isNew)
+                  {
+                    const int pos = (tail + __popc(vote & ((1u << lane) - 1u))) & qmask;
+                    qx[pos] = nx;
+                    qy[pos] = ny;
+                    qs[pos] = 0u;
+                  }
+                  tail += nNew;
+                }
+                iter += nNew;
+              }
             }
+            __syncwarp();
           }
         }
         __syncwarp();
@@ -898,9 +1004,15 @@ align_bfs(const AlignJob & J, const AlignShape & A, const AlignShape * sB, const
         }
       }
       __syncthreads();
+#ifdef MCI_ALIGN_PROFILE
+      tReplay += clock64() - c1;
+#endif
       if (st->done)
         break;
     }
+#ifdef MCI_ALIGN_PROFILE
+    nWaves = (int)(tScore >> 4) | ((int)(tReplay >> 4) << 16); // both in units of 16 cycles
+#endif
 }
 
 __global__ void __launch_bounds__(ALIGN_THREADS)

@@ -160,6 +160,34 @@ struct DtLevel
 };
 void launch_dt_level(Launch & L, int ptype, const DtLevel & lv);
 
+// the whole recursion of a root node in one CTA (k_dt_tree, mci_dt.cu)
+struct TreeParams
+{
+  Node * roots;    // node queue: roots first, then room for every child
+  const int * rootCount;
+  int * rootNext;  // [0] head, [1] wrapped-bin tables in use, [2] tail (children), [3] pushed, [4] done; zeroed before the launch
+  int * flags;     // one per child slot: 1 = published (zeroed before the launch)
+  int queueCap;    // child slots
+  uint32_t * arena;
+  unsigned long long * arenaTop;
+  unsigned long long arenaCap;
+  uint32_t * scratch;
+  unsigned long long scratchPerCta; // words
+  int histSide;
+  unsigned * bigHist;
+  int * bigCount;
+  int nbig;
+  EmitRec * emit;
+  int * emitCount;
+  int emitCap;
+  unsigned long long emitBase;
+  const void * in;
+  void * out;
+  long long VX, VY, VZ;
+  int * err;
+};
+void launch_dt_tree(Launch & L, int ptype, const TreeParams & P, int nRootsMax, int grid);
+
 long long median_tile_count(const long long dims[3]);
 void launch_median3d(Launch & L, int ptype, const void * in, void * out, const long long dims[3], int radius, unsigned * summary);
 void launch_combine_max(Launch & L, int ptype, void * dst, const void * src, long long n);

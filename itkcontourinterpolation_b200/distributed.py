@@ -196,40 +196,60 @@ class ShardedInterpolator:
 #      output voxel is produced by exactly one rank.
 # The plan functions are pure (tests/test_distributed_cpu.py drives them, and the table exchange, on gloo).
 # =====================================================================================================================
+LABEL_DT = np.dtype([("label", "<i8"), ("idx", "<i4", (3,)), ("size", "<i4", (3,))])   # mci_label_info
+SLICE_DT = np.dtype([("axis", "<i4"), ("slice", "<i4"), ("label", "<i8")])                # mci_labeled_slice
+
+
 def merge_detection(tables):
     """tables: per rank (labels [n,7] = label, bbox index xyz, bbox size xyz; slices [m,2] = label, z), global
-    coordinates.  Returns (bboxes {label: (lo[3], hi[3])}, slices {label: sorted z list})."""
-    bboxes, slices = {}, {}
-    for labels, sl in tables:
-        for row in np.asarray(labels).reshape(-1, 7).tolist():
-            lab, lo, hi = row[0], row[1:4], [row[1 + a] + row[4 + a] - 1 for a in range(3)]
-            if lab in bboxes:
-                blo, bhi = bboxes[lab]
-                bboxes[lab] = ([min(a, b) for a, b in zip(blo, lo)], [max(a, b) for a, b in zip(bhi, hi)])
-            else:
-                bboxes[lab] = (lo, hi)
-        for lab, z in np.asarray(sl).reshape(-1, 2).tolist():
-            slices.setdefault(lab, set()).add(z)
-    return bboxes, {lab: sorted(zs) for lab, zs in slices.items()}
+    coordinates.  Returns (boxes [L,7] int64: label, lo xyz, hi xyz, sorted by label; slices [S,2] int64: (label, z)
+    rows, unique, sorted by label then z).  Vectorised: C5 has 200 labels x 128 annotated planes."""
+    labs = [np.asarray(t[0], dtype=np.int64).reshape(-1, 7) for t in tables]
+    lab = np.concatenate(labs) if labs else np.zeros((0, 7), np.int64)
+    if len(lab):
+        ids, inv = np.unique(lab[:, 0], return_inverse=True)
+        lo = np.full((len(ids), 3), np.iinfo(np.int64).max)
+        hi = np.full((len(ids), 3), np.iinfo(np.int64).min)
+        np.minimum.at(lo, inv, lab[:, 1:4])
+        np.maximum.at(hi, inv, lab[:, 1:4] + lab[:, 4:7] - 1)
+        boxes = np.concatenate([ids[:, None], lo, hi], axis=1)
+    else:
+        boxes = np.zeros((0, 7), np.int64)
+    sls = [np.asarray(t[1], dtype=np.int64).reshape(-1, 2) for t in tables]
+    sl = np.concatenate(sls) if sls else np.zeros((0, 2), np.int64)
+    if len(sl):
+        sl = np.unique(sl, axis=0)  # lexicographic: by label, then z
+    return boxes, sl
+
+
+def segments_of(slices, label=0):
+    """(i, j) of every segment of InterpolateAlong (X:1492-1519): consecutive annotated planes of one label that are
+    not adjacent.  slices: merge_detection's [S,2] table."""
+    if len(slices) < 2:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
+    same = (slices[1:, 0] == slices[:-1, 0]) & (slices[:-1, 1] + 1 < slices[1:, 1])
+    if label:
+        same &= slices[1:, 0] == label
+    return slices[:-1, 1][same], slices[1:, 1][same]
 
 
 def plan_slab(slices, z0, z1, label=0):
     """Which planes rank [z0, z1) must hold: returns (zlo, zhi, needed) -- the contiguous range covering its slab and
-    both annotated slices of every segment (X:1492-1519: consecutive annotated slices i < j with i + 1 < j) that has a
-    mid slice in the slab, and the sorted annotated planes outside [z0, z1) among them."""
-    zlo, zhi, needed = z0, z1, set()
+    both annotated planes of every segment that has a mid slice in the slab, and the sorted annotated planes outside
+    [z0, z1) among them.  slices: merge_detection's table (or {label: sorted z list})."""
+    if isinstance(slices, dict):
+        rows = [(lab, z) for lab, zs in slices.items() for z in zs]
+        slices = np.unique(np.asarray(rows, dtype=np.int64).reshape(-1, 2), axis=0) if rows else np.zeros((0, 2), np.int64)
     if z1 <= z0:
-        return zlo, zhi, []
-    for lab, zs in slices.items():
-        if label not in (0, lab):
-            continue
-        for i, j in zip(zs[:-1], zs[1:]):
-            if i + 1 < j and max(i + 1, z0) <= min(j - 1, z1 - 1):
-                zlo, zhi = min(zlo, i), max(zhi, j + 1)
-                for z in (i, j):
-                    if not z0 <= z < z1:
-                        needed.add(z)
-    return zlo, zhi, sorted(needed)
+        return z0, z1, []
+    si, sj = segments_of(slices, label)
+    hit = np.maximum(si + 1, z0) <= np.minimum(sj - 1, z1 - 1)
+    if not hit.any():
+        return z0, z1, []
+    si, sj = si[hit], sj[hit]
+    ends = np.unique(np.concatenate([si, sj]))
+    needed = ends[(ends < z0) | (ends >= z1)]
+    return int(min(z0, si.min())), int(max(z1, sj.max() + 1)), [int(z) for z in needed]
 
 
 def exchange_tables(labels, slices, group=None, device="cpu", cap_labels=1024, cap_slices=32768):
@@ -371,23 +391,27 @@ class SlabShardedInterpolator:
 
     def _detect(self):
         """slab + halo planes -> this rank's tables in global coordinates (halo entries dropped)"""
-        ct, L = self.ct, self.L
+        ct = self.ct
         h0, h1 = (1 if self.z0 > 0 else 0), (1 if self.z1 < self.Z else 0)
         if self.z1 <= self.z0:
             return np.zeros((0, 7), np.int32), np.zeros((0, 2), np.int32)
         self._attach(self.z0 - h0, self.z1 + h1)
         nl, ns = ct.c_int32(0), ct.c_int32(0)
         self._lib_call(self.lib.mci_detect_slices, 2, ct.byref(nl), ct.byref(ns))
-        labels = (L.LabelInfo * max(nl.value, 1))()
-        slices = (L.LabeledSlice * max(ns.value, 1))()
-        self._check(self.lib.mci_get_detection(self.ctx, labels, slices))
+        labels = np.zeros(max(nl.value, 1), LABEL_DT)
+        slices = np.zeros(max(ns.value, 1), SLICE_DT)
+        self._check(self.lib.mci_get_detection(self.ctx, labels.ctypes.data, slices.ctypes.data))
         self._detach()
+        labels, slices = labels[:nl.value], slices[:ns.value]
         base = self.z0 - h0
-        lab = np.array([[labels[k].label, labels[k].bbox_index[0], labels[k].bbox_index[1], labels[k].bbox_index[2] + base,
-                         labels[k].bbox_size[0], labels[k].bbox_size[1], labels[k].bbox_size[2]] for k in range(nl.value)],
-                       dtype=np.int32).reshape(-1, 7)
-        sl = np.array([[slices[k].label, slices[k].slice + base] for k in range(ns.value)
-                       if slices[k].axis == 2 and self.z0 <= slices[k].slice + base < self.z1], dtype=np.int32).reshape(-1, 2)
+        lab = np.empty((len(labels), 7), np.int32)
+        lab[:, 0] = labels["label"]
+        lab[:, 1:4] = labels["idx"]
+        lab[:, 3] += base
+        lab[:, 4:7] = labels["size"]
+        z = slices["slice"].astype(np.int64) + base
+        keep = (slices["axis"] == 2) & (z >= self.z0) & (z < self.z1)
+        sl = np.stack([slices["label"][keep].astype(np.int32), z[keep].astype(np.int32)], axis=1).reshape(-1, 2)
         return lab, sl
 
     def _gather_tables(self, lab, sl):
@@ -398,25 +422,23 @@ class SlabShardedInterpolator:
         self.table_bytes += nbytes
         return tables
 
-    def _run_local(self, bboxes, slices, zlo, zhi):
+    def _run_local(self, boxes, slices, zlo, zhi):
         ct, L = self.ct, self.L
         self._attach(zlo, zhi)
-        labs = sorted(bboxes)
-        li = (L.LabelInfo * max(len(labs), 1))()
-        for k, lab in enumerate(labs):
-            lo, hi = bboxes[lab]
-            li[k].label = lab
-            for a in range(3):
-                li[k].bbox_index[a] = lo[a]
-                li[k].bbox_size[a] = hi[a] - lo[a] + 1
-            li[k].bbox_index[2] = max(0, lo[2] - zlo)  # the z extent of the box is not used by runs along z
-            li[k].bbox_size[2] = 1
-        rows = [(lab, z - zlo) for lab, zs in slices.items() for z in zs if zlo <= z < zhi]
-        ls = (L.LabeledSlice * max(len(rows), 1))()
-        for k, (lab, z) in enumerate(rows):
-            ls[k].axis, ls[k].slice, ls[k].label = 2, z, lab
+        li = np.zeros(max(len(boxes), 1), LABEL_DT)
+        n = len(boxes)
+        li["label"][:n] = boxes[:, 0]
+        li["idx"][:n] = boxes[:, 1:4]
+        li["size"][:n] = boxes[:, 4:7] - boxes[:, 1:4] + 1
+        li["idx"][:n, 2] = np.maximum(0, boxes[:, 3] - zlo)  # the z extent of a box is not used by runs along z
+        li["size"][:n, 2] = 1
+        rows = slices[(slices[:, 1] >= zlo) & (slices[:, 1] < zhi)]
+        ls = np.zeros(max(len(rows), 1), SLICE_DT)
+        ls["axis"][:len(rows)] = 2
+        ls["slice"][:len(rows)] = rows[:, 1] - zlo
+        ls["label"][:len(rows)] = rows[:, 0]
         st = L.FilterStats()
-        self._lib_call(self.lib.mci_filter_run_with_detection, ct.byref(self.opt), li, len(labs), ls, len(rows),
+        self._lib_call(self.lib.mci_filter_run_with_detection, ct.byref(self.opt), li.ctypes.data, n, ls.ctypes.data, len(rows),
                        self.z0 - zlo, self.z1 - zlo, ct.byref(st))
         self._detach()
         self.last_stats = st.as_dict()
@@ -490,7 +512,7 @@ class SlabShardedInterpolator:
         for q in range(self.world):
             for z in needs[q]:
                 o = self._owner(z)
-                if o == q:
+                if o == q or self.rank not in (o, q):
                     continue
                 plane = self.buf_in[self._p(z)].view(torch.uint8)
                 if o == self.rank:
@@ -510,19 +532,30 @@ class SlabShardedInterpolator:
 
     def run_resident(self, **options):
         """the slab loaded by load_slab is interpolated in place in HBM; returns the device tensor of output planes"""
+        import time
         self.set_options(**options)
         bounds = self.bounds
+        t = [time.perf_counter()]
         halos = [[z for z in (lo - 1, hi) if 0 <= z < self.Z and hi > lo] for lo, hi in bounds]
         self._fetch_planes(halos)
+        self.stream.synchronize()
+        t.append(time.perf_counter())
         lab, sl = self._detect()
+        t.append(time.perf_counter())
         bboxes, slices = merge_detection(self._gather_tables(lab, sl))
+        t.append(time.perf_counter())
         plans = [plan_slab(slices, lo, hi, int(self.opt.label)) for lo, hi in bounds]
         zlo, zhi, _ = plans[self.rank]
         if self._ensure_margin(zlo, zhi):
             self._fetch_planes(halos)
         extra = [[z for z in plans[q][2] if z not in halos[q]] for q in range(self.world)]
         self._fetch_planes(extra)
+        self.stream.synchronize()
+        t.append(time.perf_counter())
         if self.z1 > self.z0:
             self._run_local(bboxes, slices, zlo, zhi)
         self.stream.synchronize()
+        t.append(time.perf_counter())
+        self.phase_ms = dict(zip(("halo_exchange", "detect", "gather_tables", "plan_and_fetch", "interpolate"),
+                                 [(b - a) * 1e3 for a, b in zip(t[:-1], t[1:])]))
         return self.output_slab()

@@ -147,9 +147,9 @@ def test_slab_sharded_ranks_reproduce_their_planes(world, name):
     procs = [ctx.Process(target=_slab_worker, args=(r, world, port, name, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=600) for _ in range(world)]
+    results = [q.get(timeout=240) for _ in range(world)]
     for p in procs:
-        p.join(timeout=120)
+        p.join(timeout=60)
         assert p.exitcode == 0
     vol = _slab_volume(name)
     ref, st_full = O.interpolate(vol, axis=2, return_stats=True)

@@ -62,7 +62,7 @@ def _worker(rank, world, port, name, q):
         z0, z1 = slab_bounds(vol.shape[0], world)[rank]
         lab, sl = local_tables(vol, z0, z1)
         tables, _ = exchange_tables(lab, sl, None, "cpu", cap_labels=2, cap_slices=1)  # tiny slots: the exact re-gather runs
-        bboxes, slices = merge_detection(tables)
+        boxes, slices = merge_detection(tables)
         zlo, zhi, needed = plan_slab(slices, z0, z1)
         # the local plane range holds ONLY the slab, its halo planes and the planned foreign planes
         local = np.zeros((zhi - zlo,) + vol.shape[1:], vol.dtype)
@@ -70,8 +70,11 @@ def _worker(rank, world, port, name, q):
         for z in have:
             if zlo <= z < zhi:
                 local[z - zlo] = vol[z]
-        lb = {l: ([lo[0], lo[1], 0], [hi[0], hi[1], 0]) for l, (lo, hi) in bboxes.items()}
-        ls = {l: [z - zlo for z in zs if zlo <= z < zhi] for l, zs in slices.items()}
+        lb = {int(r[0]): ([r[1], r[2], 0], [r[4], r[5], 0]) for r in boxes}
+        ls = {}
+        for l, z in slices:
+            if zlo <= z < zhi:
+                ls.setdefault(int(l), []).append(int(z - zlo))
         out = literal_mci.interpolate_with_detection(local, lb, ls, 2, (z0 - zlo, z1 - zlo), dt=True, ball=False)
         q.put((rank, z0, z1, out[z0 - zlo:z1 - zlo].copy(), needed))
     finally:
@@ -114,5 +117,5 @@ def test_merge_detection_unions_boxes_and_slice_sets():
     a = (np.array([[7, 2, 3, 0, 4, 5, 1]]), np.array([[7, 0], [7, 5]]))
     b = (np.array([[7, 1, 6, 5, 2, 9, 2], [3, 0, 0, 6, 1, 1, 1]]), np.array([[7, 5], [3, 6]]))
     boxes, slices = merge_detection([a, b])
-    assert boxes[7] == ([1, 3, 0], [5, 14, 6]) and boxes[3] == ([0, 0, 6], [0, 0, 6])
-    assert slices == {7: [0, 5], 3: [6]}
+    assert boxes.tolist() == [[3, 0, 0, 6, 0, 0, 6], [7, 1, 3, 0, 5, 14, 6]]  # label, lo xyz, hi xyz
+    assert slices.tolist() == [[3, 6], [7, 0], [7, 5]]

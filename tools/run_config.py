@@ -21,7 +21,7 @@ for it in range(3):
     rc = lib.mci_filter_run_resident(ctx, ctypes.byref(opt), None, 0, ctypes.byref(st)); assert rc == 0, lib.mci_last_error(ctx)
 print("resident: %.2f ms" % st.ms_total, "Mvoxel/s %.0f" % (vol.size / st.ms_total / 1e3))
 kt = (L.KernelTime * 64)(); nk = ctypes.c_int32(0); lib.mci_profile_read(ctx, kt, 64, ctypes.byref(nk))
-for k in sorted(range(nk.value), key=lambda k: -kt[k].total_ms)[:10]: print("  %-18s %3d launches %.3f ms/step" % (kt[k].name.decode(), kt[k].launches // 3, kt[k].total_ms / 3))
+for k in sorted(range(nk.value), key=lambda k: -kt[k].total_ms)[:24]: print("  %-18s %3d launches %.3f ms/step" % (kt[k].name.decode(), kt[k].launches // 3, kt[k].total_ms / 3))
 assert np.array_equal(out[vol != 0], vol[vol != 0]); print("interpolated voxels:", int((out != vol).sum()))
 if check:
     from oracle import oracle_lib as O

@@ -689,7 +689,7 @@ align_count(const AlignShape & A, const AlignShape & B, int tx, int ty, int part
     if (whi > wlo)
     {
       const int rows = yhi - ylo;
-      const int r0 = (int)((long long)rows * part / nparts), r1 = (int)((long long)rows * (part + 1) / nparts);
+      const int r0 = rows * part / nparts, r1 = rows * (part + 1) / nparts; // rows <= 16383, nparts <= 32
       const int off = dx0 >> 5, sh = dx0 & 31;
       for (int r = r0 + lane; r < r1; r += 32)
       {
@@ -752,7 +752,7 @@ struct AlignBfsShared
 __device__ __forceinline__ void
 align_bfs(const AlignJob & J, const AlignShape & A, const AlignShape * sB, const MaskRef * __restrict__ refs,
           const uint32_t * __restrict__ arena, uint32_t * bitmap, int * qx, int * qy, unsigned * qs, int bpitch, int heuristic,
-          volatile AlignBfsShared * st, int & bestx, int & besty, int & nWaves, int * err)
+          volatile AlignBfsShared * st, unsigned * htab, int & bestx, int & besty, int & nWaves, int * err)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int qmask = J.qcap - 1;
@@ -884,18 +884,63 @@ align_bfs(const AlignJob & J, const AlignShape & A, const AlignShape * sB, const
             val[nb] = ex && (unsigned)rx < (unsigned)J.sw && (unsigned)ry < (unsigned)J.sh &&
                       !((bitmap[ry * bpitch + (rx >> 5)] >> (rx & 31)) & 1u);
           }
+          // A neighbour of an expanding entry is also the neighbour of up to three other entries; it is pushed by the
+          // earliest of them.  The chunk's expanding entries go into a 32 x 32 direct-mapped table keyed by the low bits
+          // of their position (adjacent positions never share a slot), so each candidate looks its three other possible
+          // sources up instead of comparing itself with every earlier lane.  Two entries 32 apart would share a slot:
+          // then the chunk falls back to the comparison loop.
           const unsigned exMask = __ballot_sync(0xFFFFFFFFu, ex);
-          for (int l = 0; l < n - 1; ++l)
+          int mySlot = 0;
+          bool coll = false, inserted = false;
+          if (ex)
           {
-            const int px = __shfl_sync(0xFFFFFFFFu, tx, l), py = __shfl_sync(0xFFFFFFFFu, ty, l);
-            if (((exMask >> l) & 1u) && l < lane)
-            {
+            const int rx = tx - J.sx0, ry = ty - J.sy0;
+            mySlot = ((ry & 31) << 5) | (rx & 31);
+            const unsigned key = 0x800000u | ((unsigned)lane << 18) | ((unsigned)(ry >> 5) << 9) | (unsigned)(rx >> 5);
+            coll = atomicCAS(&htab[mySlot], 0u, key) != 0u;
+            inserted = !coll;
+          }
+          __syncwarp();
+          if (!__any_sync(0xFFFFFFFFu, coll))
+          {
 #pragma unroll
-              for (int nb = 0; nb < 4; ++nb)
-                if (abs(cx[nb] - px) + abs(cy[nb] - py) == 1)
+            for (int nb = 0; nb < 4; ++nb)
+            {
+              if (!val[nb])
+                continue;
+#pragma unroll
+              for (int sb = 0; sb < 4; ++sb)
+              {
+                if (sb == (nb ^ 1))
+                  continue; // that neighbour of the candidate is this lane's own entry
+                const int qx_ = cx[nb] + (sb == 0 ? -1 : (sb == 1 ? 1 : 0)) - J.sx0;
+                const int qy_ = cy[nb] + (sb == 2 ? -1 : (sb == 3 ? 1 : 0)) - J.sy0;
+                if ((unsigned)qx_ >= (unsigned)J.sw || (unsigned)qy_ >= (unsigned)J.sh)
+                  continue;
+                const unsigned v = htab[((qy_ & 31) << 5) | (qx_ & 31)];
+                if ((v & 0x800000u) && (v & 0x3FFFFu) == (((unsigned)(qy_ >> 5) << 9) | (unsigned)(qx_ >> 5)) &&
+                    (int)((v >> 18) & 31u) < lane)
                   val[nb] = false;
+              }
             }
           }
+          else
+          {
+            for (int l = 0; l < n - 1; ++l)
+            {
+              const int px = __shfl_sync(0xFFFFFFFFu, tx, l), py = __shfl_sync(0xFFFFFFFFu, ty, l);
+              if (((exMask >> l) & 1u) && l < lane)
+              {
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb)
+                  if (abs(cx[nb] - px) + abs(cy[nb] - py) == 1)
+                    val[nb] = false;
+              }
+            }
+          }
+          __syncwarp();
+          if (inserted)
+            htab[mySlot] = 0u;
           const int cnt = (int)val[0] + (int)val[1] + (int)val[2] + (int)val[3];
           int incl = cnt;
 #pragma unroll
@@ -1023,6 +1068,9 @@ k_align(const AlignJob * __restrict__ jobs, int njobs, const MaskRef * __restric
   extern __shared__ uint32_t smem[];
   __shared__ AlignBfsShared s_bfs;
   __shared__ AlignShape s_A, s_B[ALIGN_MAX_STAGED];
+  __shared__ unsigned s_htab[1024]; // align_bfs: positions of the expanding entries of a replay chunk
+  for (int k = threadIdx.x; k < 1024; k += blockDim.x)
+    s_htab[k] = 0u;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int jb = blockIdx.x; jb < njobs; jb += gridDim.x)
   {
@@ -1134,11 +1182,11 @@ k_align(const AlignJob * __restrict__ jobs, int njobs, const MaskRef * __restric
       if (J.useSmem)
         align_bfs(J, A, s_B, refs, arena, smem + ALIGN_MASK_WORDS, (int *)(smem + ALIGN_MASK_WORDS + bwords),
                   (int *)(smem + ALIGN_MASK_WORDS + bwords) + J.qcap, (unsigned *)(smem + ALIGN_MASK_WORDS + bwords) + 2 * J.qcap,
-                  bpitch, heuristic, &s_bfs, bestx, besty, nWaves, err);
+                  bpitch, heuristic, &s_bfs, s_htab, bestx, besty, nWaves, err);
       else
         align_bfs(J, A, s_B, refs, arena, gscratch + J.bitmapOff, (int *)(gscratch + J.queueOff),
                   (int *)(gscratch + J.queueOff) + J.qcap, (unsigned *)(gscratch + J.queueOff) + 2 * J.qcap, bpitch, heuristic,
-                  &s_bfs, bestx, besty, nWaves, err);
+                  &s_bfs, s_htab, bestx, besty, nWaves, err);
     }
     if (threadIdx.x == 0)
     {
@@ -1155,7 +1203,7 @@ launch_align(Launch & L, const AlignJob * jobs, int njobs, const MaskRef * refs,
 {
   if (njobs == 0)
     return;
-  L.ensure_max_smem(k_align, 1, L.maxSmem - 1024);
+  L.ensure_max_smem(k_align, 1, L.maxSmem - 8192); // static shared memory (replay table, shape headers) takes ~5 KB
   int grid = std::min(njobs, L.sms * 8);
   // at most one job per SM: the launch lasts as long as its slowest job, and more warps shorten every scoring wave;
   // many jobs per SM: two smaller CTAs per SM keep the SM busy while one of them replays its queue

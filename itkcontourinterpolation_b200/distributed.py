@@ -215,10 +215,19 @@ def merge_detection(tables):
         boxes = np.concatenate([ids[:, None], lo, hi], axis=1)
     else:
         boxes = np.zeros((0, 7), np.int64)
-    sls = [np.asarray(t[1], dtype=np.int64).reshape(-1, 2) for t in tables]
+    sls = [np.asarray(t[1]).reshape(-1, 2) for t in tables]
     sl = np.concatenate(sls) if sls else np.zeros((0, 2), np.int64)
     if len(sl):
-        sl = np.unique(sl, axis=0)  # lexicographic: by label, then z
+        # unique rows in lexicographic order (label, then z) through one sorted 64-bit key
+        key = (sl[:, 0].astype(np.int64) << 32) | sl[:, 1].astype(np.int64)  # planes are >= 0
+        key.sort()
+        if len(key) > 1:
+            key = key[np.concatenate(([True], key[1:] != key[:-1]))]
+        sl = np.empty((len(key), 2), np.int64)
+        sl[:, 0] = key >> 32
+        sl[:, 1] = key & 0xFFFFFFFF
+    else:
+        sl = np.zeros((0, 2), np.int64)
     return boxes, sl
 
 
@@ -242,14 +251,15 @@ def plan_slab(slices, z0, z1, label=0):
         slices = np.unique(np.asarray(rows, dtype=np.int64).reshape(-1, 2), axis=0) if rows else np.zeros((0, 2), np.int64)
     if z1 <= z0:
         return z0, z1, []
-    si, sj = segments_of(slices, label)
-    hit = np.maximum(si + 1, z0) <= np.minimum(sj - 1, z1 - 1)
-    if not hit.any():
+    si, sj = slices if isinstance(slices, tuple) else segments_of(slices, label)  # (i, j) arrays: computed once by the caller
+    # a segment has i + 1 <= j - 1, so its mid slices meet [z0, z1) iff i + 1 <= z1 - 1 and j - 1 >= z0
+    idx = np.flatnonzero((si < z1 - 1) & (sj > z0))
+    if not len(idx):
         return z0, z1, []
-    si, sj = si[hit], sj[hit]
-    ends = np.unique(np.concatenate([si, sj]))
-    needed = ends[(ends < z0) | (ends >= z1)]
-    return int(min(z0, si.min())), int(max(z1, sj.max() + 1)), [int(z) for z in needed]
+    si, sj = si[idx], sj[idx]
+    ends = np.concatenate([si, sj])
+    ends = np.unique(ends[(ends < z0) | (ends >= z1)])
+    return int(min(z0, si.min())), int(max(z1, sj.max() + 1)), ends.tolist()
 
 
 def exchange_tables(labels, slices, group=None, device="cpu", cap_labels=1024, cap_slices=32768):
@@ -544,7 +554,8 @@ class SlabShardedInterpolator:
         t.append(time.perf_counter())
         bboxes, slices = merge_detection(self._gather_tables(lab, sl))
         t.append(time.perf_counter())
-        plans = [plan_slab(slices, lo, hi, int(self.opt.label)) for lo, hi in bounds]
+        segs = segments_of(slices, int(self.opt.label))
+        plans = [plan_slab(segs, lo, hi) for lo, hi in bounds]
         zlo, zhi, _ = plans[self.rank]
         if self._ensure_margin(zlo, zhi):
             self._fetch_planes(halos)

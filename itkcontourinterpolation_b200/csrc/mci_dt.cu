@@ -1406,8 +1406,6 @@ mask_word_cg(const uint32_t * data, const MaskRef & m, int y, int X)
   return __funnelshift_r(lo, hi, sh);
 }
 
-#define TREE_THREADS 512
-#define TREE_WARPS (TREE_THREADS / 32)
 #define TREE_NODE_WORDS 12288 // shared-memory budget (words) for one node's rows: 3 * words + h + (h + 7) / 8
 #define TREE_HWORDS 8         // words per warp visit in the histogram phase (pixels are dealt one per lane)
 
@@ -1437,10 +1435,13 @@ tree_get_big(int * sBig, int * bigCount, int nbig, int * err)
 }
 
 
-template <typename T>
-__global__ void __launch_bounds__(TREE_THREADS, 2)
+// TREE_THREADS = 512: two CTAs per SM (throughput: many more nodes than CTAs); 1024: one CTA per SM, every phase of a
+// node twice as wide (latency: few nodes, the launch lasts as long as the deepest chain of its biggest nodes)
+template <typename T, int TREE_THREADS>
+__global__ void __launch_bounds__(TREE_THREADS, TREE_THREADS == 512 ? 2 : 1)
 k_dt_tree(const TreeParams P)
 {
+  constexpr int TREE_WARPS = TREE_THREADS / 32;
   pdl_wait();
   extern __shared__ uint32_t tsm[];
   __shared__ __align__(16) Node s_child[2];
@@ -2194,8 +2195,24 @@ k_dt_tree(const TreeParams P)
 #endif
 }
 
+template <typename T>
+static void
+launch_dt_tree_t(Launch & L, int bit, const TreeParams & P, int grid, int threads, int smem)
+{
+  if (threads == 1024)
+  {
+    L.ensure_max_smem(k_dt_tree<T, 1024>, bit + 3, smem);
+    launch_pdl(k_dt_tree<T, 1024>, grid, 1024, smem, L.stream, P);
+  }
+  else
+  {
+    L.ensure_max_smem(k_dt_tree<T, 512>, bit, smem);
+    launch_pdl(k_dt_tree<T, 512>, grid, 512, smem, L.stream, P);
+  }
+}
+
 void
-launch_dt_tree(Launch & L, int ptype, const TreeParams & P, int nRootsMax, int grid)
+launch_dt_tree(Launch & L, int ptype, const TreeParams & P, int nRootsMax, int grid, int threads)
 {
   if (nRootsMax <= 0)
     return;
@@ -2204,16 +2221,13 @@ launch_dt_tree(Launch & L, int ptype, const TreeParams & P, int nRootsMax, int g
   switch (ptype)
   {
     case MCI_U8:
-      L.ensure_max_smem(k_dt_tree<uint8_t>, 8, smem);
-      launch_pdl(k_dt_tree<uint8_t>, grid, TREE_THREADS, smem, L.stream, P);
+      launch_dt_tree_t<uint8_t>(L, 8, P, grid, threads, smem);
       break;
     case MCI_U16:
-      L.ensure_max_smem(k_dt_tree<uint16_t>, 9, smem);
-      launch_pdl(k_dt_tree<uint16_t>, grid, TREE_THREADS, smem, L.stream, P);
+      launch_dt_tree_t<uint16_t>(L, 9, P, grid, threads, smem);
       break;
     default:
-      L.ensure_max_smem(k_dt_tree<int16_t>, 10, smem);
-      launch_pdl(k_dt_tree<int16_t>, grid, TREE_THREADS, smem, L.stream, P);
+      launch_dt_tree_t<int16_t>(L, 10, P, grid, threads, smem);
   }
   L.post("k_dt_tree");
 }

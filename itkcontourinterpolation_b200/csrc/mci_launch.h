@@ -186,7 +186,7 @@ struct TreeParams
   long long VX, VY, VZ;
   int * err;
 };
-void launch_dt_tree(Launch & L, int ptype, const TreeParams & P, int nRootsMax, int grid);
+void launch_dt_tree(Launch & L, int ptype, const TreeParams & P, int nRootsMax, int grid, int threads);
 
 long long median_tile_count(const long long dims[3]);
 void launch_median3d(Launch & L, int ptype, const void * in, void * out, const long long dims[3], int radius, unsigned * summary);

@@ -28,7 +28,7 @@ def launches(path, out, title, lo=None, hi=None):
         # one step = the launches from one k_copy_flag to the next; the second complete one (the first is the
         # bit-exactness check through mci_filter_run, the later ones are warm-up / timed resident steps)
         starts = [k for k, r in enumerate(recs) if r[1].startswith("k_copy_flag")] + [len(recs)]
-        segs = [(a, b) for a, b in zip(starts, starts[1:]) if any(r[1].startswith("k_dt_emit") or r[1].startswith("k_apply") for r in recs[a:b])]
+        segs = [(a, b) for a, b in zip(starts, starts[1:]) if any(r[1].startswith("k_dt_emit") or r[1].startswith("k_dt_tree") or r[1].startswith("k_apply") for r in recs[a:b])]
         a, b = segs[1] if len(segs) > 1 else segs[0]
         step = recs[a:b]
     else:

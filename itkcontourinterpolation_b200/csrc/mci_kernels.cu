@@ -882,7 +882,8 @@ align_bfs(const AlignJob & J, const AlignShape & A, const AlignShape * sB, const
             cy[nb] = ty + (nb == 2 ? -1 : (nb == 3 ? 1 : 0));
             const int rx = cx[nb] - J.sx0, ry = cy[nb] - J.sy0;
             val[nb] = ex && (unsigned)rx < (unsigned)J.sw && (unsigned)ry < (unsigned)J.sh &&
-                      !((bitmap[ry * bpitch + (rx >> 5)] >> (rx & 31)) & 1u);
+                      !((((const volatile uint32_t *)bitmap)[ry * bpitch + (rx >> 5)] >> (rx & 31)) & 1u); // volatile: the
+            // bitmap may live in global scratch, where the atomicOr of an earlier chunk went to L2 past this SM's L1
           }
           // A neighbour of an expanding entry is also the neighbour of up to three other entries; it is pushed by the
           // earliest of them.  The chunk's expanding entries go into a 32 x 32 direct-mapped table keyed by the low bits

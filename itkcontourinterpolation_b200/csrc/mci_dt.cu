@@ -2040,7 +2040,7 @@ k_dt_tree(const TreeParams P)
       if (!s_alive)
         break;
       PH(5);
-      // ---- store the mid shape and write it into the volume with the max rule (X:743-764)
+      // ---- store the mid shape, publish the children, write the shape into the volume with the max rule (X:743-764)
       {
         constexpr int VPQ = 8 / sizeof(T);
         constexpr int GPW = 32 / VPQ + 1;
@@ -2069,6 +2069,42 @@ k_dt_tree(const TreeParams P)
           vbase = (unsigned long long)mid;
         }
         const int mwords = M.h * M.pitch;
+        // the mid shape goes to the arena first and the children are published right away: other CTAs start on them
+        // while this one is still busy with the volume writes (read-modify-write round trips to L2 / HBM)
+        for (int cell = tid; cell < mwords; cell += TREE_THREADS)
+        {
+          const int r = cell / M.pitch, wi = cell - r * M.pitch;
+          const int y = M.y0 + r, x = M.x0 + 32 * wi;
+          const uint32_t * row = Ib + (size_t)(y - uy0) * pitch;
+          const int rx = x - ux0; // >= 0
+          const int sw = rx >> 5, shf = rx & 31;
+          const uint32_t lo = row[sw];
+          const uint32_t hi = sw + 1 < pitch ? row[sw + 1] : 0u;
+          uint32_t mw = __funnelshift_r(lo, hi, shf);
+          const int valid = M.w - 32 * wi;
+          if (valid < 32)
+            mw &= (1u << valid) - 1u;
+          P.arena[M.off + cell] = mw;
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0 && s_nchild)
+        {
+          const int n = s_nchild;
+          s_nchild = 0;
+          const int base = atomicAdd(P.rootNext + 2, n);
+          if (base + n > P.queueCap)
+            atomicMax(P.err, ERR_NODE_LIST);
+          else
+          {
+            for (int k = 0; k < n; ++k)
+              P.roots[nRoots + base + k] = s_child[k];
+            __threadfence();
+            for (int k = 0; k < n; ++k)
+              vflags[base + k] = 1;
+            atomicAdd(P.rootNext + 3, n);
+          }
+        }
         for (int wBeg = warp * 32; wBeg < mwords; wBeg += TREE_WARPS * 32)
         {
           const int wEnd = min(mwords, wBeg + 32);
@@ -2088,7 +2124,6 @@ k_dt_tree(const TreeParams P)
               const int valid = M.w - 32 * wi;
               if (valid < 32)
                 myM &= (1u << valid) - 1u;
-              P.arena[M.off + cell] = myM;
             }
           }
           if (su == 1)
@@ -2162,28 +2197,11 @@ k_dt_tree(const TreeParams P)
       }
     } while (0);
     PH(6);
-    // node finished: every thread fences its arena stores, then one thread publishes the children and counts the
-    // node as done (children first: see the termination test above)
-    __threadfence();
+    // node finished (its children were published as soon as its shape was in the arena): count it as done -- after
+    // the children, see the termination test above
     __syncthreads();
     if (tid == 0)
     {
-      const int n = s_nchild;
-      if (n)
-      {
-        const int base = atomicAdd(P.rootNext + 2, n);
-        if (base + n > P.queueCap)
-          atomicMax(P.err, ERR_NODE_LIST);
-        else
-        {
-          for (int k = 0; k < n; ++k)
-            P.roots[nRoots + base + k] = s_child[k];
-          __threadfence();
-          for (int k = 0; k < n; ++k)
-            vflags[base + k] = 1;
-          atomicAdd(P.rootNext + 3, n);
-        }
-      }
       __threadfence();
       atomicAdd(P.rootNext + 4, 1);
     }

@@ -1407,7 +1407,8 @@ mask_word_cg(const uint32_t * data, const MaskRef & m, int y, int X)
 }
 
 #define TREE_NODE_WORDS 12288 // shared-memory budget (words) for one node's rows: 3 * words + h + (h + 7) / 8
-#define TREE_HWORDS 8         // words per warp visit in the histogram phase (pixels are dealt one per lane)
+#define TREE_HWORDS 8         // words per warp visit in the histogram phase (pixels are dealt one per lane); measured
+                              // k_dt_tree C3 / C5 in ms: 2 words 0.43 / 6.8, 4: 0.35 / 5.7, 8: 0.35 / 4.9, 32: 0.62 / 4.7
 
 __device__ __forceinline__ int
 tree_get_big(int * sBig, int * bigCount, int nbig, int * err)

@@ -1407,6 +1407,7 @@ mask_word_cg(const uint32_t * data, const MaskRef & m, int y, int X)
 }
 
 #define TREE_NODE_WORDS 12288 // shared-memory budget (words) for one node's rows: 3 * words + h + (h + 7) / 8
+#define TREE_GROUPS 512       // nodes of up to 16 384 words have their xor pixels dealt across the whole CTA
 #define TREE_HWORDS 8         // words per warp visit in the histogram phase (pixels are dealt one per lane); measured
                               // k_dt_tree C3 / C5 in ms: 2 words 0.43 / 6.8, 4: 0.35 / 5.7, 8: 0.35 / 4.9, 32: 0.62 / 4.7
 
@@ -1449,6 +1450,7 @@ k_dt_tree(const TreeParams P)
   __shared__ __align__(16) Node s_nd;
   __shared__ MaskRef s_M;
   __shared__ int s_nchild, s_slot, s_r0, s_r1, s_big, s_thr, s_alive, s_bx0, s_bx1, s_by0, s_by1, s_maxBin;
+  __shared__ int s_gcum[TREE_GROUPS + 1]; // histogram phase: xor pixels before each 32-word group of the node's rows
   __shared__ long long redA[TREE_WARPS], redB[TREE_WARPS], bestD[TREE_WARPS];
   __shared__ int bestI[TREE_WARPS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1655,36 +1657,143 @@ k_dt_tree(const TreeParams P)
         break; // empty intersection: both median finders give an empty image
       PH(1);
       // ---- histograms of bin = PixelType(10 * sqrtf(d2)) over the (i xor j) pixels, per side (X:413-459)
-      for (int wBeg = warp * TREE_HWORDS; wBeg < words; wBeg += TREE_WARPS * TREE_HWORDS)
+      // The pixels are dealt to the lanes across the WHOLE node, 32 consecutive pixels per warp visit: counts per
+      // 32-word group -> prefix -> a visit looks its first group up and walks the groups its 32 pixels span.  Every
+      // lane of a visit then has a pixel for the row search (the costly part), and every warp gets the same number
+      // of visits, wherever the band of xor pixels happens to cross the node's rows.
+      const int nGroups = (words + 31) >> 5;
+      const bool dealt = nGroups <= TREE_GROUPS;
+      if (dealt)
       {
-        const int myIdx = wBeg + lane;
-        const bool mine = lane < TREE_HWORDS && myIdx < words;
-        const uint32_t myS = mine ? Sb[myIdx] : 0u;
-        const uint32_t myI = mine ? Ib[myIdx] : 0u;
-        int incl = __popc(myS);
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1)
+        for (int g = warp; g < nGroups; g += TREE_WARPS)
         {
-          int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-          if (lane >= o)
-            incl += v;
+          const int wi = 32 * g + lane;
+          int c = wi < words ? __popc(Sb[wi]) : 0;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+            c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+          if (lane == 0)
+            s_gcum[g + 1] = c;
         }
-        const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        __syncthreads();
+        if (warp == 0)
+        {
+          // inclusive prefix over up to TREE_GROUPS counts, 32 at a time
+          int carry = 0;
+          for (int g0 = 0; g0 < nGroups; g0 += 32)
+          {
+            int v = g0 + lane < nGroups ? s_gcum[g0 + lane + 1] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+              const int u = __shfl_up_sync(0xFFFFFFFFu, v, o);
+              if (lane >= o)
+                v += u;
+            }
+            if (g0 + lane < nGroups)
+              s_gcum[g0 + lane + 1] = carry + v;
+            carry += __shfl_sync(0xFFFFFFFFu, v, 31);
+          }
+          if (lane == 0)
+            s_gcum[0] = 0;
+        }
+        __syncthreads();
+      }
+      const int nPix = dealt ? s_gcum[nGroups] : 0;
+      const int nVisits = dealt ? (nPix + 31) >> 5 : (words + TREE_HWORDS - 1) / TREE_HWORDS;
+      for (int visit = warp; visit < nVisits; visit += TREE_WARPS)
+      {
+        // each lane ends up with: word index of its pixel (-1: none), bit, side
+        int pIdx = -1, pBit = 0, pSide = 0;
+        if (dealt)
+        {
+          const int p0 = 32 * visit, p = p0 + lane;
+          int lo = 0, hi = nGroups; // first group g with s_gcum[g + 1] > p0
+          while (lo < hi)
+          {
+            const int m = (lo + hi) >> 1;
+            if (s_gcum[m + 1] > p0)
+              hi = m;
+            else
+              lo = m + 1;
+          }
+          for (int g = lo; g < nGroups && s_gcum[g] < p0 + 32; ++g)
+          {
+            const int wi = 32 * g + lane;
+            const uint32_t myS = wi < words ? Sb[wi] : 0u;
+            const uint32_t myI = wi < words ? Ib[wi] : 0u;
+            int incl = __popc(myS);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+              int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+              if (lane >= o)
+                incl += v;
+            }
+            const int gBeg = s_gcum[g], gEnd = s_gcum[g + 1];
+            const bool here = p >= gBeg && p < gEnd;
+            int src, bit;
+            warp_pixel(myS, incl, here ? p - gBeg : 0, src, bit);
+            const uint32_t iw = __shfl_sync(0xFFFFFFFFu, myI, src);
+            if (here)
+            {
+              pIdx = 32 * g + src;
+              pBit = bit;
+              pSide = (iw >> bit) & 1u ? 0 : 1;
+            }
+          }
+        }
+        else
+        {
+          // nodes too large for the group table: 8 words per visit, their pixels dealt 32 at a time below
+          pIdx = -2;
+        }
+        const int wBeg = visit * TREE_HWORDS;
+        uint32_t myS = 0, myI = 0;
+        int incl = 0, total = dealt ? 32 : 0;
+        if (!dealt)
+        {
+          const int myIdx = wBeg + lane;
+          const bool mine = lane < TREE_HWORDS && myIdx < words;
+          myS = mine ? Sb[myIdx] : 0u;
+          myI = mine ? Ib[myIdx] : 0u;
+          incl = __popc(myS);
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1)
+          {
+            int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o)
+              incl += v;
+          }
+          total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        }
         for (int base = 0; base < total; base += 32)
         {
-          const int p = base + lane;
-          const bool on = p < total;
-          int src, bit;
-          warp_pixel(myS, incl, on ? p : total - 1, src, bit);
-          const uint32_t iw = __shfl_sync(0xFFFFFFFFu, myI, src);
-          int d2 = 0, side = 0;
+          bool on;
+          int idx, bit, side;
+          if (dealt)
+          {
+            on = pIdx >= 0;
+            idx = pIdx;
+            bit = pBit;
+            side = pSide;
+          }
+          else
+          {
+            const int p = base + lane;
+            on = p < total;
+            int src;
+            warp_pixel(myS, incl, on ? p : total - 1, src, bit);
+            const uint32_t iw = __shfl_sync(0xFFFFFFFFu, myI, src);
+            idx = wBeg + src;
+            side = (iw >> bit) & 1u ? 0 : 1;
+          }
+          int d2 = 0;
           bool over = false;
           if (on)
           {
-            const int idx = wBeg + src;
             const int r = idx / pitch, wi = idx - r * pitch;
             d2 = dt_edt_sq<false>(Xb, rowInfo, pitch, h, xr0, xr1, wi * 32 + bit, r, 0x7FFFFFFF);
-            side = (iw >> bit) & 1u ? 0 : 1;
             const int direct = dt_bin<T>(d2, P.err);
             if (direct < histSide)
             {

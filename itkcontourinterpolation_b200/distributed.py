@@ -262,41 +262,56 @@ def plan_slab(slices, z0, z1, label=0):
     return int(min(z0, si.min())), int(max(z1, sj.max() + 1)), ends.tolist()
 
 
-def exchange_tables(labels, slices, group=None, device="cpu", cap_labels=1024, cap_slices=32768):
-    """All-gather of the per-rank detection tables (int32 rows).  One collective of fixed-size slots; a second, exact
-    one only if some rank's tables overflow the slot."""
+def exchange_tables(labels, slices, group=None, device="cpu", cap_labels=512, cap_slices=4096, buffers=None):
+    """All-gather of the per-rank detection tables (int32 rows).  One collective of fixed-size slots (50 KB per rank
+    by default); a second, exact one only if some rank's tables overflow the slot.  buffers: dict the caller keeps
+    between calls (pinned staging + device tensors, so that a step allocates nothing)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     labels = np.asarray(labels, dtype=np.int32).reshape(-1, 7)
     slices = np.asarray(slices, dtype=np.int32).reshape(-1, 2)
+    on_gpu = str(device) != "cpu"
 
-    def pack(cl, cs):
-        buf = np.zeros(4 + 7 * cl + 2 * cs, np.int32)
+    def gather(cl, cs):
+        n = 4 + 7 * cl + 2 * cs
+        key = (cl, cs)
+        if buffers is not None and buffers.get("key") == key:
+            hs, hr, ds, dr = buffers["hs"], buffers["hr"], buffers["ds"], buffers["dr"]
+        else:
+            hs = torch.zeros(n, dtype=torch.int32)
+            hr = torch.zeros((world, n), dtype=torch.int32)
+            if on_gpu:
+                hs, hr = hs.pin_memory(), hr.pin_memory()
+                ds = torch.empty(n, dtype=torch.int32, device=device)
+                dr = torch.empty((world, n), dtype=torch.int32, device=device)
+            else:
+                ds, dr = hs, hr
+            if buffers is not None:
+                buffers.update(key=key, hs=hs, hr=hr, ds=ds, dr=dr)
+        buf = hs.numpy()
         buf[0], buf[1] = len(labels), len(slices)
         if len(labels) <= cl and len(slices) <= cs:
             buf[4:4 + 7 * len(labels)] = labels.reshape(-1)
             buf[4 + 7 * cl:4 + 7 * cl + 2 * len(slices)] = slices.reshape(-1)
-        return buf
-
-    def gather(cl, cs):
-        send = torch.from_numpy(pack(cl, cs)).to(device)
-        recv = torch.empty((world, send.numel()), dtype=torch.int32, device=device)
-        if hasattr(dist, "all_gather_into_tensor") and str(device) != "cpu":
-            dist.all_gather_into_tensor(recv.view(-1), send, group=group)
+        if on_gpu:
+            ds.copy_(hs, non_blocking=True)
+            dist.all_gather_into_tensor(dr.view(-1), ds, group=group)
+            hr.copy_(dr, non_blocking=True)
+            torch.cuda.current_stream(dr.device).synchronize()
         else:
-            dist.all_gather([recv[q] for q in range(world)], send, group=group)
-        return recv.cpu().numpy()
+            dist.all_gather([hr[q] for q in range(world)], hs, group=group)
+        return hr.numpy()
 
     got = gather(cap_labels, cap_slices)
     nl, ns = int(got[:, 0].max()), int(got[:, 1].max())
     if nl > cap_labels or ns > cap_slices:
-        cap_labels, cap_slices = max(nl, 1), max(ns, 1)
+        cap_labels, cap_slices = max(nl, cap_labels), max(ns, cap_slices)
         got = gather(cap_labels, cap_slices)
     out = []
     for q in range(world):
         a, b = int(got[q, 0]), int(got[q, 1])
-        out.append((got[q, 4:4 + 7 * a].reshape(-1, 7), got[q, 4 + 7 * cap_labels:4 + 7 * cap_labels + 2 * b].reshape(-1, 2)))
+        out.append((got[q, 4:4 + 7 * a].reshape(-1, 7).copy(), got[q, 4 + 7 * cap_labels:4 + 7 * cap_labels + 2 * b].reshape(-1, 2).copy()))
     return out, int(got.nbytes)
 
 
@@ -340,6 +355,7 @@ class SlabShardedInterpolator:
         self.nvlink_bytes = 0
         self.table_bytes = 0
         self.last_stats = {}
+        self._tab_buffers = {}
         # NCCL moves device memory (NVLink); any other backend (gloo, in tests) gets the planes staged through the host
         self._nccl = dist.is_initialized() and dist.get_backend(group) == "nccl"
 
@@ -428,7 +444,7 @@ class SlabShardedInterpolator:
         if self.world == 1:
             return [(lab, sl)]
         with self.torch.cuda.stream(self.stream):
-            tables, nbytes = exchange_tables(lab, sl, self.group, self.device if self._nccl else "cpu")
+            tables, nbytes = exchange_tables(lab, sl, self.group, self.device if self._nccl else "cpu", buffers=self._tab_buffers)
         self.table_bytes += nbytes
         return tables
 

@@ -1864,105 +1864,184 @@ k_dt_tree(const TreeParams P)
           cntJ = bh + 65536;
           bm = bbm;
         }
-        // bins are dealt to the threads in contiguous ranges up to the highest touched bin (thread order = bin order).
-        // Untouched bins inside a range repeat the score of the bin before them and lose every tie, so visiting
-        // them is exact; bin 0 is visited by thread 0 whether touched or not (bestDiff starts at LLONG_MAX, X:482-494)
-        const int nWords = big ? 2048 : smallWords;
-        if (tid == 0)
-          s_maxBin = -1;
-        __syncthreads();
-        for (int wI = tid; wI < nWords; wI += TREE_THREADS)
-        {
-          const unsigned bits = bm[wI];
-          if (bits)
-          {
-            atomicMax(&s_maxBin, wI * 32 + 31 - __clz(bits));
-            bm[wI] = 0u; // leave the tables clean for the next node
-          }
-        }
-        __syncthreads();
-        const int nb = s_maxBin + 1;
-        const int per = (nb + TREE_THREADS - 1) / TREE_THREADS;
-        const int k0 = min(nb, tid * per), k1 = min(nb, k0 + per);
-        long long li = 0, lj = 0;
-        for (int k = k0; k < k1; ++k)
-        {
-          li += cntI[k];
-          lj += cntJ[k];
-        }
-        long long sa = li, sb = lj;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1)
-        {
-          long long ta = __shfl_up_sync(0xFFFFFFFFu, sa, o), tb = __shfl_up_sync(0xFFFFFFFFu, sb, o);
-          if (lane >= o)
-          {
-            sa += ta;
-            sb += tb;
-          }
-        }
-        if (lane == 31)
-        {
-          redA[warp] = sa;
-          redB[warp] = sb;
-        }
-        __syncthreads();
-        long long oa = 0, ob = 0, iTot = 0, jTot = 0;
-        for (int k = 0; k < TREE_WARPS; ++k)
-        {
-          if (k < warp)
-          {
-            oa += redA[k];
-            ob += redB[k];
-          }
-          iTot += redA[k];
-          jTot += redB[k];
-        }
         int thr = -1; // -1: no pixel outside the intersection, the median is the intersection (X:463-466)
-        if (iTot + jTot > 0) // block-uniform
+        if (!big)
         {
-          long long si = oa + sa - li, sj = ob + sb - lj;
-          long long bd = 0x7FFFFFFFFFFFFFFFll;
-          int bidx = 0x7FFFFFFF;
-          for (int k = k0; k < k1; ++k)
+          // the node's own table (the common case: distances of a few pixels, a few hundred bins): ONE warp does it,
+          // no block-wide barrier, scan or reduction.  Bins are dealt to the lanes in contiguous ranges up to the
+          // highest touched bin (lane order = bin order); untouched bins inside a range repeat the score of the bin
+          // before them and lose every tie, so visiting them is exact; bin 0 is visited by lane 0 whether touched or
+          // not (bestDiff starts at LLONG_MAX, X:482-494)
+          if (warp == 0)
           {
-            si += cntI[k];
-            sj += cntJ[k];
-            const long long d = llabs(llabs(iTot - si + sj) - llabs(jTot - sj + si));
-            if (d < bd)
+            int mb = -1;
+            for (int wI = lane; wI < smallWords; wI += 32)
             {
-              bd = d;
-              bidx = k;
+              const unsigned bits = hsBm[wI];
+              if (bits)
+              {
+                mb = max(mb, wI * 32 + 31 - __clz(bits));
+                hsBm[wI] = 0u; // leave the tables clean for the next node
+              }
             }
-            cntI[k] = 0u;
-            cntJ[k] = 0u;
-          }
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1)
-          {
-            long long od = __shfl_xor_sync(0xFFFFFFFFu, bd, o);
-            int oi = __shfl_xor_sync(0xFFFFFFFFu, bidx, o);
-            if (od < bd || (od == bd && oi < bidx))
+            for (int o = 16; o > 0; o >>= 1)
+              mb = max(mb, __shfl_xor_sync(0xFFFFFFFFu, mb, o));
+            const int nb = mb + 1;
+            const int per = (nb + 31) >> 5;
+            const int k0 = min(nb, lane * per), k1 = min(nb, k0 + per);
+            long long li = 0, lj = 0;
+            for (int k = k0; k < k1; ++k)
             {
-              bd = od;
-              bidx = oi;
+              li += cntI[k];
+              lj += cntJ[k];
+            }
+            long long sa = li, sb = lj;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+              long long ta = __shfl_up_sync(0xFFFFFFFFu, sa, o), tb = __shfl_up_sync(0xFFFFFFFFu, sb, o);
+              if (lane >= o)
+              {
+                sa += ta;
+                sb += tb;
+              }
+            }
+            const long long iTot = __shfl_sync(0xFFFFFFFFu, sa, 31), jTot = __shfl_sync(0xFFFFFFFFu, sb, 31);
+            if (iTot + jTot > 0)
+            {
+              long long si = sa - li, sj = sb - lj;
+              long long bd = 0x7FFFFFFFFFFFFFFFll;
+              int bidx = 0x7FFFFFFF;
+              for (int k = k0; k < k1; ++k)
+              {
+                si += cntI[k];
+                sj += cntJ[k];
+                const long long d = llabs(llabs(iTot - si + sj) - llabs(jTot - sj + si));
+                if (d < bd)
+                {
+                  bd = d;
+                  bidx = k;
+                }
+                cntI[k] = 0u;
+                cntJ[k] = 0u;
+              }
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1)
+              {
+                long long od = __shfl_xor_sync(0xFFFFFFFFu, bd, o);
+                int oi = __shfl_xor_sync(0xFFFFFFFFu, bidx, o);
+                if (od < bd || (od == bd && oi < bidx))
+                {
+                  bd = od;
+                  bidx = oi;
+                }
+              }
+              thr = dt_threshold_d2(bidx);
             }
           }
-          if (lane == 0)
+        }
+        else
+        {
+          // bins are dealt to the threads in contiguous ranges up to the highest touched bin (thread order = bin order).
+          // Untouched bins inside a range repeat the score of the bin before them and lose every tie, so visiting
+          // them is exact; bin 0 is visited by thread 0 whether touched or not (bestDiff starts at LLONG_MAX, X:482-494)
+          const int nWords = big ? 2048 : smallWords;
+          if (tid == 0)
+            s_maxBin = -1;
+          __syncthreads();
+          for (int wI = tid; wI < nWords; wI += TREE_THREADS)
           {
-            bestD[warp] = bd;
-            bestI[warp] = bidx;
+            const unsigned bits = bm[wI];
+            if (bits)
+            {
+              atomicMax(&s_maxBin, wI * 32 + 31 - __clz(bits));
+              bm[wI] = 0u; // leave the tables clean for the next node
+            }
           }
           __syncthreads();
-          bd = bestD[0];
-          bidx = bestI[0];
-          for (int k = 1; k < TREE_WARPS; ++k)
-            if (bestD[k] < bd || (bestD[k] == bd && bestI[k] < bidx))
+          const int nb = s_maxBin + 1;
+          const int per = (nb + TREE_THREADS - 1) / TREE_THREADS;
+          const int k0 = min(nb, tid * per), k1 = min(nb, k0 + per);
+          long long li = 0, lj = 0;
+          for (int k = k0; k < k1; ++k)
+          {
+            li += cntI[k];
+            lj += cntJ[k];
+          }
+          long long sa = li, sb = lj;
+  #pragma unroll
+          for (int o = 1; o < 32; o <<= 1)
+          {
+            long long ta = __shfl_up_sync(0xFFFFFFFFu, sa, o), tb = __shfl_up_sync(0xFFFFFFFFu, sb, o);
+            if (lane >= o)
             {
-              bd = bestD[k];
-              bidx = bestI[k];
+              sa += ta;
+              sb += tb;
             }
-          thr = dt_threshold_d2(bidx);
+          }
+          if (lane == 31)
+          {
+            redA[warp] = sa;
+            redB[warp] = sb;
+          }
+          __syncthreads();
+          long long oa = 0, ob = 0, iTot = 0, jTot = 0;
+          for (int k = 0; k < TREE_WARPS; ++k)
+          {
+            if (k < warp)
+            {
+              oa += redA[k];
+              ob += redB[k];
+            }
+            iTot += redA[k];
+            jTot += redB[k];
+          }
+          if (iTot + jTot > 0) // block-uniform
+          {
+            long long si = oa + sa - li, sj = ob + sb - lj;
+            long long bd = 0x7FFFFFFFFFFFFFFFll;
+            int bidx = 0x7FFFFFFF;
+            for (int k = k0; k < k1; ++k)
+            {
+              si += cntI[k];
+              sj += cntJ[k];
+              const long long d = llabs(llabs(iTot - si + sj) - llabs(jTot - sj + si));
+              if (d < bd)
+              {
+                bd = d;
+                bidx = k;
+              }
+              cntI[k] = 0u;
+              cntJ[k] = 0u;
+            }
+  #pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+            {
+              long long od = __shfl_xor_sync(0xFFFFFFFFu, bd, o);
+              int oi = __shfl_xor_sync(0xFFFFFFFFu, bidx, o);
+              if (od < bd || (od == bd && oi < bidx))
+              {
+                bd = od;
+                bidx = oi;
+              }
+            }
+            if (lane == 0)
+            {
+              bestD[warp] = bd;
+              bestI[warp] = bidx;
+            }
+            __syncthreads();
+            bd = bestD[0];
+            bidx = bestI[0];
+            for (int k = 1; k < TREE_WARPS; ++k)
+              if (bestD[k] < bd || (bestD[k] == bd && bestI[k] < bidx))
+              {
+                bd = bestD[k];
+                bidx = bestI[k];
+              }
+            thr = dt_threshold_d2(bidx);
+          }
         }
         if (tid == 0)
           s_thr = thr;

@@ -130,7 +130,7 @@ struct mci_ctx
   int nPairs = 0, capPairs = 0;
   // interpolation
   DBuf dJobBlob, dArena, dScratch, dBigHist, dSlab, dNodes, dLevelCounts, dArenaTop, dTrans;
-  DBuf dWork, dItems, dLevelScratch, dHist, dDtBig, dDtCounters, dEmit, dArrival;
+  DBuf dWork, dItems, dLevelScratch, dHist, dDtBig, dDtCounters, dEmit, dArrival, dCompose;
   unsigned long long emitBase = 0; // arena word where the mid shapes of the last run start
   int emitCap = 0;
   bool haveEmit = false;
@@ -341,7 +341,7 @@ extern "C"
                       &ctx->dPairs,    &ctx->dJobBlob,  &ctx->dArena,   &ctx->dScratch,   &ctx->dBigHist, &ctx->dSlab,
                       &ctx->dNodes,    &ctx->dLevelCounts, &ctx->dArenaTop, &ctx->dTrans,
                       &ctx->dWork, &ctx->dItems, &ctx->dLevelScratch, &ctx->dHist, &ctx->dDtBig, &ctx->dDtCounters,
-                      &ctx->dChunkBits, &ctx->dEmit, &ctx->dArrival };
+                      &ctx->dChunkBits, &ctx->dEmit, &ctx->dArrival, &ctx->dCompose };
     for (DBuf * b : bufs)
       b->release();
     recycle_events(ctx);
@@ -1453,6 +1453,23 @@ extern "C"
         P.VY = ctx->dims[1];
         P.VZ = ctx->dims[2];
         P.err = ctx->dErr;
+        // mid slices perpendicular to z are written by one compose pass after the recursion (one thread per voxel, no
+        // atomics) instead of compare-and-swap groups inside it; MCI_NO_COMPOSE=1 keeps the writes in the nodes (A/B)
+        static const bool useCompose = std::getenv("MCI_NO_COMPOSE") == nullptr;
+        P.composeAxis2 = useCompose ? 1 : 0;
+        int * composeTables = nullptr;
+        if (useCompose)
+        {
+          const size_t VZ = (size_t)ctx->dims[2];
+          const size_t nInts = 7 * VZ + 1 + (size_t)ctx->emitCap + 8;
+          CK(ctx->dCompose.ensure(nInts * sizeof(int)));
+          composeTables = (int *)ctx->dCompose.p;
+          CK(cudaMemsetAsync(composeTables, 0, (3 * VZ + 1) * sizeof(int), s));                           // count, start, fill
+          CK(cudaMemsetAsync(composeTables + 3 * VZ + 1, 0x7F, 4 * VZ * sizeof(int), s));                  // box: minima ...
+          // ... and maxima: k_compose_count takes atomicMax against them, so they must start below any coordinate
+          // (0x7F7F7F7F as a maximum would never move): the box rows are {min x, min y, max x, max y}
+          CK(cudaMemset2DAsync(composeTables + 3 * VZ + 1 + 2, 4 * sizeof(int), 0x80, 2 * sizeof(int), VZ, s));
+        }
         if (std::getenv("MCI_TREE_PROFILE"))
           CK(cudaMemsetAsync(P.scratch + (size_t)grid * perCta, 0, 64, s));
         launch_dt_tree(ctx->L, ctx->ptype, P, nRootNodes, grid, treeThreads);
@@ -1519,7 +1536,10 @@ extern "C"
           off += levelCap[d];
         }
       }
-      // k_dt_emit wrote the slices of axes 1 and 2; the trees perpendicular to x go x-run by x-run
+      if (!useLevels && std::getenv("MCI_NO_COMPOSE") == nullptr)
+        launch_compose_axis2(ctx->L, ctx->ptype, dEmitRecs, dEmitCount, ctx->emitCap, (uint32_t *)ctx->dArena.p + ctx->emitBase,
+                             (int *)ctx->dCompose.p, ctx->dIn, ctx->dOut, ctx->dims);
+      // slices of axis 1 were written by the nodes; the trees perpendicular to x go x-run by x-run
       launch_apply_axis0(ctx->L, ctx->ptype, (Axis0Group *)(jb + oGroups), (int)axis0Groups.size(), dEmitRecs, dSlots,
                          (uint32_t *)ctx->dArena.p + ctx->emitBase, ctx->dIn, ctx->dOut, ctx->dims);
     }

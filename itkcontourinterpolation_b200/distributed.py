@@ -512,11 +512,30 @@ class SlabShardedInterpolator:
         return out_slab
 
     # ---- resident mode --------------------------------------------------------------------------------------------
-    def load_slab(self, slab):
-        """slab: tensor [z1 - z0, Y, X] (host or device) = this rank's planes of the input volume"""
+    def load_slab(self, slab, ghost_lo=None, ghost_hi=None):
+        """slab: tensor [z1 - z0, Y, X] (host or device) = this rank's planes of the input volume.  ghost_lo / ghost_hi:
+        the plane just below / above the slab ([Y, X]); when the resident layout carries these ghost planes (both, or
+        the one that exists at a volume end) run_resident skips the halo exchange -- slice detection reads z +- 1."""
         with self.torch.cuda.stream(self.stream):
             self.buf_in[self._p(self.z0):self._p(self.z1)].copy_(slab, non_blocking=True)
+            if ghost_lo is not None and self.z0 > 0:
+                self.buf_in[self._p(self.z0 - 1)].copy_(ghost_lo, non_blocking=True)
+            if ghost_hi is not None and self.z1 < self.Z:
+                self.buf_in[self._p(self.z1)].copy_(ghost_hi, non_blocking=True)
         self.stream.synchronize()
+        self._ghosts_agreed = None
+        self.has_ghosts = (ghost_lo is not None or self.z0 == 0) and (ghost_hi is not None or self.z1 == self.Z)
+
+    def _all_have_ghosts(self):
+        """every rank must take the same branch (the halo exchange is a collective): agreed once, at the first run"""
+        if getattr(self, "_ghosts_agreed", None) is None:
+            mine = 1 if getattr(self, "has_ghosts", False) else 0
+            if self.world > 1:
+                t = self.torch.tensor([mine], dtype=self.torch.int32, device=self.device if self._nccl else "cpu")
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
+                mine = int(t.item())
+            self._ghosts_agreed = bool(mine)
+        return self._ghosts_agreed
 
     def output_slab(self):
         return self.buf_out[self._p(self.z0):self._p(self.z1)]
@@ -563,7 +582,9 @@ class SlabShardedInterpolator:
         bounds = self.bounds
         t = [time.perf_counter()]
         halos = [[z for z in (lo - 1, hi) if 0 <= z < self.Z and hi > lo] for lo, hi in bounds]
-        self._fetch_planes(halos)
+        ghosts = self._all_have_ghosts()
+        if not ghosts:
+            self._fetch_planes(halos)
         self.stream.synchronize()
         t.append(time.perf_counter())
         lab, sl = self._detect()
@@ -573,7 +594,7 @@ class SlabShardedInterpolator:
         segs = segments_of(slices, int(self.opt.label))
         plans = [plan_slab(segs, lo, hi) for lo, hi in bounds]
         zlo, zhi, _ = plans[self.rank]
-        if self._ensure_margin(zlo, zhi):
+        if self._ensure_margin(zlo, zhi) and not ghosts:
             self._fetch_planes(halos)
         extra = [[z for z in plans[q][2] if z not in halos[q]] for q in range(self.world)]
         self._fetch_planes(extra)

@@ -127,6 +127,10 @@ def _slab_worker(rank, world, port, name, q):
             st = dict(f.last_stats)
             f.load_slab(host[f.z0:f.z1])
             res = f.run_resident().cpu().numpy().view(np.uint16).copy()
+            # the same with ghost planes resident: no halo exchange
+            f.load_slab(host[f.z0:f.z1], host[f.z0 - 1] if f.z0 > 0 else None, host[f.z1] if f.z1 < Z else None)
+            res2 = f.run_resident().cpu().numpy().view(np.uint16).copy()
+            assert np.array_equal(res, res2)
             q.put((rank, f.z0, f.z1, e2e, res, st, f.nvlink_bytes))
         finally:
             f.close()

@@ -28,7 +28,8 @@ def main():
     f = SlabShardedInterpolator(lr, dims, torch.uint16, margin=9)
     host = torch.from_numpy(win).pin_memory()
     out = torch.empty((z1 - z0, dims[1], dims[0]), dtype=torch.uint16).pin_memory()
-    f.load_slab(host[z0 - w0:z1 - w0])
+    ghosts = len(sys.argv) > 3 and sys.argv[3] == "ghosts"
+    f.load_slab(host[z0 - w0:z1 - w0], host[z0 - 1 - w0] if ghosts and z0 > 0 else None, host[z1 - w0] if ghosts and z1 < dims[2] else None)
     for k in range(steps):
         dist.barrier()
         t0 = time.perf_counter()

@@ -103,6 +103,23 @@ def test_int16_and_uint8_pixel_types(flt):
                 assert_same(run_gpu(flt, v, **kw), O.interpolate(v, **kw), "%s %s" % (name, dt.__name__))
 
 
+def test_negative_int16_labels_follow_the_write_rule(flt):
+    # Image<short,3> may hold negative labels: they are detected and interpolated like any other (X:146, X:1459-1521),
+    # but `out < label` (X:757) never holds on the zero background, so only positive labels reach the output; where a
+    # negative and a positive label meet, the positive one wins.  Slices along z go through the compose pass.
+    h = cases.handcrafted()
+    v = h["DoubleTwoLabelBranching"].astype(np.int16)
+    v[v == 2] = -3
+    w = h["OneToThree"].astype(np.int16)
+    w[w == 3] = -7
+    for vol in (v, w):
+        for algo in ("D", "C"):
+            kw = cases.ALGOS[algo]
+            out = run_gpu(flt, vol, **kw)
+            assert_same(out, O.interpolate(vol, **kw), "negative labels " + algo)
+    assert np.array_equal(run_gpu(flt, w), w)  # nothing but a negative label: the output is the input
+
+
 def test_int16_distance_bin_overflow_fails_cleanly(flt):
     # a distance of 3276.8 pixels or more makes `short dist = 10 * sdf` negative: the reference indexes out of
     # bounds (X:431-437); both the oracle and the CUDA path report an error instead

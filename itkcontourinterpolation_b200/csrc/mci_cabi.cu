@@ -134,6 +134,7 @@ struct mci_ctx
   unsigned long long emitBase = 0; // arena word where the mid shapes of the last run start
   int emitCap = 0;
   bool haveEmit = false;
+  int axisJobs[3] = { 0, 0, 0 }; // jobs of the current mci_interpolate call per slice axis
   bool histClean = false, dtBigClean = false;
   int bigHistGrid = 0;
   int nJobs = 0;
@@ -1057,6 +1058,29 @@ extern "C"
     return d;
   }
 
+  // Volume writes of the mid slices perpendicular to z, then of those perpendicular to y (two passes: a voxel can lie
+  // on slices of both kinds, and a pass assumes it is the only writer): tables prepared here, kernels in mci_dt.cu.
+  static int compose_axes(mci_ctx * ctx, const EmitRec * recs, const int * nrecsDev)
+  {
+    cudaStream_t s = ctx->L.stream;
+    const size_t maxPlanes = (size_t)std::max(ctx->dims[1], ctx->dims[2]);
+    CK(ctx->dCompose.ensure((7 * maxPlanes + 1 + (size_t)ctx->emitCap + 8) * sizeof(int)));
+    int * tables = (int *)ctx->dCompose.p;
+    for (int axis = 2; axis >= 1; --axis)
+    {
+      if (!ctx->axisJobs[axis])
+        continue; // no slices perpendicular to this axis in the run
+      const size_t nP = (size_t)ctx->dims[axis];
+      CK(cudaMemsetAsync(tables, 0, (3 * nP + 1) * sizeof(int), s));         // count, start, fill
+      CK(cudaMemsetAsync(tables + 3 * nP + 1, 0x7F, 4 * nP * sizeof(int), s)); // box rows {min x, min y, max x, max y}: minima ...
+      // ... and maxima, which k_compose_count raises with atomicMax: they must start below any coordinate
+      CK(cudaMemset2DAsync(tables + 3 * nP + 1 + 2, 4 * sizeof(int), 0x80, 2 * sizeof(int), nP, s));
+      launch_compose(ctx->L, ctx->ptype, axis, recs, nrecsDev, ctx->emitCap, (const uint32_t *)ctx->dArena.p + ctx->emitBase, tables,
+                     ctx->dIn, ctx->dOut, ctx->dims);
+    }
+    return MCI_OK;
+  }
+
   int mci_interpolate(mci_ctx * ctx, int32_t njobs, const mci_job * jobs, const int32_t * b_ids, int32_t n_b_ids,
                       const mci_params * prm)
   {
@@ -1065,6 +1089,7 @@ extern "C"
     CK(cudaSetDevice(ctx->device));
     ctx->nJobs = njobs;
     ctx->haveEmit = false;
+    ctx->axisJobs[0] = ctx->axisJobs[1] = ctx->axisJobs[2] = 0;
     if (njobs == 0)
       return MCI_OK;
     int rc = fetch_stats(ctx);
@@ -1141,6 +1166,7 @@ extern "C"
       R.posA = jb.pos_a;
       R.posB = jb.pos_b;
       R.axis = SA.axis;
+      ctx->axisJobs[SA.axis]++;
       R.label = SA.label;
       R.rootOff = nRootNodes;
       R.slot0 = -1;
@@ -1457,19 +1483,6 @@ extern "C"
         // atomics) instead of compare-and-swap groups inside it; MCI_NO_COMPOSE=1 keeps the writes in the nodes (A/B)
         static const bool useCompose = std::getenv("MCI_NO_COMPOSE") == nullptr;
         P.composeAxis2 = useCompose ? 1 : 0;
-        int * composeTables = nullptr;
-        if (useCompose)
-        {
-          const size_t VZ = (size_t)ctx->dims[2];
-          const size_t nInts = 7 * VZ + 1 + (size_t)ctx->emitCap + 8;
-          CK(ctx->dCompose.ensure(nInts * sizeof(int)));
-          composeTables = (int *)ctx->dCompose.p;
-          CK(cudaMemsetAsync(composeTables, 0, (3 * VZ + 1) * sizeof(int), s));                           // count, start, fill
-          CK(cudaMemsetAsync(composeTables + 3 * VZ + 1, 0x7F, 4 * VZ * sizeof(int), s));                  // box: minima ...
-          // ... and maxima: k_compose_count takes atomicMax against them, so they must start below any coordinate
-          // (0x7F7F7F7F as a maximum would never move): the box rows are {min x, min y, max x, max y}
-          CK(cudaMemset2DAsync(composeTables + 3 * VZ + 1 + 2, 4 * sizeof(int), 0x80, 2 * sizeof(int), VZ, s));
-        }
         if (std::getenv("MCI_TREE_PROFILE"))
           CK(cudaMemsetAsync(P.scratch + (size_t)grid * perCta, 0, 64, s));
         launch_dt_tree(ctx->L, ctx->ptype, P, nRootNodes, grid, treeThreads);
@@ -1537,9 +1550,12 @@ extern "C"
         }
       }
       if (!useLevels && std::getenv("MCI_NO_COMPOSE") == nullptr)
-        launch_compose_axis2(ctx->L, ctx->ptype, dEmitRecs, dEmitCount, ctx->emitCap, (uint32_t *)ctx->dArena.p + ctx->emitBase,
-                             (int *)ctx->dCompose.p, ctx->dIn, ctx->dOut, ctx->dims);
-      // slices of axis 1 were written by the nodes; the trees perpendicular to x go x-run by x-run
+      {
+        int rc2 = compose_axes(ctx, dEmitRecs, dEmitCount);
+        if (rc2)
+          return rc2;
+      }
+      // the trees perpendicular to x go x-run by x-run
       launch_apply_axis0(ctx->L, ctx->ptype, (Axis0Group *)(jb + oGroups), (int)axis0Groups.size(), dEmitRecs, dSlots,
                          (uint32_t *)ctx->dArena.p + ctx->emitBase, ctx->dIn, ctx->dOut, ctx->dims);
     }
@@ -1576,9 +1592,17 @@ extern "C"
                      dEmitRecs, dEmitCount, ctx->emitCap, ctx->emitBase, ctx->dErr);
         off += levelCap[d];
       }
-      // the node kernel only stores the mid shapes; their volume writes (X:743-764) happen here in one grid-wide pass
-      launch_apply_masks(ctx->L, ctx->ptype, dEmitRecs, ctx->emitCap, dEmitCount, (uint32_t *)ctx->dArena.p + ctx->emitBase, ctx->dIn,
-                         ctx->dOut, ctx->dims, /*skipAxis0=*/1);
+      // the node kernel only stores the mid shapes; their volume writes (X:743-764) happen here: slices perpendicular to z
+      // and y through the compose passes (MCI_NO_COMPOSE=1: one grid-wide pass of compare-and-swap groups, as in round 1)
+      if (std::getenv("MCI_NO_COMPOSE") == nullptr)
+      {
+        int rc2 = compose_axes(ctx, dEmitRecs, dEmitCount);
+        if (rc2)
+          return rc2;
+      }
+      else
+        launch_apply_masks(ctx->L, ctx->ptype, dEmitRecs, ctx->emitCap, dEmitCount, (uint32_t *)ctx->dArena.p + ctx->emitBase, ctx->dIn,
+                           ctx->dOut, ctx->dims, /*skipAxis0=*/1);
       launch_apply_axis0(ctx->L, ctx->ptype, (Axis0Group *)(jb + oGroups), (int)axis0Groups.size(), dEmitRecs, dSlots,
                          (uint32_t *)ctx->dArena.p + ctx->emitBase, ctx->dIn, ctx->dOut, ctx->dims);
     }

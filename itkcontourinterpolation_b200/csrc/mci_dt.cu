@@ -2294,8 +2294,8 @@ k_dt_tree(const TreeParams P)
             atomicAdd(P.rootNext + 3, n);
           }
         }
-        // slices perpendicular to z: the compose pass after this kernel writes them, one thread per voxel
-        const int mwordsW = (P.composeAxis2 && axis == 2) ? 0 : mwords;
+        // slices perpendicular to z and to y: the compose passes after this kernel write them, no atomics
+        const int mwordsW = (P.composeAxis2 && axis != 0) ? 0 : mwords;
         for (int wBeg = warp * 32; wBeg < mwordsW; wBeg += TREE_WARPS * 32)
         {
           const int wEnd = min(mwords, wBeg + 32);
@@ -2463,14 +2463,14 @@ struct ComposeTables
 };
 
 __global__ void __launch_bounds__(256)
-k_compose_count(const EmitRec * __restrict__ recs, const int * __restrict__ nrecsDev, int cap, ComposeTables t, int VZ)
+k_compose_count(const EmitRec * __restrict__ recs, const int * __restrict__ nrecsDev, int cap, ComposeTables t, int VZ, int axis)
 {
   pdl_wait();
   const int n = min(*nrecsDev, cap);
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
   {
     const EmitRec r = recs[e];
-    if (r.axis != 2 || (unsigned)r.mid >= (unsigned)VZ)
+    if (r.axis != axis || (unsigned)r.mid >= (unsigned)VZ)
       continue;
     atomicAdd(&t.count[r.mid], 1);
     atomicMin(&t.box[4 * r.mid + 0], r.M.x0);
@@ -2520,14 +2520,14 @@ k_compose_scan(ComposeTables t, int VZ)
 }
 
 __global__ void __launch_bounds__(256)
-k_compose_fill(const EmitRec * __restrict__ recs, const int * __restrict__ nrecsDev, int cap, ComposeTables t, int VZ)
+k_compose_fill(const EmitRec * __restrict__ recs, const int * __restrict__ nrecsDev, int cap, ComposeTables t, int VZ, int axis)
 {
   pdl_wait();
   const int n = min(*nrecsDev, cap);
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
   {
     const EmitRec r = recs[e];
-    if (r.axis != 2 || (unsigned)r.mid >= (unsigned)VZ)
+    if (r.axis != axis || (unsigned)r.mid >= (unsigned)VZ)
       continue;
     t.recs[t.start[r.mid] + atomicAdd(&t.fill[r.mid], 1)] = e;
   }
@@ -2547,7 +2547,7 @@ struct ComposeEntry
 template <typename T>
 __global__ void __launch_bounds__(32 * COMPOSE_ROWS)
 k_compose(const EmitRec * __restrict__ recs, const uint32_t * __restrict__ words, ComposeTables t, const T * __restrict__ in, T * out,
-          long long VX, long long VY)
+          long long VX, long long VY, int axis)
 {
   pdl_wait();
   __shared__ ComposeEntry s_list[COMPOSE_ROWS][COMPOSE_LIST];
@@ -2562,7 +2562,11 @@ k_compose(const EmitRec * __restrict__ recs, const uint32_t * __restrict__ words
     return; // no block-wide barrier below
   const int * list = t.recs + t.start[z];
   ComposeEntry * L = s_list[warp];
-  const unsigned long long rowBase = ((unsigned long long)z * (unsigned long long)VY + (unsigned long long)y) * (unsigned long long)VX;
+  // slices perpendicular to z (axis 2): plane = z, row = y; perpendicular to y (axis 1): plane = y, row = z (X:681-693);
+  // either way a shape's bits run along x, i.e. along contiguous voxels
+  const unsigned long long rowBase = axis == 2
+                                       ? ((unsigned long long)z * (unsigned long long)VY + (unsigned long long)y) * (unsigned long long)VX
+                                       : ((unsigned long long)y * (unsigned long long)VY + (unsigned long long)z) * (unsigned long long)VX;
   constexpr int VPQ = 8 / sizeof(T);
   const bool vec = (VX % VPQ) == 0;
   for (int first = 0; first < n;)
@@ -2655,40 +2659,41 @@ k_compose(const EmitRec * __restrict__ recs, const uint32_t * __restrict__ words
 }
 
 void
-launch_compose_axis2(Launch & L, int ptype, const EmitRec * recs, const int * nrecsDev, int cap, const uint32_t * words, int * tables,
-                     const void * in, void * out, const long long dims[3])
+launch_compose(Launch & L, int ptype, int axis, const EmitRec * recs, const int * nrecsDev, int cap, const uint32_t * words, int * tables,
+               const void * in, void * out, const long long dims[3])
 {
-  if (cap <= 0)
+  if (cap <= 0 || (axis != 1 && axis != 2))
     return;
-  const int VZ = (int)dims[2];
+  const int nPlanes = (int)dims[axis];                 // slice positions along the axis
+  const long long nRows = axis == 2 ? dims[1] : dims[2]; // second coordinate of a slice
   ComposeTables t;
   t.count = tables;
-  t.start = t.count + VZ;
-  t.fill = t.start + VZ + 1;
-  t.box = t.fill + VZ;
-  t.recs = t.box + 4 * VZ;
+  t.start = t.count + nPlanes;
+  t.fill = t.start + nPlanes + 1;
+  t.box = t.fill + nPlanes;
+  t.recs = t.box + 4 * nPlanes;
   const int g = std::max(1, std::min((cap + 255) / 256, L.sms * 4));
   L.pre("k_compose_count");
-  launch_pdl(k_compose_count, g, 256, 0, L.stream, recs, nrecsDev, cap, t, VZ);
+  launch_pdl(k_compose_count, g, 256, 0, L.stream, recs, nrecsDev, cap, t, nPlanes, axis);
   L.post("k_compose_count");
   L.pre("k_compose_scan");
-  launch_pdl(k_compose_scan, 1, 1024, 0, L.stream, t, VZ);
+  launch_pdl(k_compose_scan, 1, 1024, 0, L.stream, t, nPlanes);
   L.post("k_compose_scan");
   L.pre("k_compose_fill");
-  launch_pdl(k_compose_fill, g, 256, 0, L.stream, recs, nrecsDev, cap, t, VZ);
+  launch_pdl(k_compose_fill, g, 256, 0, L.stream, recs, nrecsDev, cap, t, nPlanes, axis);
   L.post("k_compose_fill");
-  const dim3 grid((unsigned)((dims[1] + COMPOSE_ROWS - 1) / COMPOSE_ROWS), (unsigned)VZ);
+  const dim3 grid((unsigned)((nRows + COMPOSE_ROWS - 1) / COMPOSE_ROWS), (unsigned)nPlanes);
   L.pre("k_compose");
   switch (ptype)
   {
     case MCI_U8:
-      launch_pdl(k_compose<uint8_t>, grid, 32 * COMPOSE_ROWS, 0, L.stream, recs, words, t, (const uint8_t *)in, (uint8_t *)out, dims[0], dims[1]);
+      launch_pdl(k_compose<uint8_t>, grid, 32 * COMPOSE_ROWS, 0, L.stream, recs, words, t, (const uint8_t *)in, (uint8_t *)out, dims[0], dims[1], axis);
       break;
     case MCI_U16:
-      launch_pdl(k_compose<uint16_t>, grid, 32 * COMPOSE_ROWS, 0, L.stream, recs, words, t, (const uint16_t *)in, (uint16_t *)out, dims[0], dims[1]);
+      launch_pdl(k_compose<uint16_t>, grid, 32 * COMPOSE_ROWS, 0, L.stream, recs, words, t, (const uint16_t *)in, (uint16_t *)out, dims[0], dims[1], axis);
       break;
     default:
-      launch_pdl(k_compose<int16_t>, grid, 32 * COMPOSE_ROWS, 0, L.stream, recs, words, t, (const int16_t *)in, (int16_t *)out, dims[0], dims[1]);
+      launch_pdl(k_compose<int16_t>, grid, 32 * COMPOSE_ROWS, 0, L.stream, recs, words, t, (const int16_t *)in, (int16_t *)out, dims[0], dims[1], axis);
   }
   L.post("k_compose");
 }

@@ -184,13 +184,14 @@ struct TreeParams
   const void * in;
   void * out;
   long long VX, VY, VZ;
-  int composeAxis2; // 1: slices perpendicular to z are written by the compose pass that follows, not by the nodes
+  int composeAxis2; // 1: slices perpendicular to z and y are written by the compose passes that follow, not by the nodes
   int * err;
 };
 void launch_dt_tree(Launch & L, int ptype, const TreeParams & P, int nRootsMax, int grid, int threads);
-// volume writes of all mid slices perpendicular to z, one thread per voxel (tables: 7 * VZ + 1 + cap ints, zeroed / box preset by the caller)
-void launch_compose_axis2(Launch & L, int ptype, const EmitRec * recs, const int * nrecsDev, int cap, const uint32_t * words, int * tables,
-                          const void * in, void * out, const long long dims[3]);
+// volume writes of all mid slices perpendicular to `axis` (1 or 2), no atomics (tables: 7 * dims[axis] + 1 + cap ints,
+// prepared by the caller: counts / starts / fills zero, box minima INT_MAX-like, maxima INT_MIN-like)
+void launch_compose(Launch & L, int ptype, int axis, const EmitRec * recs, const int * nrecsDev, int cap, const uint32_t * words,
+                    int * tables, const void * in, void * out, const long long dims[3]);
 
 long long median_tile_count(const long long dims[3]);
 void launch_median3d(Launch & L, int ptype, const void * in, void * out, const long long dims[3], int radius, unsigned * summary);

@@ -1443,9 +1443,12 @@ extern "C"
         // one CTA per recursion tree (k_dt_tree): a node's rows live in shared memory when they fit, else in the
         // CTA's own slice of global scratch
         const u64 perCta = 4 * maxNodeWords + 64;
-        // few nodes: one 1024-thread CTA per SM (the launch lasts as long as the deepest chain of its biggest nodes;
-        // C3: 0.37 vs 0.41 ms); many nodes: two 512-thread CTAs per SM (C5: 5.0 vs 6.5 ms)
-        const int treeThreads = nodeTotal <= 8ll * ctx->L.sms ? 1024 : 512;
+        // few nodes: one 1024-thread CTA per SM -- every phase of a node twice as wide, the launch lasts as long as the
+        // chains of its biggest nodes; many nodes: two 512-thread CTAs per SM.  Measured k_dt_tree, 1024 / 512 threads:
+        // 940 nodes (C3) 0.24 / 0.29 ms; 2 300 nodes (one of eight C5 slabs) 0.79 / 1.17; 5 000 nodes (one of four)
+        // 1.02 / 0.96; 9 000 nodes 1.75 / 1.64; 17 900 nodes (C5) 3.29 / 2.56
+        static const char * forceWidth = std::getenv("MCI_TREE_THREADS"); // A/B runs: 512 or 1024
+        const int treeThreads = forceWidth ? (std::atoi(forceWidth) >= 1024 ? 1024 : 512) : (nodeTotal <= 28ll * ctx->L.sms ? 1024 : 512);
         int grid = (int)std::max<long long>(1, std::min<long long>(nodeTotal, treeThreads == 1024 ? ctx->L.sms : treeGridMax));
         while (grid > 1 && (u64)grid * perCta * 4 > (u64(2) << 30))
           grid = (grid + 1) / 2;

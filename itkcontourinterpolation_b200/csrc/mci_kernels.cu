@@ -1207,8 +1207,12 @@ launch_align(Launch & L, const AlignJob * jobs, int njobs, const MaskRef * refs,
   L.ensure_max_smem(k_align, 1, L.maxSmem - 8192); // static shared memory (replay table, shape headers) takes ~5 KB
   int grid = std::min(njobs, L.sms * 8);
   // at most one job per SM: the launch lasts as long as its slowest job, and more warps shorten every scoring wave;
-  // many jobs per SM: two smaller CTAs per SM keep the SM busy while one of them replays its queue
-  const int threads = njobs > L.sms ? ALIGN_THREADS / 2 : ALIGN_THREADS;
+  // many jobs per SM: two smaller CTAs per SM keep the SM busy while one of them replays its queue -- but only if two
+  // of them fit: with large search regions (visited bitmap + queue + staged shapes beyond half an SM's shared memory)
+  // a second CTA would not be resident anyway, and half-width CTAs would leave half the SM idle
+  const int smemPerCta = smemBytes + ALIGN_MASK_WORDS * 4 + 6 * 1024;
+  const bool twoFit = 2 * smemPerCta <= L.maxSmem;
+  const int threads = (njobs > L.sms && twoFit) ? ALIGN_THREADS / 2 : ALIGN_THREADS;
   L.pre("k_align");
   launch_pdl(k_align, grid, threads, smemBytes + ALIGN_MASK_WORDS * 4, L.stream, jobs, njobs, refs, arena, gscratch, heuristic,
              result, dbg, err);

@@ -1,5 +1,6 @@
 // mci_kernels.cu -- kernels + launch wrappers (see mci_kernels.cuh for helpers).
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 #include "mci_kernels.cuh"
 #include "mci_launch.h"
@@ -440,6 +441,99 @@ k_compact_labels(const int * __restrict__ bbox, int nl, const uint32_t * __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same streaming pass with the copy done by the TMA unit (sm_100a bulk async copies): one thread per CTA
+// issues `cp.async.bulk` global -> shared (completion counted on an mbarrier) and shared -> global (bulk groups),
+// COPY_STAGES tiles of 16 KB in flight per CTA, while the warps only read each tile from shared memory to build the
+// "chunk holds a label" bitmap.  No voxel passes through a register on its way from `in` to `out`.
+// ------------------------------------------------------------------------------------------------
+#define COPY_TILE 16384 // bytes per tile: 1024 chunks of 16 bytes = 32 bitmap words
+#define COPY_STAGES 4
+#define COPY_THREADS 128
+
+__device__ __forceinline__ uint32_t
+smem_u32(const void * p)
+{
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__global__ void __launch_bounds__(COPY_THREADS)
+k_copy_flag_tma(const uint8_t * __restrict__ in, uint8_t * __restrict__ out, long long nTiles, uint32_t * __restrict__ chunkBits)
+{
+  extern __shared__ __align__(128) uint8_t tile_smem[];
+  __shared__ __align__(8) unsigned long long full[COPY_STAGES];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0)
+  {
+    for (int s = 0; s < COPY_STAGES; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[s])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const long long first = blockIdx.x, step = gridDim.x;
+  const long long mine = first < nTiles ? (nTiles - first + step - 1) / step : 0;
+  auto issue_load = [&](long long k) {
+    const int s = (int)(k % COPY_STAGES);
+    const uint32_t bar = smem_u32(&full[s]), dst = smem_u32(tile_smem + (size_t)s * COPY_TILE);
+    const uint8_t * src = in + (first + k * step) * (long long)COPY_TILE;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(COPY_TILE) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(COPY_TILE), "r"(bar)
+                 : "memory");
+  };
+  if (tid == 0)
+    for (long long k = 0; k < COPY_STAGES - 1 && k < mine; ++k)
+      issue_load(k);
+  for (long long k = 0; k < mine; ++k)
+  {
+    const int s = (int)(k % COPY_STAGES);
+    const uint32_t parity = (uint32_t)((k / COPY_STAGES) & 1);
+    // wait for the tile
+    {
+      const uint32_t bar = smem_u32(&full[s]);
+      asm volatile("{\n"
+                   ".reg .pred p;\n"
+                   "WAIT_TILE:\n"
+                   "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                   "@p bra DONE_TILE;\n"
+                   "bra WAIT_TILE;\n"
+                   "DONE_TILE:\n"
+                   "}" ::"r"(bar),
+                   "r"(parity)
+                   : "memory");
+    }
+    // bitmap: one ballot word per 32 chunks, 8 words per warp
+    const uint4 * t4 = reinterpret_cast<const uint4 *>(tile_smem + (size_t)s * COPY_TILE);
+    const long long tileIdx = first + k * step;
+#pragma unroll
+    for (int w = 0; w < (COPY_TILE / 512) / (COPY_THREADS / 32); ++w)
+    {
+      const int word = warp * ((COPY_TILE / 512) / (COPY_THREADS / 32)) + w;
+      const uint4 q = t4[word * 32 + lane];
+      const unsigned vote = __ballot_sync(0xFFFFFFFFu, (q.x | q.y | q.z | q.w) != 0u);
+      if (lane == 0)
+        chunkBits[tileIdx * (COPY_TILE / 512) + word] = vote;
+    }
+    __syncthreads(); // every warp has read the tile
+    if (tid == 0)
+    {
+      const uint32_t src = smem_u32(tile_smem + (size_t)s * COPY_TILE);
+      uint8_t * dst = out + tileIdx * (long long)COPY_TILE;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(COPY_TILE) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      // the stage consumed one iteration ago is loaded next: its store must have finished READING shared memory
+      if (k + COPY_STAGES - 1 < mine)
+      {
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        issue_load(k + COPY_STAGES - 1);
+      }
+    }
+  }
+  if (tid == 0)
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 void
 launch_detect(Launch & L, int ptype, const void * in, void * out, const long long dims[3], int axisSel, int * bbox, int nl,
               uint32_t * sliceBits, int wordsPerLabel, int wo1, int wo2, uint32_t * chunkBits)
@@ -451,16 +545,46 @@ launch_detect(Launch & L, int ptype, const void * in, void * out, const long lon
   int gridA = (int)std::max<long long>(1, std::min<long long>((nchunks + 4 * 256 - 1) / (4 * 256), (long long)L.sms * 8));
   int gridB = (int)std::max<long long>(1, std::min<long long>((nWords + 7) / 8, (long long)L.sms * 8));
   L.pre("k_copy_flag");
-  switch (ptype)
+  static const bool useTma = std::getenv("MCI_NO_TMA_COPY") == nullptr;
+  long long doneVox = 0;
+  // (volumes below half a gigabyte are over before the bulk pipeline has filled: C3, 134 MB, 49 us against 47 us for the
+  // register path; C5, 8.6 GB, 2.79 against 3.05 ms = 0.94 against 0.86 of the measured copy bandwidth)
+  if (useTma && out && n * elt >= (512ll << 20))
   {
-    case MCI_U8:
-      k_copy_flag<uint8_t><<<gridA, 256, 0, L.stream>>>((const uint8_t *)in, (uint8_t *)out, n, chunkBits);
-      break;
-    case MCI_U16:
-      k_copy_flag<uint16_t><<<gridA, 256, 0, L.stream>>>((const uint16_t *)in, (uint16_t *)out, n, chunkBits);
-      break;
-    default:
-      k_copy_flag<int16_t><<<gridA, 256, 0, L.stream>>>((const int16_t *)in, (int16_t *)out, n, chunkBits);
+    // full 16 KB tiles through the TMA unit; what is left (less than a tile) goes through the register path below
+    const long long nTiles = (n * elt) / COPY_TILE;
+    if (nTiles > 0)
+    {
+      static bool attr = false;
+      if (!attr)
+      {
+        cudaFuncSetAttribute(k_copy_flag_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, COPY_STAGES * COPY_TILE);
+        attr = true;
+      }
+      const int gridT = (int)std::min<long long>(nTiles, (long long)L.sms * 3);
+      k_copy_flag_tma<<<gridT, COPY_THREADS, COPY_STAGES * COPY_TILE, L.stream>>>((const uint8_t *)in, (uint8_t *)out, nTiles, chunkBits);
+      doneVox = nTiles * (COPY_TILE / elt);
+    }
+  }
+  if (doneVox < n)
+  {
+    const char * inT = (const char *)in + doneVox * elt;
+    char * outT = out ? (char *)out + doneVox * elt : nullptr;
+    uint32_t * bitsT = chunkBits + doneVox / (16 / elt) / 32;
+    const long long nT = n - doneVox;
+    const long long nchT = nT / (16 / elt);
+    gridA = (int)std::max<long long>(1, std::min<long long>((nchT + 4 * 256 - 1) / (4 * 256), (long long)L.sms * 8));
+    switch (ptype)
+    {
+      case MCI_U8:
+        k_copy_flag<uint8_t><<<gridA, 256, 0, L.stream>>>((const uint8_t *)inT, (uint8_t *)outT, nT, bitsT);
+        break;
+      case MCI_U16:
+        k_copy_flag<uint16_t><<<gridA, 256, 0, L.stream>>>((const uint16_t *)inT, (uint16_t *)outT, nT, bitsT);
+        break;
+      default:
+        k_copy_flag<int16_t><<<gridA, 256, 0, L.stream>>>((const int16_t *)inT, (int16_t *)outT, nT, bitsT);
+    }
   }
   L.post("k_copy_flag");
   L.pre("k_detect_marked");

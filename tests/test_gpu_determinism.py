@@ -59,3 +59,21 @@ def test_concurrent_contexts_do_not_disturb_each_other():
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("env", [{"MCI_DT_LEVELS": "1"}, {"MCI_NO_COMPOSE": "1"}, {"MCI_TREE_THREADS": "512"}, {"MCI_TREE_THREADS": "1024"}])
+def test_alternative_code_paths_kept_for_ab_runs_still_match(env):
+    """The round-1 level-synchronous recursion, in-node volume writes and both widths of k_dt_tree stay selectable by
+    environment variable (DESIGN.md section 3 quotes A/B numbers taken with them): they must keep giving the same bits.
+    The variables are read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r); import cases\n"
+            "from itkcontourinterpolation_b200 import morphological_contour_interpolator as f\n"
+            "from oracle import oracle_lib as O\n"
+            "h = cases.handcrafted(); vols = [h['OneToThree'], h['ThreeAxis'], h['DriftOddGaps'], cases.synthetic_small()['C3'][0]]\n"
+            "bad = [k for k, v in enumerate(vols) if not np.array_equal(f(v), O.interpolate(v))]\n"
+            "sys.exit(1 if bad else 0)\n") % (os.path.dirname(cases.GOLDEN.rstrip('/')).rsplit('/tests', 1)[0], os.path.dirname(cases.GOLDEN))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (env, r.stderr[-2000:])

@@ -181,6 +181,28 @@ def test_slice_detection_phase(flt):
     assert got == set(map(tuple, trip.tolist()))
 
 
+def test_streaming_pass_through_the_tma_unit_with_a_ragged_tail(flt):
+    # volumes of half a gigabyte and more are copied by cp.async.bulk in 16 KB tiles (k_copy_flag_tma), the remainder by
+    # the register path: a size that is not a multiple of the tile, labels sitting in the last tile and in the tail
+    X, Y, Z = 1031, 1021, 260                      # 547 MB of uint16, 273 691 660 voxels: 33 409 tiles + 8 184 bytes
+    vol = np.zeros((Z, Y, X), np.uint16)
+    vol[3, 100:140, 200:260] = 5
+    vol[11, 104:150, 190:250] = 5                  # one segment far from the end
+    vol[Z - 9, Y - 60:Y - 8, X - 70:X - 6] = 9
+    vol[Z - 1, Y - 50:Y - 1, X - 64:X - 1] = 9     # annotated slice in the very last plane: last tile + tail
+    vol[Z - 1, Y - 1, X - 5:X] = 9
+    flt.SetAxis(2); flt.SetLabel(0); flt.SetUseCustomSlicePositions(False)
+    flt.SetInput(vol)
+    table = flt.DetermineSliceOrientations()
+    got = set((a, l, s) for a, d in table.items() for l, ss in d.items() for s in ss)
+    assert got == {(2, 5, 3), (2, 5, 11), (2, 9, Z - 9), (2, 9, Z - 1)}
+    out = run_gpu(flt, vol, axis=2)
+    assert np.array_equal(out[vol != 0], vol[vol != 0])            # the copy, tail included
+    ref = O.interpolate(vol, axis=2, threads=os.cpu_count() or 1)
+    assert_same(out, ref, "ragged 547 MB volume")
+    assert (out != vol).any()
+
+
 def test_connected_components_phase_raster_numbering(flt):
     # phase-level ABI: component images must equal the oracle's (ITK numbering), 4- and 8-connected
     rng = np.random.default_rng(5)

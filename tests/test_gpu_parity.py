@@ -120,6 +120,24 @@ def test_negative_int16_labels_follow_the_write_rule(flt):
     assert np.array_equal(run_gpu(flt, w), w)  # nothing but a negative label: the output is the input
 
 
+def test_many_shapes_on_one_row_of_a_mid_slice(flt):
+    # 150 components of one label side by side: every mid slice holds 150 shapes crossing the same rows, more than the
+    # compose pass lists at once (COMPOSE_LIST = 64: several passes over the row), and with two labels interleaved the
+    # larger label must win where their interpolated shapes touch
+    n = 150
+    v = np.zeros((7, 24, 8 * n + 8), np.uint16)
+    for k in range(n):
+        x = 4 + 8 * k
+        lab = 3 if k % 2 else 9
+        v[0, 8:13, x:x + 5] = lab
+        v[6, 9:15, x + 1:x + 7] = lab
+    for algo in ("D", "C"):
+        kw = cases.ALGOS[algo]
+        out = run_gpu(flt, v, axis=2, **kw)
+        assert_same(out, O.interpolate(v, axis=2, **kw), "many shapes per row " + algo)
+        assert (out[3] != 0).sum() > 20 * n
+
+
 def test_int16_distance_bin_overflow_fails_cleanly(flt):
     # a distance of 3276.8 pixels or more makes `short dist = 10 * sdf` negative: the reference indexes out of
     # bounds (X:431-437); both the oracle and the CUDA path report an error instead

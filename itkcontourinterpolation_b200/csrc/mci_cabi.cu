@@ -1402,7 +1402,8 @@ extern "C"
     int * dCounts = (int *)ctx->dLevelCounts.p;
     if (prm->use_distance_transform)
     {
-      // distance-transform median: six grid-wide kernels per level (mci_dt.cu)
+      // distance-transform median: one persistent kernel over a device-side node queue + compose passes (mci_dt.cu);
+      // MCI_DT_LEVELS=1 selects the round-1 form, six grid-wide kernels per level
       long long maxLevelNodes = 0;
       u64 scratchCap = 0, itemCap = 0, hitemCap = 0;
       for (int d = 0; d < maxDepth; ++d)

@@ -1,6 +1,16 @@
-// mci_dt.cu -- one level of the Interpolate1to1 recursion with the distance-transform median
-// (reference X:556-793 with FindMedianImageDistances X:405-516), as six grid-wide kernels:
+// mci_dt.cu -- the Interpolate1to1 recursion with the distance-transform median
+// (reference X:556-793 with FindMedianImageDistances X:405-516).
 //
+// What runs (round 2):
+//   k_dt_tree          ONE persistent launch: a CTA takes a node from a global ready queue and runs it from start to
+//                      end (prep, d2 histograms, scan, median, mid shape), then publishes its children; rows and
+//                      histograms live in shared memory.  See the comment above the kernel.
+//   k_compose_*        volume writes of all mid slices perpendicular to z, then y: shapes binned by plane, one warp per
+//                      row, plain loads / stores (X:743-764 with X:1623-1636 folded in)
+//   k_apply_axis0      volume writes of the trees perpendicular to x, x-run by x-run
+//   k_apply_masks      replay of another GPU's mid slices (segment-sharded multi-GPU combine)
+//
+// Kept for A/B runs (MCI_DT_LEVELS=1), the round-1 form of the same recursion as six grid-wide kernels per level:
 //   k_dt_prep    per node : translation halving, union region, translate+binarise+AND into bit rows,
 //                           per-row extents of the intersection, work items            (X:570-666)
 //   k_dt_hist    per item : exact squared distance d2 of every (i xor j) pixel to the intersection,
@@ -9,9 +19,8 @@
 //   k_dt_median  per item : median = intersection | (xor pixels with d2 <= threshold), bounding box (X:497-515)
 //   k_dt_alloc   per node : crop/clip, allocate the mid shape, spawn the children        (X:679-729, 766-792)
 //   k_dt_emit    per item : store the mid shape, write it into the volume with the max rule (X:743-764)
-//
-// Work items are fixed-size word ranges of a node's bit rows, so the whole GPU works on a level no
-// matter how few nodes it has or how unequal they are.
+// (work items there are fixed-size word ranges of a node's bit rows, so the whole GPU works on a level no matter how
+// few nodes it has or how unequal they are; the price is 18 dependent launches for a gap of 8).
 #include <algorithm>
 #include <type_traits>
 #include "mci_kernels.cuh"

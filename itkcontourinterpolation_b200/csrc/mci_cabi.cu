@@ -192,17 +192,36 @@ struct TableSegs
 __global__ void __launch_bounds__(256) k_table_copy(TableSegs t)
 {
   pdl_wait();
-  for (int k = 0; k < t.n; ++k)
+  unsigned n[6], nmax = 0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
   {
-    const TableSeg sg = t.s[k];
-    unsigned n = sg.nWords;
-    if (sg.count)
+    n[k] = 0;
+    if (k < t.n)
     {
-      const long long want = (long long)max(*sg.count, 0) * sg.wordsPerElem;
-      n = (unsigned)min((long long)n, want);
+      n[k] = t.s[k].nWords;
+      if (t.s[k].count)
+      {
+        const long long want = (long long)max(*t.s[k].count, 0) * t.s[k].wordsPerElem;
+        n[k] = (unsigned)min((long long)n[k], want);
+      }
+      nmax = max(nmax, n[k]);
     }
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-      sg.dst[i] = sg.src[i];
+  }
+  // the loads of every segment are issued before the first store: a load from mapped host memory is a PCIe round
+  // trip, and the grid is sized for one word per thread and segment, so a launch costs one round trip, not one per
+  // segment and grid stride
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nmax; i += gridDim.x * blockDim.x)
+  {
+    uint32_t v[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      if (i < n[k])
+        v[k] = t.s[k].src[i];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      if (i < n[k])
+        t.s[k].dst[i] = v[k];
   }
 }
 struct TableCopy
@@ -225,7 +244,7 @@ struct TableCopy
   {
     if (!t.n)
       return;
-    const int grid = (int)std::max(1u, std::min((maxWords + 1023) / 1024, 64u));
+    const int grid = (int)std::max(1u, std::min((maxWords + 255) / 256, 1184u));
     L.pre("k_table_copy");
     launch_pdl(k_table_copy, grid, 256, 0, L.stream, t);
     L.post("k_table_copy");

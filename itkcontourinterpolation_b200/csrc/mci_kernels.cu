@@ -1348,16 +1348,183 @@ launch_align(Launch & L, const AlignJob * jobs, int njobs, const MaskRef * refs,
 //     lowest index (Interpolate1toN, X:824-986)
 // ================================================================================================
 #define SPLIT_THREADS 1024
+#define SPLIT_FAST_NB 4 // blobs the register-resident path holds per word
+
+// The usual case -- mask and both plane buffers in shared memory, at most SPLIT_FAST_NB blobs, at most WPT words per
+// thread: a thread keeps its words of every blob in REGISTERS for the whole growth and only the neighbour words come
+// from shared memory (LDS with compile-time plane strides instead of generic loads through a pointer that may be
+// global; about 40 instructions per word and step instead of about 200).  Same synchronous rule as below: every blob
+// dilates from the state at the beginning of the step, a free pixel reached by several blobs goes to the lowest index.
+template <int WPT, int NBMAX, bool BALL>
+__device__ __forceinline__ void
+split_fast(const SplitJob & J, const MaskRef & A, const int2 t, const MaskRef * __restrict__ refs, uint32_t * arena,
+           uint32_t * smem, const int words, const int nB, int * s_pixels, int * err)
+{
+  const int pitch = A.pitch, h = A.h;
+  const uint32_t * mask = smem;
+  uint32_t * buf0 = smem + words;
+  uint32_t * buf1 = smem + (size_t)(1 + nB) * words;
+  uint32_t own[WPT][NBMAX];
+  uint32_t m[WPT];
+  int rr[WPT], ww[WPT];
+  int c = 0;
+#pragma unroll
+  for (int j = 0; j < WPT; ++j)
+  {
+    const int idx = threadIdx.x + j * blockDim.x;
+    const bool has = idx < words;
+    rr[j] = has ? idx / pitch : 0;
+    ww[j] = has ? idx - rr[j] * pitch : 0;
+    m[j] = has ? mask[idx] : 0u;
+    c += __popc(m[j]);
+#pragma unroll
+    for (int k = 0; k < NBMAX; ++k)
+    {
+      own[j][k] = 0u;
+      if (k < nB && has)
+      {
+        // seeds: pixels of the mask whose translate lies in component k of the other slice (X:871-892)
+        const MaskRef B = refs[J.bRef + k];
+        own[j][k] = m[j] ? (m[j] & mask_word(arena, B, A.y0 + rr[j] + t.y, A.x0 + 32 * ww[j] + t.x)) : 0u;
+        buf0[k * words + idx] = own[j][k];
+      }
+    }
+  }
+  if (c)
+    atomicAdd(s_pixels, c);
+  __syncthreads();
+  const int maxSteps = *s_pixels + 1;
+  unsigned settled = 0; // bit j: my j-th word has no free pixel left and both buffers hold its final planes
+#pragma unroll
+  for (int j = 0; j < WPT; ++j)
+    if (threadIdx.x + j * blockDim.x >= words)
+      settled |= 1u << j;
+  int pending = 1;
+  const uint32_t * C = buf0;
+  uint32_t * N = buf1;
+  for (int step = 0; step < maxSteps && pending; ++step)
+  {
+    int flag = 0;
+#pragma unroll
+    for (int j = 0; j < WPT; ++j)
+    {
+      if ((settled >> j) & 1u)
+        continue;
+      const int idx = threadIdx.x + j * blockDim.x;
+      const bool up = rr[j] > 0, dn = rr[j] + 1 < h, lf = ww[j] > 0, rt = ww[j] + 1 < pitch;
+      uint32_t owned = 0;
+#pragma unroll
+      for (int k = 0; k < NBMAX; ++k)
+        owned |= own[j][k];
+      const uint32_t freeBits = m[j] & ~owned;
+      // neighbour words of every blob first (no branch between them: the loads of all blobs are in flight together;
+      // an absent blob loads nothing, holds no pixel and therefore grows nowhere)
+      uint32_t nu[NBMAX], nd[NBMAX], nl[NBMAX], nr[NBMAX];
+#pragma unroll
+      for (int k = 0; k < NBMAX; ++k)
+      {
+        const bool on = k < nB;
+        const uint32_t * p = C + k * words + idx;
+        nu[k] = (on && up) ? p[-pitch] : 0u;
+        nd[k] = (on && dn) ? p[pitch] : 0u;
+        nl[k] = (on && lf) ? p[-1] : 0u;
+        nr[k] = (on && rt) ? p[1] : 0u;
+        if (BALL)
+        {
+          nl[k] |= ((on && up && lf) ? p[-pitch - 1] : 0u) | ((on && dn && lf) ? p[pitch - 1] : 0u);
+          nr[k] |= ((on && up && rt) ? p[-pitch + 1] : 0u) | ((on && dn && rt) ? p[pitch + 1] : 0u);
+        }
+      }
+      uint32_t taken = 0;
+#pragma unroll
+      for (int k = 0; k < NBMAX; ++k)
+      {
+        const uint32_t cc = own[j][k];
+        const uint32_t v = BALL ? (cc | nu[k] | nd[k]) : cc;
+        uint32_t g = v | (v << 1) | (v >> 1) | (nl[k] >> 31) | (nr[k] << 31);
+        if (!BALL)
+          g |= nu[k] | nd[k];
+        g &= freeBits & ~taken;
+        own[j][k] = cc | g;
+        if (k < nB)
+          N[k * words + idx] = cc | g;
+        taken |= g;
+      }
+      if (freeBits & ~taken)
+        flag = 1;
+      if (!freeBits)
+        settled |= 1u << j;
+    }
+    pending = __syncthreads_or(flag);
+    const uint32_t * sw = C;
+    C = N;
+    N = const_cast<uint32_t *>(sw);
+  }
+  if (pending && threadIdx.x == 0)
+    atomicMax(err, ERR_SPLIT_STUCK);
+#pragma unroll
+  for (int j = 0; j < WPT; ++j)
+  {
+    const int idx = threadIdx.x + j * blockDim.x;
+    if (idx < words)
+    {
+#pragma unroll
+      for (int k = 0; k < NBMAX; ++k)
+        if (k < nB)
+          arena[refs[J.outRef + k].off + idx] = own[j][k];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(SPLIT_THREADS)
 k_split(const SplitJob * __restrict__ jobs, const MaskRef * __restrict__ refs, uint32_t * arena, uint32_t * gscratch,
-        const int2 * __restrict__ trans, int ball, int smemWords, int * err)
+        const int2 * __restrict__ trans, int ball, int smemWords, int fastPath, int * err)
 {
   extern __shared__ uint32_t smem[];
+  __shared__ int s_pixels;
   const SplitJob J = jobs[blockIdx.x];
   const MaskRef A = refs[J.aRef];
   const int2 t = trans[J.job];
   const int words = A.h * A.pitch;
   const int nB = J.nB;
+  if (fastPath && nB <= SPLIT_FAST_NB && (long long)(1 + 2 * nB) * words <= smemWords && words <= 4 * (int)blockDim.x)
+  {
+    for (int idx = threadIdx.x; idx < words; idx += blockDim.x)
+      smem[idx] = arena[A.off + idx];
+    if (threadIdx.x == 0)
+      s_pixels = 0;
+    __syncthreads();
+    const bool one = words <= (int)blockDim.x; // one word per thread (else up to four; absent words start settled)
+#define SPLIT_CASE(NBMAX)                                                                        \
+  if (ball)                                                                                      \
+  {                                                                                              \
+    if (one)                                                                                     \
+      split_fast<1, NBMAX, true>(J, A, t, refs, arena, smem, words, nB, &s_pixels, err);         \
+    else                                                                                         \
+      split_fast<4, NBMAX, true>(J, A, t, refs, arena, smem, words, nB, &s_pixels, err);         \
+  }                                                                                              \
+  else                                                                                           \
+  {                                                                                              \
+    if (one)                                                                                     \
+      split_fast<1, NBMAX, false>(J, A, t, refs, arena, smem, words, nB, &s_pixels, err);        \
+    else                                                                                         \
+      split_fast<4, NBMAX, false>(J, A, t, refs, arena, smem, words, nB, &s_pixels, err);        \
+  }
+    if (nB <= 2)
+    {
+      SPLIT_CASE(2)
+    }
+    else if (nB == 3)
+    {
+      SPLIT_CASE(3)
+    }
+    else
+    {
+      SPLIT_CASE(4)
+    }
+#undef SPLIT_CASE
+    return;
+  }
   // planes: mask | cur[nB] | nxt[nB]; in shared memory when they fit, else mask in the arena and the
   // ping-pong planes in the arena (final home) and global scratch
   const bool inSmem = (long long)(1 + 2 * nB) * words <= smemWords;
@@ -1392,7 +1559,6 @@ k_split(const SplitJob * __restrict__ jobs, const MaskRef * __restrict__ refs, u
   // growth (X:905-963): every blob dilates inside the mask at once; a free pixel reached by several blobs in
   // the same step goes to the lowest index.  A connected mask of P pixels fills in at most P steps; if free
   // pixels remain after that no seed can reach them (the reference would loop forever).
-  __shared__ int s_pixels;
   if (threadIdx.x == 0)
     s_pixels = 0;
   __syncthreads();
@@ -1486,7 +1652,8 @@ launch_split(Launch & L, const SplitJob * jobs, int njobs, const MaskRef * refs,
   L.pre("k_split");
   // one word per thread where the shapes allow it; fewer warps make the per-step barrier cheaper
   const int threads = std::max(128, std::min(SPLIT_THREADS, (maxWords + 31) / 32 * 32));
-  k_split<<<njobs, threads, smemBytes, L.stream>>>(jobs, refs, arena, gscratch, trans, ball, smemBytes / 4, err);
+  static const int fastPath = getenv("MCI_SPLIT_GENERIC") ? 0 : 1; // A/B switch: the generic path for every job
+  k_split<<<njobs, threads, smemBytes, L.stream>>>(jobs, refs, arena, gscratch, trans, ball, smemBytes / 4, fastPath, err);
   L.post("k_split");
 }
 

@@ -336,6 +336,31 @@ def _big_roi_volume(n=1200, dtype=np.uint16):
     return v
 
 
+def _one_to_n_volume(n_blobs, size, dtype=np.uint16):
+    """one big disc on plane 0 against n_blobs small discs on plane 4, all inside the big disc's footprint"""
+    v = np.zeros((5, size, size), dtype)
+    yy, xx = np.mgrid[0:size, 0:size]
+    c = size // 2
+    v[0][(yy - c) ** 2 + (xx - c) ** 2 <= (size * 0.45) ** 2] = 2
+    for k in range(n_blobs):
+        ang = 2 * np.pi * k / n_blobs + 0.3
+        cy, cx = c + size * 0.27 * np.sin(ang), c + size * 0.27 * np.cos(ang)
+        r = size * (0.055 + 0.01 * (k % 3))
+        v[4][(yy - cy) ** 2 + (xx - cx) ** 2 <= r ** 2] = 2
+    return v
+
+
+@pytest.mark.parametrize("algo", ["D", "C", "B"])
+def test_one_to_n_split_for_every_blob_count_and_shape_size(flt, algo):
+    """k_split: the register-resident path is instantiated for up to 2 / 3 / 4 blobs, one or up to four words per
+    thread, cross and ball; more blobs or shapes beyond shared memory take the generic path"""
+    kw = cases.ALGOS[algo]
+    for n_blobs, size in [(2, 64), (3, 64), (4, 64), (5, 64), (6, 96), (2, 300), (3, 340), (4, 300), (2, 40), (1, 64)]:
+        v = _one_to_n_volume(n_blobs, size)
+        out = run_gpu(flt, v, **kw)
+        assert_same(out, O.interpolate(v, threads=os.cpu_count() or 1, **kw), "1-to-%d at %d px, %s" % (n_blobs, size, algo))
+
+
 @pytest.mark.parametrize("algo", ["D", "C"])
 def test_big_regions_take_the_global_scratch_paths(flt, algo):
     kw = cases.ALGOS[algo]

@@ -1090,10 +1090,13 @@ extern "C"
       if (!ctx->axisJobs[axis])
         continue; // no slices perpendicular to this axis in the run
       const size_t nP = (size_t)ctx->dims[axis];
-      CK(cudaMemsetAsync(tables, 0, (3 * nP + 1) * sizeof(int), s));         // count, start, fill
-      CK(cudaMemsetAsync(tables + 3 * nP + 1, 0x7F, 4 * nP * sizeof(int), s)); // box rows {min x, min y, max x, max y}: minima ...
-      // ... and maxima, which k_compose_count raises with atomicMax: they must start below any coordinate
-      CK(cudaMemset2DAsync(tables + 3 * nP + 1 + 2, 4 * sizeof(int), 0x80, 2 * sizeof(int), nP, s));
+      if (!compose_tables_in_one_launch(ctx->emitCap)) // else k_compose_tables initialises them itself
+      {
+        CK(cudaMemsetAsync(tables, 0, (3 * nP + 1) * sizeof(int), s));         // count, start, fill
+        CK(cudaMemsetAsync(tables + 3 * nP + 1, 0x7F, 4 * nP * sizeof(int), s)); // box rows {min x, min y, max x, max y}: minima ...
+        // ... and maxima, which k_compose_count raises with atomicMax: they must start below any coordinate
+        CK(cudaMemset2DAsync(tables + 3 * nP + 1 + 2, 4 * sizeof(int), 0x80, 2 * sizeof(int), nP, s));
+      }
       launch_compose(ctx->L, ctx->ptype, axis, recs, nrecsDev, ctx->emitCap, (const uint32_t *)ctx->dArena.p + ctx->emitBase, tables,
                      ctx->dIn, ctx->dOut, ctx->dims);
     }

@@ -22,6 +22,7 @@
 // (work items there are fixed-size word ranges of a node's bit rows, so the whole GPU works on a level no matter how
 // few nodes it has or how unequal they are; the price is 18 dependent launches for a gap of 8).
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 #include "mci_kernels.cuh"
 #include "mci_launch.h"
@@ -2542,6 +2543,81 @@ k_compose_fill(const EmitRec * __restrict__ recs, const int * __restrict__ nrecs
   }
 }
 
+// The three table kernels and the three memsets before them in ONE single-CTA launch, for runs with few mid slices (a
+// C3 step has 938): initialise, count + boxes, prefix, record lists, with CTA barriers in between.  The counters are
+// read back with L2 loads (the atomics that raised them were performed at L2).
+#define COMPOSE_SMALL_CAP 8192
+__global__ void __launch_bounds__(1024)
+k_compose_tables(const EmitRec * __restrict__ recs, const int * __restrict__ nrecsDev, int cap, ComposeTables t, int VZ, int axis)
+{
+  pdl_wait();
+  __shared__ int warpSum[32];
+  __shared__ int carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int z = tid; z < VZ; z += 1024)
+  {
+    t.count[z] = 0;
+    t.fill[z] = 0;
+    t.box[4 * z + 0] = 0x7F7F7F7F;
+    t.box[4 * z + 1] = 0x7F7F7F7F;
+    t.box[4 * z + 2] = (int)0x80808080;
+    t.box[4 * z + 3] = (int)0x80808080;
+  }
+  if (tid == 0)
+    carry = 0;
+  __syncthreads();
+  const int n = min(*nrecsDev, cap);
+  for (int e = tid; e < n; e += 1024)
+  {
+    const EmitRec r = recs[e];
+    if (r.axis != axis || (unsigned)r.mid >= (unsigned)VZ)
+      continue;
+    atomicAdd(&t.count[r.mid], 1);
+    atomicMin(&t.box[4 * r.mid + 0], r.M.x0);
+    atomicMin(&t.box[4 * r.mid + 1], r.M.y0);
+    atomicMax(&t.box[4 * r.mid + 2], r.M.x0 + r.M.w - 1);
+    atomicMax(&t.box[4 * r.mid + 3], r.M.y0 + r.M.h - 1);
+  }
+  __threadfence();
+  __syncthreads();
+  for (int base = 0; base < VZ; base += 1024)
+  {
+    const int z = base + tid;
+    const int c = z < VZ ? __ldcg(&t.count[z]) : 0;
+    int v = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      const int u = __shfl_up_sync(0xFFFFFFFFu, v, o);
+      if (lane >= o)
+        v += u;
+    }
+    if (lane == 31)
+      warpSum[warp] = v;
+    __syncthreads();
+    int off = carry;
+    for (int k = 0; k < warp; ++k)
+      off += warpSum[k];
+    if (z < VZ)
+      t.start[z] = off + v - c;
+    __syncthreads();
+    if (tid == 1023)
+      carry = off + v;
+    __syncthreads();
+  }
+  if (tid == 0)
+    t.start[VZ] = carry;
+  __threadfence();
+  __syncthreads();
+  for (int e = tid; e < n; e += 1024)
+  {
+    const EmitRec r = recs[e];
+    if (r.axis != axis || (unsigned)r.mid >= (unsigned)VZ)
+      continue;
+    t.recs[__ldcg(&t.start[r.mid]) + atomicAdd(&t.fill[r.mid], 1)] = e;
+  }
+}
+
 #define COMPOSE_ROWS 8  // rows of a plane per CTA (one warp each)
 #define COMPOSE_LIST 64 // shapes crossing a row kept per pass (more: further passes over the row)
 struct ComposeEntry
@@ -2667,6 +2743,14 @@ k_compose(const EmitRec * __restrict__ recs, const uint32_t * __restrict__ words
   }
 }
 
+// few records: k_compose_tables initialises the tables itself (the caller then skips its memsets)
+bool
+compose_tables_in_one_launch(int cap)
+{
+  static const bool off = std::getenv("MCI_COMPOSE_3K") != nullptr; // A/B switch: the three table kernels
+  return !off && cap <= COMPOSE_SMALL_CAP;
+}
+
 void
 launch_compose(Launch & L, int ptype, int axis, const EmitRec * recs, const int * nrecsDev, int cap, const uint32_t * words, int * tables,
                const void * in, void * out, const long long dims[3])
@@ -2682,6 +2766,14 @@ launch_compose(Launch & L, int ptype, int axis, const EmitRec * recs, const int 
   t.box = t.fill + nPlanes;
   t.recs = t.box + 4 * nPlanes;
   const int g = std::max(1, std::min((cap + 255) / 256, L.sms * 4));
+  if (compose_tables_in_one_launch(cap))
+  {
+    L.pre("k_compose_tables");
+    launch_pdl(k_compose_tables, 1, 1024, 0, L.stream, recs, nrecsDev, cap, t, nPlanes, axis);
+    L.post("k_compose_tables");
+  }
+  else
+  {
   L.pre("k_compose_count");
   launch_pdl(k_compose_count, g, 256, 0, L.stream, recs, nrecsDev, cap, t, nPlanes, axis);
   L.post("k_compose_count");
@@ -2691,6 +2783,7 @@ launch_compose(Launch & L, int ptype, int axis, const EmitRec * recs, const int 
   L.pre("k_compose_fill");
   launch_pdl(k_compose_fill, g, 256, 0, L.stream, recs, nrecsDev, cap, t, nPlanes, axis);
   L.post("k_compose_fill");
+  }
   const dim3 grid((unsigned)((nRows + COMPOSE_ROWS - 1) / COMPOSE_ROWS), (unsigned)nPlanes);
   L.pre("k_compose");
   switch (ptype)

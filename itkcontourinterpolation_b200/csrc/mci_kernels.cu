@@ -416,9 +416,19 @@ k_compact_labels(const int * __restrict__ bbox, int nl, const uint32_t * __restr
   }
   labels[slot] = L;
   const uint32_t * w = sliceBits + (size_t)li * wordsPerLabel;
-  for (int k = 0; k < wordsPerLabel; ++k)
+  // few labels are present, so this loop is a handful of threads walking their bitmaps alone: eight words are
+  // loaded before any is looked at (a thread's time is its chain of dependent global loads)
+  for (int k0 = 0; k0 < wordsPerLabel; k0 += 8)
   {
-    uint32_t bits = w[k];
+    uint32_t batch[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      batch[j] = k0 + j < wordsPerLabel ? w[k0 + j] : 0u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+    {
+    const int k = k0 + j;
+    uint32_t bits = batch[j];
     if (!bits)
       continue;
     int axis = k >= wo2 ? 2 : (k >= wo1 ? 1 : 0);
@@ -437,6 +447,7 @@ k_compact_labels(const int * __restrict__ bbox, int nl, const uint32_t * __restr
         slices[pos] = s;
       }
       ++pos;
+    }
     }
   }
 }

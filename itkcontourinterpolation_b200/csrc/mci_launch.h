@@ -190,6 +190,7 @@ struct TreeParams
 void launch_dt_tree(Launch & L, int ptype, const TreeParams & P, int nRootsMax, int grid, int threads);
 // volume writes of all mid slices perpendicular to `axis` (1 or 2), no atomics (tables: 7 * dims[axis] + 1 + cap ints,
 // prepared by the caller: counts / starts / fills zero, box minima INT_MAX-like, maxima INT_MIN-like)
+bool compose_tables_in_one_launch(int cap); // few mid slices: one table kernel that also initialises the tables
 void launch_compose(Launch & L, int ptype, int axis, const EmitRec * recs, const int * nrecsDev, int cap, const uint32_t * words,
                     int * tables, const void * in, void * out, const long long dims[3]);
 

@@ -5,7 +5,7 @@ algorithm with single calls deviating).  Every variant is run through the litera
 (tests/literal_mci.py) on SevenLabels, written through ITK's NRRD byte layout and hashed; SevenLabels_B must stay
 reproduced by a variant for it to count as a candidate (printed separately).
 
-Usage: python tools/variant_search.py C|T [nproc]
+Usage: python tools/variant_search.py C|T [nproc [knob=value]]
 """
 import itertools
 import multiprocessing as mp
@@ -56,6 +56,11 @@ class Variant(L.Literal):
         super().__init__(vol, **kw)
         self.k = k
         self.extrap = k.get("extrap", True)
+
+    def bounding_box(self, image):
+        if not image.a.any():  # a variant translation moved the shape out of the union region
+            return image.region
+        return super().bounding_box(image)
 
     def regioned_cc(self, axis, label, s):
         if self.k.get("cc", "se") == "se":
@@ -261,6 +266,9 @@ def main():
     mode = sys.argv[1].upper()
     nproc = int(sys.argv[2]) if len(sys.argv) > 2 else os.cpu_count()
     spaces = (STRUCT, DT) if mode == "T" else (STRUCT, DIL)
+    if len(sys.argv) > 3:  # restrict one knob: name=value
+        name, val = sys.argv[3].split("=")
+        spaces = tuple({k: ([x for x in v if str(x) == val] if k == name else v) for k, v in sp.items()} for sp in spaces)
     # sanity: the default reading must give today's oracle output
     k0, h0 = run_one((mode, {}))
     print("default reading:", h0[:16], "target:", TARGETS[mode][:16], flush=True)

@@ -266,7 +266,9 @@ int mci_filter_run_batch(mci_ctx * const * ctxs, int32_t n_ctx, const mci_filter
  * GetLabeledSliceIndices (H:209-224) */
 int mci_filter_detect(mci_ctx * ctx, const mci_filter_options * opt, int64_t * n_triplets);
 int mci_filter_get_labeled_slices(mci_ctx * ctx, int64_t * triplets /* [3*n] */);
-/* the pair bookkeeping of one segment (X:1274-1446) as a pure host function: needs no device (host-logic tests) */
+/* the pair bookkeeping of one segment (X:1274-1446) as a pure host function: needs no device (host-logic tests).
+ * use_extrapolation: bit 0 = the option; bit 1 set = take the literal std::set algebra even for pair sets the scheduler
+ * handles on its allocation-free path (extrapolations and 1-to-1 pairs only), so that tests can compare the two */
 int mci_filter_schedule_pairs(const mci_pair * pairs, int32_t n_pairs, int use_extrapolation, mci_job * jobs, int32_t cap_jobs,
                               int32_t * n_jobs, int32_t * b_ids, int32_t cap_b_ids, int32_t * n_b_ids);
 /* drops the scheduler's per-context state (called by mci_destroy) */

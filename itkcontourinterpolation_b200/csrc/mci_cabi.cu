@@ -1125,7 +1125,13 @@ extern "C"
     std::vector<AlignJob> aligns(njobs);
     std::vector<SplitJob> splits;
     std::vector<RootJob> roots(njobs);
-    std::map<std::pair<int, int>, MaskRef> compMasks;
+    // mask of a component, made at its first use: looked up by the component's dense index (compBase[slice] + id - 1),
+    // not through a map -- this loop runs on the host between two device phases of every step
+    std::vector<int> compMaskAt(ctx->hStats.size(), -1);
+    std::vector<MaskRef> compMaskStore;
+    refs.reserve(size_t(njobs) * 3 + 16);
+    extracts.reserve(size_t(njobs) * 4 + 16);
+    compMaskStore.reserve(size_t(njobs) * 2 + 16);
     u64 arenaWords = 0, scratchWords = 0;
     int maxSplitWords = 0;
     int nSlots = 0; // axis-0 slot table entries
@@ -1140,10 +1146,9 @@ extern "C"
 
     auto statOf = [&](int slice, int id) -> const CompStat & { return ctx->hStats[ctx->compBase[slice] + id - 1]; };
     auto compMask = [&](int slice, int id) -> MaskRef {
-      auto key = std::make_pair(slice, id);
-      auto it = compMasks.find(key);
-      if (it != compMasks.end())
-        return it->second;
+      int & at = compMaskAt[size_t(ctx->compBase[slice] + id - 1)];
+      if (at >= 0)
+        return compMaskStore[size_t(at)];
       const CompStat & c = statOf(slice, id);
       MaskRef m;
       m.x0 = c.minU;
@@ -1165,7 +1170,8 @@ extern "C"
         e.m = m;
         extracts.push_back(e);
       }
-      compMasks[key] = m;
+      at = (int)compMaskStore.size();
+      compMaskStore.push_back(m);
       return m;
     };
 

@@ -4,6 +4,7 @@
 // InterpolateAlong's segment list (X:1449-1521) and InterpolateBetweenTwo's pair bookkeeping
 // (X:1250-1446), where X = reference include/itkMorphologicalContourInterpolator.hxx.  It calls
 // CUDA only through the phase-level C ABI; it never touches a voxel itself.
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -215,6 +216,72 @@ schedule_segment(const Segment & seg, const std::set<IdPair> & uncleanPairs, boo
     }
     pairs.erase(p++);
   }
+}
+
+// The same bookkeeping for the segments that need none of the set algebra -- after the unwanted pairs are dropped,
+// every component takes part in at most one pair (extrapolations and 1-to-1 correspondences only; all but a few
+// segments of a real volume) -- on the sorted pair list itself, without a std::set / std::map node allocation per
+// pair.  q[0..n) sorted, distinct.  Emits exactly what schedule_segment emits (extrapolations in set order
+// X:1280-1304, then the 1-to-1 jobs in set order X:1315-1333) or returns false without emitting anything.
+bool
+schedule_simple(const Segment & seg, const IdPair * q, int n, bool useExtrapolation, std::vector<mci_job> & jobs,
+                std::vector<int32_t> & bIds)
+{
+  if (n > 32)
+    return false;
+  unsigned keep = 0; // bit k: q[k] survives the set difference of X:1274-1278
+  for (int k = 0; k < n; ++k)
+  {
+    bool unwanted = false;
+    if (q[k].first == 0 || q[k].second == 0)
+      for (int m = 0; m < n && !unwanted; ++m)
+        if (q[m].first != 0 && q[m].second != 0 && (q[k].first == 0 ? q[m].second == q[k].second : q[m].first == q[k].first))
+          unwanted = true;
+    if (!unwanted)
+      keep |= 1u << k;
+  }
+  for (int k = 0; k < n; ++k)
+    if (((keep >> k) & 1u) && q[k].first != 0 && q[k].second != 0)
+      for (int m = k + 1; m < n; ++m)
+        if (q[m].first != 0 && q[m].second != 0 && (q[m].first == q[k].first || q[m].second == q[k].second))
+          return false; // 1-to-N, M-to-1 or M-to-N: the literal path
+  auto emit = [&](int kind, bool swapped, int aId, int nB, int bId) {
+    mci_job jb;
+    jb.kind = kind;
+    jb.slice_a = swapped ? seg.sj : seg.si;
+    jb.a_id = aId;
+    jb.slice_b = swapped ? seg.si : seg.sj;
+    jb.n_b = nB;
+    jb.b_ids_offset = (int)bIds.size();
+    jb.pos_a = swapped ? seg.j : seg.i;
+    jb.pos_b = swapped ? seg.i : seg.j;
+    if (nB)
+      bIds.push_back(bId);
+    jobs.push_back(jb);
+  };
+  if (useExtrapolation)
+    for (int k = 0; k < n; ++k)
+      if ((keep >> k) & 1u)
+      {
+        if (q[k].second == 0)
+          emit(MCI_JOB_EXTRAPOLATE, false, q[k].first, 0, 0);
+        else if (q[k].first == 0)
+          emit(MCI_JOB_EXTRAPOLATE, true, q[k].second, 0, 0);
+      }
+  for (int k = 0; k < n; ++k)
+    if (((keep >> k) & 1u) && q[k].first != 0 && q[k].second != 0)
+      emit(MCI_JOB_ONE_TO_ONE, false, q[k].first, 1, q[k].second);
+  return true;
+}
+
+// one segment's sorted, distinct pairs -> jobs
+void
+schedule_pairs_of_segment(const Segment & seg, const IdPair * q, int n, bool useExtrapolation, std::vector<mci_job> & jobs,
+                          std::vector<int32_t> & bIds)
+{
+  if (schedule_simple(seg, q, n, useExtrapolation, jobs, bIds))
+    return;
+  schedule_segment(seg, std::set<IdPair>(q, q + n), useExtrapolation, jobs, bIds);
 }
 
 int
@@ -440,19 +507,35 @@ run_from_state(mci_ctx * ctx, const mci_filter_options * opt, const int64_t dims
   if (rc)
     return rc;
   stats->n_pairs = nPairs;
-  std::vector<std::set<IdPair>> perSegment(segments.size());
+  // the pairs of each segment as a sorted, duplicate-free range (std::set iteration order) of one array
+  std::vector<int> segStart(segments.size() + 1, 0);
   for (const mci_pair & q : pairs)
-    perSegment[(size_t)q.segment].insert(IdPair(q.i_id, q.j_id));
+    ++segStart[(size_t)q.segment + 1];
+  for (size_t k = 0; k < segments.size(); ++k)
+    segStart[k + 1] += segStart[k];
+  std::vector<IdPair> sorted(pairs.size());
+  {
+    std::vector<int> fill(segStart.begin(), segStart.end() - 1);
+    for (const mci_pair & q : pairs)
+      sorted[(size_t)fill[(size_t)q.segment]++] = IdPair(q.i_id, q.j_id);
+  }
   double t3 = now_ms();
   stats->ms_pairs = t3 - t2;
 
   // pair bookkeeping -> jobs
   std::vector<mci_job> jobs;
   std::vector<int32_t> bIds;
+  jobs.reserve(pairs.size());
+  bIds.reserve(pairs.size());
   {
     NvtxRange r("mci.schedule_pairs");
     for (size_t k = 0; k < segments.size(); ++k)
-      schedule_segment(segments[k], perSegment[k], opt->use_extrapolation != 0, jobs, bIds);
+    {
+      IdPair * b = sorted.data() + segStart[k], * e = sorted.data() + segStart[k + 1];
+      std::sort(b, e);
+      e = std::unique(b, e);
+      schedule_pairs_of_segment(segments[k], b, (int)(e - b), opt->use_extrapolation != 0, jobs, bIds);
+    }
   }
   stats->n_jobs = (int64_t)jobs.size();
 
@@ -694,12 +777,17 @@ extern "C"
     seg.j = 1;
     seg.si = 0;
     seg.sj = 1;
-    std::set<IdPair> unclean;
+    std::vector<IdPair> unclean;
     for (int32_t k = 0; k < n_pairs; ++k)
-      unclean.insert(IdPair(pairs[k].i_id, pairs[k].j_id));
+      unclean.push_back(IdPair(pairs[k].i_id, pairs[k].j_id));
+    std::sort(unclean.begin(), unclean.end());
+    unclean.erase(std::unique(unclean.begin(), unclean.end()), unclean.end());
     std::vector<mci_job> js;
     std::vector<int32_t> ids;
-    schedule_segment(seg, unclean, use_extrapolation != 0, js, ids);
+    if (use_extrapolation & 2) // bit 1 (tests): the literal set algebra for every pair set, simple or not
+      schedule_segment(seg, std::set<IdPair>(unclean.begin(), unclean.end()), (use_extrapolation & 1) != 0, js, ids);
+    else
+      schedule_pairs_of_segment(seg, unclean.data(), (int)unclean.size(), (use_extrapolation & 1) != 0, js, ids);
     *n_jobs = (int32_t)js.size();
     *n_b_ids = (int32_t)ids.size();
     if ((int32_t)js.size() > cap_jobs || (int32_t)ids.size() > cap_b_ids)

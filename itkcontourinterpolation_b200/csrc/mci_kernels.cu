@@ -416,8 +416,23 @@ k_compact_labels(const int * __restrict__ bbox, int nl, const uint32_t * __restr
   }
   labels[slot] = L;
   const uint32_t * w = sliceBits + (size_t)li * wordsPerLabel;
-  // few labels are present, so this loop is a handful of threads walking their bitmaps alone: eight words are
-  // loaded before any is looked at (a thread's time is its chain of dependent global loads)
+  // few labels are present, so this is a handful of threads walking their bitmaps alone, and a thread's time is its
+  // chain of dependent global operations: eight words are loaded before any is looked at, and the label's slots in
+  // the slice list are claimed with ONE atomic (first pass: count; second pass: write)
+  int total = 0;
+  for (int k0 = 0; k0 < wordsPerLabel; k0 += 8)
+  {
+    uint32_t batch[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      batch[j] = k0 + j < wordsPerLabel ? w[k0 + j] : 0u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      total += __popc(batch[j]);
+  }
+  if (!total)
+    return;
+  int pos = atomicAdd(&counters[1], total);
   for (int k0 = 0; k0 < wordsPerLabel; k0 += 8)
   {
     uint32_t batch[8];
@@ -427,27 +442,26 @@ k_compact_labels(const int * __restrict__ bbox, int nl, const uint32_t * __restr
 #pragma unroll
     for (int j = 0; j < 8; ++j)
     {
-    const int k = k0 + j;
-    uint32_t bits = batch[j];
-    if (!bits)
-      continue;
-    int axis = k >= wo2 ? 2 : (k >= wo1 ? 1 : 0);
-    int base = (k - (axis == 0 ? 0 : (axis == 1 ? wo1 : wo2))) * 32;
-    int pos = atomicAdd(&counters[1], __popc(bits));
-    while (bits)
-    {
-      int b = __ffs(bits) - 1;
-      bits &= bits - 1;
-      if (pos < capSlices)
+      const int k = k0 + j;
+      uint32_t bits = batch[j];
+      if (!bits)
+        continue;
+      const int axis = k >= wo2 ? 2 : (k >= wo1 ? 1 : 0);
+      const int base = (k - (axis == 0 ? 0 : (axis == 1 ? wo1 : wo2))) * 32;
+      while (bits)
       {
-        mci_labeled_slice s;
-        s.axis = axis;
-        s.slice = base + b;
-        s.label = label;
-        slices[pos] = s;
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        if (pos < capSlices)
+        {
+          mci_labeled_slice s;
+          s.axis = axis;
+          s.slice = base + b;
+          s.label = label;
+          slices[pos] = s;
+        }
+        ++pos;
       }
-      ++pos;
-    }
     }
   }
 }

@@ -142,3 +142,27 @@ def test_quirk_second_element_scan():
     got = schedule_cpp(pairs)
     assert got == schedule_py(pairs)
     assert len(got) >= 2
+
+
+def test_allocation_free_path_equals_the_literal_set_algebra():
+    """The scheduler handles pair sets that hold only extrapolations and 1-to-1 correspondences without the std::set /
+    std::map algebra; bit 1 of the hook's flag forces the literal path, and the two must emit the same jobs in the same
+    order on every pair set (simple or not)."""
+    rng = random.Random(20260421)
+    simple = 0
+    for trial in range(3000):
+        n_i, n_j = rng.randint(1, 5), rng.randint(1, 5)
+        pairs = set()
+        for _ in range(rng.randint(1, 8)):
+            a, b = rng.randint(0, n_i), rng.randint(0, n_j)
+            if a or b:
+                pairs.add((a, b))
+        pairs = sorted(pairs)
+        rng.shuffle(pairs)
+        for extrap in (0, 1):
+            fast = schedule_cpp(pairs, extrap)
+            literal = schedule_cpp(pairs, extrap | 2)
+            assert fast == literal == schedule_py(pairs, bool(extrap)), (pairs, extrap)
+        if all(k != L.JOB_ONE_TO_N for k, *_ in fast):
+            simple += 1
+    assert simple > 300  # the family the fast path exists for is well represented

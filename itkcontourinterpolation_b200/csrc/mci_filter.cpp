@@ -411,11 +411,12 @@ run_from_state(mci_ctx * ctx, const mci_filter_options * opt, const int64_t dims
           continue;
         region = bb->second;
       }
-      std::map<int, int> sliceIndex; // position -> batch index (created on demand)
+      // position -> batch index, created on demand.  Positions are visited in ascending order and a slice is shared
+      // only by two consecutive segments (j of one, i of the next), so remembering the last one created is enough
+      int lastPos = -1, lastIdx = -1;
       auto sliceOf = [&](int pos) {
-        auto f = sliceIndex.find(pos);
-        if (f != sliceIndex.end())
-          return f->second;
+        if (pos == lastPos)
+          return lastIdx;
         mci_slice_desc d;
         d.axis = axis;
         d.slice = pos;
@@ -425,8 +426,9 @@ run_from_state(mci_ctx * ctx, const mci_filter_options * opt, const int64_t dims
         d.w = region.size[d0];
         d.h = region.size[d1];
         sliceDescs.push_back(d);
-        sliceIndex[pos] = (int)sliceDescs.size() - 1;
-        return (int)sliceDescs.size() - 1;
+        lastPos = pos;
+        lastIdx = (int)sliceDescs.size() - 1;
+        return lastIdx;
       };
       std::vector<int> positions(kv.second.begin(), kv.second.end());
       for (int pos : positions)

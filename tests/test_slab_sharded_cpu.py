@@ -119,3 +119,32 @@ def test_merge_detection_unions_boxes_and_slice_sets():
     boxes, slices = merge_detection([a, b])
     assert boxes.tolist() == [[3, 0, 0, 6, 0, 0, 6], [7, 1, 3, 0, 5, 14, 6]]  # label, lo xyz, hi xyz
     assert slices.tolist() == [[3, 6], [7, 0], [7, 5]]
+
+
+def test_far_plane_test_agrees_with_the_per_rank_plans():
+    """the resident path with ghost planes plans only its own rank when no rank needs a plane beyond its ghost planes;
+    that shortcut's test must say exactly what planning every rank says, uneven and empty slabs included"""
+    from itkcontourinterpolation_b200.distributed import far_planes_needed, segments_of
+    rng = np.random.default_rng(11)
+    seen = set()
+    for trial in range(400):
+        nz = int(rng.integers(4, 90))
+        rows = set()
+        for lab in range(1, int(rng.integers(2, 7))):
+            step = int(rng.integers(1, 9))
+            for z in (rng.choice(nz, size=int(rng.integers(1, min(nz, 12) + 1)), replace=False) if trial % 2 else range(0, nz, step)):
+                rows.add((lab, int(z)))
+        slices = np.array(sorted(rows), dtype=np.int64).reshape(-1, 2)
+        world = int(rng.integers(1, 7))
+        cuts = sorted(int(c) for c in rng.integers(0, nz + 1, size=world - 1))
+        if trial % 4 == 0:
+            cuts = [c // 8 * 8 for c in cuts]
+        bounds = list(zip([0] + cuts, cuts + [nz]))
+        label = int(rng.integers(0, 3))
+        segs = segments_of(slices, label)
+        halos = [[z for z in (lo - 1, hi) if 0 <= z < nz and hi > lo] for lo, hi in bounds]
+        plans = [plan_slab(slices, lo, hi, label) for lo, hi in bounds]
+        far = any(z not in halos[q] for q in range(len(bounds)) for z in plans[q][2])
+        assert far_planes_needed(segs, bounds) == far, (trial, bounds, slices.tolist(), label)
+        seen.add(far)
+    assert seen == {True, False}

@@ -277,7 +277,7 @@ main(int argc, char * argv[])
     }
     return EXIT_SUCCESS;
   }
-  if (argc >= 3 && endsWith(argv[1], ".nrrd"))
+  if (argc >= 3 && (endsWith(argv[1], ".nrrd") || mci_b200::detail::IsMetaImageName(argv[1])))
   {
     // the reference driver's command line (test/itkMorphologicalContourInterpolationTest.cxx:52-140)
     bool dt = false, ball = true;

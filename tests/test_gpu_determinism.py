@@ -62,9 +62,10 @@ def test_concurrent_contexts_do_not_disturb_each_other():
 
 
 @pytest.mark.parametrize("env", [{"MCI_DT_LEVELS": "1"}, {"MCI_NO_COMPOSE": "1"}, {"MCI_TREE_THREADS": "512"}, {"MCI_TREE_THREADS": "1024"},
-                                 {"MCI_SPLIT_GENERIC": "1"}])
+                                 {"MCI_SPLIT_GENERIC": "1"}, {"MCI_COMPOSE_3K": "1"}])
 def test_alternative_code_paths_kept_for_ab_runs_still_match(env):
-    """The round-1 level-synchronous recursion, in-node volume writes and both widths of k_dt_tree stay selectable by
+    """The round-1 level-synchronous recursion, in-node volume writes, both widths of k_dt_tree, the generic k_split and
+    the three-kernel compose tables stay selectable by
     environment variable (DESIGN.md section 3 quotes A/B numbers taken with them): they must keep giving the same bits.
     The variables are read once per process, hence the subprocess."""
     import os

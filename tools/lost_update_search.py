@@ -3,7 +3,7 @@ update": before the reference serialised its volume writes (the mutex of X:740-7
 `if (out < label) out = label` (X:754-763) to the same voxel could leave the LOWER label.  Every voxel that several
 labels cover may have kept any lower covering label; all combinations of K such voxels are written through ITK's NRRD
 byte layout and hashed.  Usage: python tools/lost_update_search.py C|T K
-Result (round 2): no hit for K <= 4 (C, 21.4 M volumes) and K <= 7 (T)."""
+Result (round 2): no hit for K <= 5 (C, 632 M volumes) and K <= 7 (T, 62 M)."""
 import sys, itertools, multiprocessing as mp
 sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests'); sys.path.insert(0,'/root/repo/tools')
 import numpy as np
